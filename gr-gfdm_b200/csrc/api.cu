@@ -1,0 +1,1339 @@
+// api.cu -- the C ABI of include/gfdm_b200.h on top of the CUDA kernels.
+//
+// Host-side mirror of gr-gfdm's kernel classes: constructor validation with the
+// reference's conditions and messages, tap renormalisation, precomputed tables,
+// per-handle stream + scratch, host<->device staging for HOST pointers.  There is
+// no CPU compute path in this file: every data-path entry launches CUDA kernels
+// and fails with GFDM_ERR_CUDA when no device is usable.
+#include "../../include/gfdm_b200.h"
+
+#include "engine.h"
+#include "fused.h"
+
+#include <algorithm>
+#include <cmath>
+#include <complex>
+#include <cstring>
+#include <memory>
+#include <sstream>
+
+using namespace gfdm;
+typedef std::complex<float> cf;
+
+static thread_local std::string g_err;
+static int g_device = 0;
+
+static int fail(int code, const std::string& msg)
+{
+    g_err = msg;
+    return code;
+}
+
+#define API_TRY try {
+#define API_CATCH                                                                     \
+    }                                                                                 \
+    catch (const std::invalid_argument& e) { return fail(GFDM_ERR_INVALID_ARGUMENT, e.what()); } \
+    catch (const CudaError& e) { return fail(GFDM_ERR_CUDA, e.what()); }              \
+    catch (const std::exception& e) { return fail(GFDM_ERR_RUNTIME, e.what()); }      \
+    return GFDM_OK;
+
+static const uint32_t HANDLE_MAGIC = 0x47464442u; // "GFDB"
+
+// Common prefix of every handle (gfdm_set_stream / gfdm_sync accept any of them).
+struct HandleBase {
+    uint32_t magic = HANDLE_MAGIC;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    long long launches = 0;
+    const char* last_kernel = "none";
+    DeviceBuf stage_in, stage_in2, stage_out; // HOST-pointer staging
+    DeviceBuf work_a, work_b, work_c;         // pipeline scratch
+
+    void open()
+    {
+        int n = 0;
+        cudaError_t e = cudaGetDeviceCount(&n);
+        if (e != cudaSuccess || n <= 0)
+            throw CudaError(std::string("gfdm_b200: no usable CUDA device (") + cudaGetErrorString(e) +
+                            "); this library has no CPU fallback");
+        device = g_device;
+        GFDM_CUDA_CHECK(cudaSetDevice(device));
+        GFDM_CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        own_stream = true;
+    }
+    void close()
+    {
+        stage_in.release(); stage_in2.release(); stage_out.release();
+        work_a.release(); work_b.release(); work_c.release();
+        if (own_stream && stream) cudaStreamDestroy(stream);
+        stream = nullptr;
+    }
+    void use() { GFDM_CUDA_CHECK(cudaSetDevice(device)); }
+    void sync() { GFDM_CUDA_CHECK(cudaStreamSynchronize(stream)); }
+};
+
+static std::vector<cf> vec(const gfdm_complex* p, int n)
+{
+    return std::vector<cf>(reinterpret_cast<const cf*>(p), reinterpret_cast<const cf*>(p) + (n > 0 ? n : 0));
+}
+static cpx* dev_upload(const std::vector<cf>& v)
+{
+    std::vector<cpx> t(v.size());
+    for (size_t i = 0; i < v.size(); ++i) t[i] = make_float2(v[i].real(), v[i].imag());
+    return upload(t);
+}
+
+// taps <- taps / sqrt(sum|taps|^2 / M)   (lib/modulator_kernel_cc.cc:71-90, lib/receiver_kernel_cc.cc:99-118)
+static std::vector<cf> normalize_taps(const std::vector<cf>& taps, int n_timeslots)
+{
+    cf res(0.f, 0.f);
+    for (const cf& t : taps) res += t * std::conj(t);
+    const cf sf = cf(1. / std::sqrt(std::abs(res) / n_timeslots), 0.0f);
+    std::vector<cf> out(taps.size());
+    for (size_t i = 0; i < taps.size(); ++i)
+        out[i] = cf(taps[i].real() * sf.real() - taps[i].imag() * sf.imag(),
+                    taps[i].real() * sf.imag() + taps[i].imag() * sf.real());
+    return out;
+}
+
+static void check_taps(size_t n_taps, int M, int L)
+{
+    if ((int)n_taps != M * L) {
+        std::stringstream s;
+        s << "number of frequency taps(" << n_taps << ") MUST be equal to n_timeslots(" << M << ") * overlap(" << L
+          << ") = " << M * L << "!";
+        throw std::invalid_argument(s.str());
+    }
+}
+
+// Run `body(d_out, d_in..., n)` either directly on device pointers or through staging.
+// in_sizes / out_size are per-frame element counts (cpx unless noted).
+struct Staging {
+    HandleBase* h;
+    int mem;
+    explicit Staging(HandleBase* hb, int m) : h(hb), mem(m)
+    {
+        if (m != GFDM_MEM_HOST && m != GFDM_MEM_DEVICE) throw std::invalid_argument("mem MUST be GFDM_MEM_HOST or GFDM_MEM_DEVICE");
+    }
+    const cpx* in(const gfdm_complex* p, size_t elems, DeviceBuf& buf)
+    {
+        if (!p) return nullptr;
+        if (mem == GFDM_MEM_DEVICE) return reinterpret_cast<const cpx*>(p);
+        buf.ensure(elems * sizeof(cpx));
+        GFDM_CUDA_CHECK(cudaMemcpyAsync(buf.p, p, elems * sizeof(cpx), cudaMemcpyHostToDevice, h->stream));
+        return buf.as<cpx>();
+    }
+    cpx* out(gfdm_complex* p, size_t elems, DeviceBuf& buf)
+    {
+        if (mem == GFDM_MEM_DEVICE) return reinterpret_cast<cpx*>(p);
+        buf.ensure(elems * sizeof(cpx));
+        return buf.as<cpx>();
+    }
+    void finish(gfdm_complex* p, size_t elems, DeviceBuf& buf)
+    {
+        if (mem == GFDM_MEM_DEVICE) return;
+        GFDM_CUDA_CHECK(cudaMemcpyAsync(p, buf.p, elems * sizeof(cpx), cudaMemcpyDeviceToHost, h->stream));
+        h->sync();
+    }
+};
+
+// frames per staging chunk for HOST batches (bounds device staging memory)
+static size_t chunk_frames(size_t bytes_per_frame, size_t n)
+{
+    const size_t budget = (size_t)256 << 20;
+    size_t c = budget / (bytes_per_frame ? bytes_per_frame : 1);
+    if (c < 1) c = 1;
+    return c < n ? c : n;
+}
+
+/* ======================================================================== */
+/* library-wide                                                              */
+extern "C" {
+
+const char* gfdm_last_error(void) { return g_err.c_str(); }
+const char* gfdm_backend(void) { return "cuda-sm_100a"; }
+int gfdm_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+int gfdm_set_device(int device)
+{
+    API_TRY
+    int n = 0;
+    GFDM_CUDA_CHECK(cudaGetDeviceCount(&n));
+    if (device < 0 || device >= n) throw std::invalid_argument("device index out of range");
+    g_device = device;
+    API_CATCH
+}
+static HandleBase* base(void* handle)
+{
+    HandleBase* b = reinterpret_cast<HandleBase*>(handle);
+    if (!b || b->magic != HANDLE_MAGIC) throw std::invalid_argument("not a gfdm_b200 handle");
+    return b;
+}
+int gfdm_set_stream(void* handle, void* cuda_stream)
+{
+    API_TRY
+    HandleBase* b = base(handle);
+    if (b->own_stream && b->stream) cudaStreamDestroy(b->stream);
+    b->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+    b->own_stream = false;
+    API_CATCH
+}
+int gfdm_sync(void* handle)
+{
+    API_TRY
+    HandleBase* b = base(handle);
+    b->use();
+    b->sync();
+    API_CATCH
+}
+long long gfdm_launch_count(void* handle)
+{
+    HandleBase* b = reinterpret_cast<HandleBase*>(handle);
+    return (b && b->magic == HANDLE_MAGIC) ? b->launches : -1;
+}
+const char* gfdm_last_kernel(void* handle)
+{
+    HandleBase* b = reinterpret_cast<HandleBase*>(handle);
+    return (b && b->magic == HANDLE_MAGIC) ? b->last_kernel : "invalid";
+}
+
+int gfdm_calculate_signal_energy(float* energy, const gfdm_complex* in, int n)
+{
+    API_TRY
+    if (n < 0) throw std::invalid_argument("n MUST NOT be negative");
+    HandleBase hb;
+    hb.open();
+    try {
+        hb.stage_in.ensure(sizeof(cpx) * (size_t)(n > 0 ? n : 1));
+        hb.stage_out.ensure(sizeof(float));
+        GFDM_CUDA_CHECK(cudaMemcpyAsync(hb.stage_in.p, in, sizeof(cpx) * (size_t)n, cudaMemcpyHostToDevice, hb.stream));
+        launch_energy(hb.stage_out.as<float>(), hb.stage_in.as<cpx>(), (size_t)n, hb.stream);
+        GFDM_CUDA_CHECK(cudaMemcpyAsync(energy, hb.stage_out.p, sizeof(float), cudaMemcpyDeviceToHost, hb.stream));
+        hb.sync();
+    } catch (...) {
+        hb.close();
+        throw;
+    }
+    hb.close();
+    API_CATCH
+}
+
+/* ---- FFT engine --------------------------------------------------------- */
+struct gfdm_fft : HandleBase {
+    FftPlan plan;
+    bool forward = true;
+};
+int gfdm_fft_create(gfdm_fft** out, int fft_size, int forward)
+{
+    API_TRY
+    if (fft_size < 1) throw std::invalid_argument("fft_size MUST be positive");
+    std::unique_ptr<gfdm_fft> h(new gfdm_fft);
+    h->open();
+    h->plan.init(fft_size);
+    h->forward = forward != 0;
+    *out = h.release();
+    API_CATCH
+}
+void gfdm_fft_destroy(gfdm_fft* h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    h->plan.destroy();
+    h->close();
+    delete h;
+}
+int gfdm_fft_execute_batch(gfdm_fft* h, gfdm_complex* out, const gfdm_complex* in, int n, int mem)
+{
+    API_TRY
+    h->use();
+    if (n < 0) throw std::invalid_argument("n_transforms MUST NOT be negative");
+    Staging st(h, mem);
+    const size_t el = (size_t)n * h->plan.n;
+    const cpx* di = st.in(in, el, h->stage_in);
+    cpx* dout = st.out(out, el, h->stage_out);
+    h->work_a.ensure(el * sizeof(cpx));
+    h->launches += fft_exec(h->plan, dout, di, h->work_a.as<cpx>(), (size_t)n, !h->forward, 1.0f, h->stream);
+    h->last_kernel = "stockham_pass";
+    st.finish(out, el, h->stage_out);
+    API_CATCH
+}
+
+/* ---- modulator_kernel_cc ------------------------------------------------ */
+struct gfdm_modulator : HandleBase {
+    int M = 0, K = 0, L = 0, N = 0;
+    std::vector<cf> taps; // normalised
+    cpx* d_taps = nullptr;
+    FftPlan fft_m, fft_n;
+    FusedModem fused; // fused single-kernel path when (M, K, L) has one
+};
+
+static void modulator_run(gfdm_modulator* h, cpx* out, const cpx* in, size_t frames)
+{
+    if (!frames) return;
+    if (h->fused.available()) {
+        h->launches += h->fused.modulate(out, in, frames, h->stream);
+        h->last_kernel = h->fused.mod_name();
+        return;
+    }
+    const size_t el = frames * (size_t)h->N;
+    h->work_a.ensure(el * sizeof(cpx));
+    h->work_b.ensure(el * sizeof(cpx));
+    cpx* A = h->work_a.as<cpx>();
+    cpx* B = h->work_b.as<cpx>();
+    h->launches += fft_exec(h->fft_m, A, in, B, frames * h->K, false, 1.0f, h->stream); // D_k = FFT_M(d_k)
+    launch_mod_filter(B, A, h->d_taps, h->M, h->K, h->L, frames, h->stream);            // X
+    h->launches += 1;
+    h->launches += fft_exec(h->fft_n, out, B, A, frames, true, (float)(1.0 / h->N), h->stream); // IFFT_N / N
+    h->last_kernel = "generic:fft_m+mod_filter+ifft_n";
+}
+
+int gfdm_modulator_create(gfdm_modulator** out, int M, int K, int L, const gfdm_complex* taps, int n_taps)
+{
+    API_TRY
+    check_taps((size_t)(n_taps > 0 ? n_taps : 0), M, L);
+    if (M < 1 || K < 1 || L < 1) throw std::invalid_argument("timeslots, subcarriers and overlap MUST be positive");
+    std::unique_ptr<gfdm_modulator> h(new gfdm_modulator);
+    h->M = M; h->K = K; h->L = L; h->N = M * K;
+    h->taps = normalize_taps(vec(taps, n_taps), M);
+    h->open();
+    h->d_taps = dev_upload(h->taps);
+    h->fused.init_tx(M, K, L, h->taps);
+    if (!h->fused.available()) {
+        h->fft_m.init(M);
+        h->fft_n.init(h->N);
+    }
+    *out = h.release();
+    API_CATCH
+}
+void gfdm_modulator_destroy(gfdm_modulator* h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->d_taps) cudaFree(h->d_taps);
+    h->fft_m.destroy();
+    h->fft_n.destroy();
+    h->fused.destroy();
+    h->close();
+    delete h;
+}
+int gfdm_modulator_block_size(const gfdm_modulator* h) { return h->N; }
+int gfdm_modulator_filter_taps(const gfdm_modulator* h, gfdm_complex* o)
+{
+    memcpy(o, h->taps.data(), sizeof(cf) * h->taps.size());
+    return GFDM_OK;
+}
+int gfdm_modulator_work_batch(gfdm_modulator* h, gfdm_complex* out, const gfdm_complex* in, int n, int mem)
+{
+    API_TRY
+    h->use();
+    if (n < 0) throw std::invalid_argument("n_frames MUST NOT be negative");
+    Staging st(h, mem);
+    if (mem == GFDM_MEM_DEVICE) {
+        modulator_run(h, reinterpret_cast<cpx*>(out), reinterpret_cast<const cpx*>(in), (size_t)n);
+    } else {
+        const size_t c = chunk_frames(2 * sizeof(cpx) * h->N, (size_t)n);
+        for (size_t f0 = 0; f0 < (size_t)n; f0 += c) {
+            const size_t nf = std::min(c, (size_t)n - f0), el = nf * h->N;
+            const cpx* di = st.in(in + f0 * h->N, el, h->stage_in);
+            cpx* dout = st.out(out, el, h->stage_out);
+            modulator_run(h, dout, di, nf);
+            st.finish(out + f0 * h->N, el, h->stage_out);
+        }
+    }
+    API_CATCH
+}
+int gfdm_modulator_work(gfdm_modulator* h, gfdm_complex* out, const gfdm_complex* in)
+{
+    return gfdm_modulator_work_batch(h, out, in, 1, GFDM_MEM_HOST);
+}
+
+/* ---- receiver_kernel_cc ------------------------------------------------- */
+struct gfdm_receiver : HandleBase {
+    int M = 0, K = 0, L = 0, N = 0;
+    std::vector<cf> taps, ic_taps;
+    cpx* d_taps = nullptr;
+    cpx* d_ic = nullptr;
+    FftPlan fft_m, fft_n;
+    FusedModem fused;
+};
+
+static void receiver_init(gfdm_receiver* h, int M, int K, int L, const std::vector<cf>& taps_in)
+{
+    check_taps(taps_in.size(), M, L);
+    if (L < 2) throw std::invalid_argument("overlap MUST be greater or equal 2");
+    if (M < 1 || K < 1) throw std::invalid_argument("timeslots and subcarriers MUST be positive");
+    h->M = M; h->K = K; h->L = L; h->N = M * K;
+    h->taps = normalize_taps(taps_in, M);
+    h->ic_taps.resize(M);
+    for (int m = 0; m < M; ++m) { // lib/receiver_kernel_cc.cc:56-63
+        const cf a = h->taps[m], b = h->taps[M * (L - 1) + m];
+        h->ic_taps[m] = cf(a.real() * b.real() - a.imag() * b.imag(), a.real() * b.imag() + a.imag() * b.real());
+    }
+    h->open();
+    h->d_taps = dev_upload(h->taps);
+    h->d_ic = dev_upload(h->ic_taps);
+    h->fused.init_rx(M, K, L, h->taps, h->ic_taps);
+    h->fft_m.init(M);
+    if (!h->fused.available()) h->fft_n.init(h->N);
+}
+static void receiver_free(gfdm_receiver* h)
+{
+    cudaSetDevice(h->device);
+    if (h->d_taps) cudaFree(h->d_taps);
+    if (h->d_ic) cudaFree(h->d_ic);
+    h->fft_m.destroy();
+    h->fft_n.destroy();
+    h->fused.destroy();
+    h->close();
+}
+
+// fft_filter_downsample / fft_equalize_filter_downsample (:301-320) -> R
+static void receiver_fd(gfdm_receiver* h, cpx* R, const cpx* in, const cpx* eq, size_t frames)
+{
+    if (!frames) return;
+    if (h->fused.available()) {
+        h->launches += h->fused.demodulate(nullptr, R, in, eq, frames, h->stream);
+        h->last_kernel = h->fused.rx_name();
+        return;
+    }
+    const size_t el = frames * (size_t)h->N;
+    h->work_a.ensure(el * sizeof(cpx));
+    h->work_b.ensure(el * sizeof(cpx));
+    cpx* A = h->work_a.as<cpx>();
+    cpx* B = h->work_b.as<cpx>();
+    h->launches += fft_exec(h->fft_n, A, in, B, frames, false, 1.0f, h->stream); // Y = FFT_N(in)
+    if (eq) {
+        launch_eq_divide(A, A, eq, el, h->stream);
+        h->launches += 1;
+    }
+    launch_rx_filter(R, A, h->d_taps, h->M, h->K, h->L, frames, h->stream);
+    h->launches += 1;
+    h->last_kernel = "generic:fft_n+rx_filter";
+}
+// transform_subcarriers_to_td (:211-225); out != in
+static void receiver_td(gfdm_receiver* h, cpx* out, const cpx* R, size_t frames)
+{
+    if (!frames) return;
+    const size_t el = frames * (size_t)h->N;
+    h->work_c.ensure(el * sizeof(cpx));
+    h->launches += fft_exec(h->fft_m, out, R, h->work_c.as<cpx>(), frames * h->K, true, (float)(1.0 / h->M), h->stream);
+}
+// generic_work[_equalize] (:322-334)
+static void receiver_run(gfdm_receiver* h, cpx* out, const cpx* in, const cpx* eq, size_t frames)
+{
+    if (!frames) return;
+    if (h->fused.available()) {
+        h->launches += h->fused.demodulate(out, nullptr, in, eq, frames, h->stream);
+        h->last_kernel = h->fused.rx_name();
+        return;
+    }
+    const size_t el = frames * (size_t)h->N;
+    h->work_c.ensure(el * sizeof(cpx));
+    cpx* R = h->work_c.as<cpx>();
+    receiver_fd(h, R, in, eq, frames); // uses work_a / work_b
+    // M-point IFFTs: scratch = work_a (free again after receiver_fd)
+    h->launches += fft_exec(h->fft_m, out, R, h->work_a.as<cpx>(), frames * h->K, true, (float)(1.0 / h->M), h->stream);
+    h->last_kernel = "generic:fft_n+rx_filter+ifft_m";
+}
+// cancel_sc_interference (:274-299); out may not alias inputs
+static void receiver_cancel(gfdm_receiver* h, cpx* out, const cpx* td, const cpx* fd, size_t frames)
+{
+    if (!frames) return;
+    const size_t el = frames * (size_t)h->N;
+    h->work_a.ensure(el * sizeof(cpx));
+    h->work_b.ensure(el * sizeof(cpx));
+    cpx* A = h->work_a.as<cpx>();
+    cpx* B = h->work_b.as<cpx>();
+    launch_neighbor_sum(A, td, h->M, h->K, frames, h->stream);
+    h->launches += 1;
+    h->launches += fft_exec(h->fft_m, B, A, out, frames * h->K, false, 1.0f, h->stream); // out as scratch
+    launch_ic_subtract(out, fd, B, h->d_ic, h->M, h->K, frames, h->stream);
+    h->launches += 1;
+    h->last_kernel = "generic:neighbor_sum+fft_m+ic_subtract";
+}
+
+int gfdm_receiver_create(gfdm_receiver** out, int M, int K, int L, const gfdm_complex* taps, int n_taps)
+{
+    API_TRY
+    std::unique_ptr<gfdm_receiver> h(new gfdm_receiver);
+    receiver_init(h.get(), M, K, L, vec(taps, n_taps));
+    *out = h.release();
+    API_CATCH
+}
+void gfdm_receiver_destroy(gfdm_receiver* h)
+{
+    if (!h) return;
+    receiver_free(h);
+    delete h;
+}
+int gfdm_receiver_block_size(const gfdm_receiver* h) { return h->N; }
+int gfdm_receiver_timeslots(const gfdm_receiver* h) { return h->M; }
+int gfdm_receiver_subcarriers(const gfdm_receiver* h) { return h->K; }
+int gfdm_receiver_overlap(const gfdm_receiver* h) { return h->L; }
+int gfdm_receiver_filter_taps(const gfdm_receiver* h, gfdm_complex* o)
+{
+    memcpy(o, h->taps.data(), sizeof(cf) * h->taps.size());
+    return GFDM_OK;
+}
+int gfdm_receiver_ic_filter_taps(const gfdm_receiver* h, gfdm_complex* o)
+{
+    memcpy(o, h->ic_taps.data(), sizeof(cf) * h->ic_taps.size());
+    return GFDM_OK;
+}
+
+enum RxOp { RX_WORK, RX_FD, RX_TD, RX_CANCEL };
+static int receiver_batch(gfdm_receiver* h, RxOp op, gfdm_complex* out, const gfdm_complex* in0,
+                          const gfdm_complex* in1, int n, int mem)
+{
+    API_TRY
+    h->use();
+    if (n < 0) throw std::invalid_argument("n_frames MUST NOT be negative");
+    if (op == RX_CANCEL && !in1) throw std::invalid_argument("fd_in MUST NOT be NULL");
+    Staging st(h, mem);
+    const size_t N = h->N;
+    const size_t c = mem == GFDM_MEM_DEVICE ? (size_t)n : chunk_frames(3 * sizeof(cpx) * N, (size_t)n);
+    for (size_t f0 = 0; f0 < (size_t)n; f0 += c) {
+        const size_t nf = std::min(c, (size_t)n - f0), el = nf * N;
+        const cpx* d0 = st.in(in0 + f0 * N, el, h->stage_in);
+        const cpx* d1 = st.in(in1 ? in1 + f0 * N : nullptr, el, h->stage_in2);
+        cpx* dout = st.out(out + f0 * N, el, h->stage_out);
+        switch (op) {
+        case RX_WORK: receiver_run(h, dout, d0, d1, nf); break;
+        case RX_FD: receiver_fd(h, dout, d0, d1, nf); break;
+        case RX_TD:
+            receiver_td(h, dout, d0, nf);
+            h->last_kernel = "generic:ifft_m";
+            break;
+        case RX_CANCEL: receiver_cancel(h, dout, d0, d1, nf); break;
+        }
+        st.finish(out + f0 * N, el, h->stage_out);
+    }
+    API_CATCH
+}
+int gfdm_receiver_work_batch(gfdm_receiver* h, gfdm_complex* out, const gfdm_complex* in, const gfdm_complex* eq,
+                             int n, int mem)
+{
+    return receiver_batch(h, RX_WORK, out, in, eq, n, mem);
+}
+int gfdm_receiver_work(gfdm_receiver* h, gfdm_complex* out, const gfdm_complex* in)
+{
+    return receiver_batch(h, RX_WORK, out, in, nullptr, 1, GFDM_MEM_HOST);
+}
+int gfdm_receiver_work_equalize(gfdm_receiver* h, gfdm_complex* out, const gfdm_complex* in, const gfdm_complex* eq)
+{
+    if (!eq) return fail(GFDM_ERR_INVALID_ARGUMENT, "f_eq_in MUST NOT be NULL");
+    return receiver_batch(h, RX_WORK, out, in, eq, 1, GFDM_MEM_HOST);
+}
+int gfdm_receiver_fft_filter_downsample_batch(gfdm_receiver* h, gfdm_complex* out, const gfdm_complex* in,
+                                              const gfdm_complex* eq, int n, int mem)
+{
+    return receiver_batch(h, RX_FD, out, in, eq, n, mem);
+}
+int gfdm_receiver_fft_filter_downsample(gfdm_receiver* h, gfdm_complex* out, const gfdm_complex* in)
+{
+    return receiver_batch(h, RX_FD, out, in, nullptr, 1, GFDM_MEM_HOST);
+}
+int gfdm_receiver_fft_equalize_filter_downsample(gfdm_receiver* h, gfdm_complex* out, const gfdm_complex* in,
+                                                 const gfdm_complex* eq)
+{
+    if (!eq) return fail(GFDM_ERR_INVALID_ARGUMENT, "f_eq_in MUST NOT be NULL");
+    return receiver_batch(h, RX_FD, out, in, eq, 1, GFDM_MEM_HOST);
+}
+int gfdm_receiver_transform_subcarriers_to_td_batch(gfdm_receiver* h, gfdm_complex* out, const gfdm_complex* in,
+                                                    int n, int mem)
+{
+    return receiver_batch(h, RX_TD, out, in, nullptr, n, mem);
+}
+int gfdm_receiver_transform_subcarriers_to_td(gfdm_receiver* h, gfdm_complex* out, const gfdm_complex* in)
+{
+    return receiver_batch(h, RX_TD, out, in, nullptr, 1, GFDM_MEM_HOST);
+}
+int gfdm_receiver_cancel_sc_interference_batch(gfdm_receiver* h, gfdm_complex* out, const gfdm_complex* td,
+                                               const gfdm_complex* fd, int n, int mem)
+{
+    return receiver_batch(h, RX_CANCEL, out, td, fd, n, mem);
+}
+int gfdm_receiver_cancel_sc_interference(gfdm_receiver* h, gfdm_complex* out, const gfdm_complex* td,
+                                         const gfdm_complex* fd)
+{
+    return receiver_batch(h, RX_CANCEL, out, td, fd, 1, GFDM_MEM_HOST);
+}
+
+/* ---- advanced_receiver_kernel_cc ---------------------------------------- */
+struct gfdm_advanced_receiver : gfdm_receiver {
+    std::vector<int> smap;
+    int ic_iter = 0;
+    int phase_comp = 0;
+    int n_points = 0, rule = 0;
+    int* d_smap = nullptr;
+    unsigned char* d_active = nullptr;
+    cpx* d_points = nullptr;
+    DeviceBuf freq_block, ic_time, ic_freq;
+};
+
+// generic_work[_equalize] + perform_ic_iterations, lib/advanced_receiver_kernel_cc.cc:56-107
+static void advanced_run(gfdm_advanced_receiver* h, cpx* out, const cpx* in, const cpx* eq, size_t frames)
+{
+    if (!frames) return;
+    const size_t el = frames * (size_t)h->N;
+    h->freq_block.ensure(el * sizeof(cpx));
+    h->ic_time.ensure(el * sizeof(cpx));
+    h->ic_freq.ensure(el * sizeof(cpx));
+    cpx* FB = h->freq_block.as<cpx>();
+    cpx* IT = h->ic_time.as<cpx>();
+    cpx* IF = h->ic_freq.as<cpx>();
+    receiver_fd(h, FB, in, eq, frames);
+    receiver_td(h, out, FB, frames);
+    for (int j = 0; j < h->ic_iter; ++j) {
+        launch_decide(IT, out, h->d_active, h->d_points, h->n_points, h->rule, h->M, h->K, frames, h->stream);
+        h->launches += 1;
+        if (h->phase_comp > 0 && j == 0) {
+            launch_phase_rotate(FB, IT, out, h->d_smap, (int)h->smap.size(), h->M, h->K, frames, h->stream);
+            h->launches += 1;
+        }
+        receiver_cancel(h, IF, IT, FB, frames);
+        receiver_td(h, out, IF, frames);
+    }
+    h->last_kernel = "generic:advanced_receiver";
+}
+
+int gfdm_advanced_receiver_create(gfdm_advanced_receiver** out, int M, int K, int L, const gfdm_complex* taps,
+                                  int n_taps, const int* smap, int n_map, int ic_iter, const gfdm_constellation* c,
+                                  int do_phase_compensation)
+{
+    API_TRY
+    if (!c || c->n_points < 1 || !c->points) throw std::invalid_argument("constellation MUST hold at least one point");
+    if (n_map < 0) throw std::invalid_argument("subcarrier_map size MUST NOT be negative");
+    for (int i = 0; i < n_map; ++i)
+        if (smap[i] < 0 || smap[i] >= K) throw std::invalid_argument("subcarrier_map entries MUST lie in [0, subcarriers)");
+    std::unique_ptr<gfdm_advanced_receiver> h(new gfdm_advanced_receiver);
+    h->smap.assign(smap, smap + n_map);
+    h->ic_iter = ic_iter;
+    h->phase_comp = do_phase_compensation;
+    h->n_points = c->n_points;
+    h->rule = c->decision_rule;
+    receiver_init(h.get(), M, K, L, vec(taps, n_taps));
+    std::vector<unsigned char> active(K, 0);
+    for (int k : h->smap) active[k] = 1;
+    h->d_active = upload(active);
+    h->d_smap = upload(h->smap);
+    h->d_points = dev_upload(vec(c->points, c->n_points));
+    *out = h.release();
+    API_CATCH
+}
+void gfdm_advanced_receiver_destroy(gfdm_advanced_receiver* h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->d_smap) cudaFree(h->d_smap);
+    if (h->d_active) cudaFree(h->d_active);
+    if (h->d_points) cudaFree(h->d_points);
+    h->freq_block.release(); h->ic_time.release(); h->ic_freq.release();
+    receiver_free(h);
+    delete h;
+}
+int gfdm_advanced_receiver_block_size(const gfdm_advanced_receiver* h) { return h->N; }
+int gfdm_advanced_receiver_set_ic(gfdm_advanced_receiver* h, int v) { h->ic_iter = v; return GFDM_OK; }
+int gfdm_advanced_receiver_get_ic(const gfdm_advanced_receiver* h) { return h->ic_iter; }
+int gfdm_advanced_receiver_set_phase_compensation(gfdm_advanced_receiver* h, int v) { h->phase_comp = v; return GFDM_OK; }
+int gfdm_advanced_receiver_get_phase_compensation(const gfdm_advanced_receiver* h) { return h->phase_comp; }
+int gfdm_advanced_receiver_work_batch(gfdm_advanced_receiver* h, gfdm_complex* out, const gfdm_complex* in,
+                                      const gfdm_complex* eq, int n, int mem)
+{
+    API_TRY
+    h->use();
+    if (n < 0) throw std::invalid_argument("n_frames MUST NOT be negative");
+    Staging st(h, mem);
+    const size_t N = h->N;
+    const size_t c = mem == GFDM_MEM_DEVICE ? (size_t)n : chunk_frames(6 * sizeof(cpx) * N, (size_t)n);
+    for (size_t f0 = 0; f0 < (size_t)n; f0 += c) {
+        const size_t nf = std::min(c, (size_t)n - f0), el = nf * N;
+        const cpx* d0 = st.in(in + f0 * N, el, h->stage_in);
+        const cpx* d1 = st.in(eq ? eq + f0 * N : nullptr, el, h->stage_in2);
+        cpx* dout = st.out(out + f0 * N, el, h->stage_out);
+        advanced_run(h, dout, d0, d1, nf);
+        st.finish(out + f0 * N, el, h->stage_out);
+    }
+    API_CATCH
+}
+int gfdm_advanced_receiver_work(gfdm_advanced_receiver* h, gfdm_complex* out, const gfdm_complex* in)
+{
+    return gfdm_advanced_receiver_work_batch(h, out, in, nullptr, 1, GFDM_MEM_HOST);
+}
+int gfdm_advanced_receiver_work_equalize(gfdm_advanced_receiver* h, gfdm_complex* out, const gfdm_complex* in,
+                                         const gfdm_complex* eq)
+{
+    if (!eq) return fail(GFDM_ERR_INVALID_ARGUMENT, "f_eq_in MUST NOT be NULL");
+    return gfdm_advanced_receiver_work_batch(h, out, in, eq, 1, GFDM_MEM_HOST);
+}
+
+/* ---- resource_mapper_kernel_cc ------------------------------------------ */
+struct MapperCore {
+    int M = 0, K = 0, A = 0;
+    size_t block_size = 0, frame_size = 0;
+    bool per_timeslot = true, is_mapper = true;
+    std::vector<int> smap; // sorted
+    int* d_smap = nullptr;
+    int* d_inv = nullptr;
+    // lib/resource_mapper_kernel_cc.cc:30-70
+    void validate(int M_, int K_, int A_, const int* map, int n_map, bool pts, bool mapper)
+    {
+        if (A_ > K_)
+            throw std::invalid_argument("active_subcarriers(" + std::to_string(A_) +
+                                        ") MUST be smaller or equal to subcarriers(" + std::to_string(K_) + ")!");
+        if (n_map != A_)
+            throw std::invalid_argument("number of subcarrier_map entries(" + std::to_string(n_map) +
+                                        ") MUST be equal to active_subcarriers(" + std::to_string(A_) + ")!");
+        if (M_ < 1 || K_ < 1) throw std::invalid_argument("timeslots and subcarriers MUST be positive");
+        smap.assign(map, map + n_map);
+        std::sort(smap.begin(), smap.end());
+        if (std::adjacent_find(smap.begin(), smap.end()) != smap.end())
+            throw std::invalid_argument("All entries in subcarrier_map MUST be unique!");
+        if (!smap.empty() && smap.front() < 0)
+            throw std::invalid_argument("All subcarrier indices MUST be greater or equal to ZERO!");
+        // the reference tests `> subcarriers` (:65) and would then index out of bounds for == subcarriers
+        if (!smap.empty() && smap.back() >= K_)
+            throw std::invalid_argument("All subcarrier indices MUST be smaller or equal to subcarriers!");
+        M = M_; K = K_; A = A_;
+        block_size = (size_t)M * A;
+        frame_size = (size_t)M * K;
+        per_timeslot = pts;
+        is_mapper = mapper;
+    }
+    void to_device()
+    {
+        std::vector<int> inv(K, -1);
+        for (int a = 0; a < A; ++a) inv[smap[a]] = a;
+        d_smap = upload(smap);
+        d_inv = upload(inv);
+    }
+    void destroy()
+    {
+        if (d_smap) cudaFree(d_smap);
+        if (d_inv) cudaFree(d_inv);
+        d_smap = d_inv = nullptr;
+    }
+    void check_map_size(size_t n) const
+    {
+        if (n > block_size)
+            throw std::invalid_argument("input vector size(" + std::to_string(n) +
+                                        ") MUST not exceed active_subcarriers * timeslots(" +
+                                        std::to_string(block_size) + ")!");
+    }
+    void check_demap_size(size_t n) const
+    {
+        if (n > block_size)
+            throw std::invalid_argument("output vector size(" + std::to_string(n) +
+                                        ") MUST not exceed active_subcarriers * timeslots(" +
+                                        std::to_string(block_size) + ")!");
+    }
+};
+struct gfdm_resource_mapper : HandleBase {
+    MapperCore c;
+};
+int gfdm_resource_mapper_create(gfdm_resource_mapper** out, int M, int K, int A, const int* smap, int n_map,
+                                int per_timeslot, int is_mapper)
+{
+    API_TRY
+    std::unique_ptr<gfdm_resource_mapper> h(new gfdm_resource_mapper);
+    h->c.validate(M, K, A, smap, n_map, per_timeslot != 0, is_mapper != 0);
+    h->open();
+    h->c.to_device();
+    *out = h.release();
+    API_CATCH
+}
+void gfdm_resource_mapper_destroy(gfdm_resource_mapper* h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    h->c.destroy();
+    h->close();
+    delete h;
+}
+size_t gfdm_resource_mapper_frame_size(const gfdm_resource_mapper* h) { return h->c.frame_size; }
+size_t gfdm_resource_mapper_block_size(const gfdm_resource_mapper* h) { return h->c.block_size; }
+size_t gfdm_resource_mapper_input_vector_size(const gfdm_resource_mapper* h) { return h->c.is_mapper ? h->c.block_size : h->c.frame_size; }
+size_t gfdm_resource_mapper_output_vector_size(const gfdm_resource_mapper* h) { return h->c.is_mapper ? h->c.frame_size : h->c.block_size; }
+int gfdm_resource_mapper_map_to_resources_batch(gfdm_resource_mapper* h, gfdm_complex* out, const gfdm_complex* in,
+                                                size_t sz, int n, int mem)
+{
+    API_TRY
+    h->use();
+    h->c.check_map_size(sz);
+    if (n < 0) throw std::invalid_argument("n_frames MUST NOT be negative");
+    Staging st(h, mem);
+    const size_t fs = h->c.frame_size;
+    const size_t c = mem == GFDM_MEM_DEVICE ? (size_t)n : chunk_frames(sizeof(cpx) * (fs + sz), (size_t)n);
+    for (size_t f0 = 0; f0 < (size_t)n; f0 += c) {
+        const size_t nf = std::min(c, (size_t)n - f0);
+        const cpx* di = sz ? st.in(in + f0 * sz, nf * sz, h->stage_in) : nullptr;
+        cpx* dout = st.out(out + f0 * fs, nf * fs, h->stage_out);
+        launch_map(dout, di, h->c.d_inv, h->c.M, h->c.K, h->c.A, h->c.per_timeslot, sz, sz, nf, h->stream);
+        h->launches += 1;
+        h->last_kernel = "map_kernel";
+        st.finish(out + f0 * fs, nf * fs, h->stage_out);
+    }
+    API_CATCH
+}
+int gfdm_resource_mapper_map_to_resources(gfdm_resource_mapper* h, gfdm_complex* out, const gfdm_complex* in, size_t n)
+{
+    return gfdm_resource_mapper_map_to_resources_batch(h, out, in, n, 1, GFDM_MEM_HOST);
+}
+int gfdm_resource_mapper_demap_from_resources_batch(gfdm_resource_mapper* h, gfdm_complex* out,
+                                                    const gfdm_complex* in, size_t sz, int n, int mem)
+{
+    API_TRY
+    h->use();
+    h->c.check_demap_size(sz);
+    if (n < 0) throw std::invalid_argument("n_frames MUST NOT be negative");
+    if (sz == 0) return GFDM_OK;
+    Staging st(h, mem);
+    const size_t fs = h->c.frame_size;
+    const size_t c = mem == GFDM_MEM_DEVICE ? (size_t)n : chunk_frames(sizeof(cpx) * (fs + sz), (size_t)n);
+    for (size_t f0 = 0; f0 < (size_t)n; f0 += c) {
+        const size_t nf = std::min(c, (size_t)n - f0);
+        const cpx* di = st.in(in + f0 * fs, nf * fs, h->stage_in);
+        cpx* dout = st.out(out + f0 * sz, nf * sz, h->stage_out);
+        launch_demap(dout, di, h->c.d_smap, h->c.M, h->c.K, h->c.A, h->c.per_timeslot, sz, sz, nf, h->stream);
+        h->launches += 1;
+        h->last_kernel = "demap_kernel";
+        st.finish(out + f0 * sz, nf * sz, h->stage_out);
+    }
+    API_CATCH
+}
+int gfdm_resource_mapper_demap_from_resources(gfdm_resource_mapper* h, gfdm_complex* out, const gfdm_complex* in,
+                                              size_t n)
+{
+    return gfdm_resource_mapper_demap_from_resources_batch(h, out, in, n, 1, GFDM_MEM_HOST);
+}
+
+/* ---- add_cyclic_prefix_cc ----------------------------------------------- */
+struct PrefixCore {
+    int block_len = 0, cp_len = 0, cs_len = 0, ramp_len = 0, cyclic_shift = 0;
+    std::vector<cf> front, back;
+    cpx* d_front = nullptr;
+    cpx* d_back = nullptr;
+    // lib/add_cyclic_prefix_cc.cc:30-57
+    void validate(int bl, int cp, int cs, int ramp, const std::vector<cf>& w, int shift)
+    {
+        const int window_len = bl + cp + cs;
+        if (w.size() != (size_t)window_len && w.size() != (size_t)(2 * ramp)) {
+            std::stringstream s;
+            s << "number of window taps(" << w.size() << ") MUST be equal to 2*ramp_len(" << 2 * ramp
+              << ") OR block_len+cp_len (" << window_len << ")!";
+            throw std::invalid_argument(s.str());
+        }
+        if (bl < 1 || cp < 0 || cs < 0 || ramp < 0 || (size_t)ramp > w.size())
+            throw std::invalid_argument("block_len MUST be positive; cp_len, cs_len, ramp_len MUST NOT be negative");
+        block_len = bl; cp_len = cp; cs_len = cs; ramp_len = ramp; cyclic_shift = shift;
+        front.assign(w.begin(), w.begin() + ramp);
+        back.assign(w.end() - ramp, w.end());
+    }
+    void to_device()
+    {
+        d_front = dev_upload(front);
+        d_back = dev_upload(back);
+    }
+    void destroy()
+    {
+        if (d_front) cudaFree(d_front);
+        if (d_back) cudaFree(d_back);
+        d_front = d_back = nullptr;
+    }
+    int frame_size() const { return block_len + cp_len + cs_len; }
+    void check_shift(int s) const
+    {
+        if (s < 0 || s > cs_len || cp_len + s > block_len)
+            throw std::invalid_argument("cyclic_shift MUST lie in [0, cs_len] and cp_len + cyclic_shift MUST NOT exceed block_len");
+    }
+};
+struct gfdm_cyclic_prefixer : HandleBase {
+    PrefixCore c;
+};
+int gfdm_cyclic_prefixer_create(gfdm_cyclic_prefixer** out, int block_len, int cp_len, int cs_len, int ramp_len,
+                                const gfdm_complex* w, int n_w, int cyclic_shift)
+{
+    API_TRY
+    std::unique_ptr<gfdm_cyclic_prefixer> h(new gfdm_cyclic_prefixer);
+    h->c.validate(block_len, cp_len, cs_len, ramp_len, vec(w, n_w), cyclic_shift);
+    h->open();
+    h->c.to_device();
+    *out = h.release();
+    API_CATCH
+}
+void gfdm_cyclic_prefixer_destroy(gfdm_cyclic_prefixer* h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    h->c.destroy();
+    h->close();
+    delete h;
+}
+int gfdm_cyclic_prefixer_block_size(const gfdm_cyclic_prefixer* h) { return h->c.block_len; }
+int gfdm_cyclic_prefixer_frame_size(const gfdm_cyclic_prefixer* h) { return h->c.frame_size(); }
+int gfdm_cyclic_prefixer_cyclic_shift(const gfdm_cyclic_prefixer* h) { return h->c.cyclic_shift; }
+int gfdm_cyclic_prefixer_add_cyclic_prefix_batch(gfdm_cyclic_prefixer* h, gfdm_complex* out, const gfdm_complex* in,
+                                                 int shift, int n, int mem)
+{
+    API_TRY
+    h->use();
+    h->c.check_shift(shift);
+    if (n < 0) throw std::invalid_argument("n_frames MUST NOT be negative");
+    Staging st(h, mem);
+    const size_t N = h->c.block_len, W = h->c.frame_size();
+    const size_t c = mem == GFDM_MEM_DEVICE ? (size_t)n : chunk_frames(sizeof(cpx) * (N + W), (size_t)n);
+    for (size_t f0 = 0; f0 < (size_t)n; f0 += c) {
+        const size_t nf = std::min(c, (size_t)n - f0);
+        const cpx* di = st.in(in + f0 * N, nf * N, h->stage_in);
+        cpx* dout = st.out(out + f0 * W, nf * W, h->stage_out);
+        launch_add_cp(dout, di, h->c.block_len, h->c.cp_len, h->c.cs_len, h->c.ramp_len, h->c.d_front, h->c.d_back,
+                      shift, W, nf, h->stream);
+        h->launches += 1;
+        h->last_kernel = "add_cp_kernel";
+        st.finish(out + f0 * W, nf * W, h->stage_out);
+    }
+    API_CATCH
+}
+int gfdm_cyclic_prefixer_add_cyclic_prefix(gfdm_cyclic_prefixer* h, gfdm_complex* out, const gfdm_complex* in, int shift)
+{
+    return gfdm_cyclic_prefixer_add_cyclic_prefix_batch(h, out, in, shift, 1, GFDM_MEM_HOST);
+}
+int gfdm_cyclic_prefixer_work(gfdm_cyclic_prefixer* h, gfdm_complex* out, const gfdm_complex* in)
+{
+    return gfdm_cyclic_prefixer_add_cyclic_prefix_batch(h, out, in, h->c.cyclic_shift, 1, GFDM_MEM_HOST);
+}
+int gfdm_cyclic_prefixer_remove_cyclic_prefix_batch(gfdm_cyclic_prefixer* h, gfdm_complex* out,
+                                                    const gfdm_complex* in, int n, int mem)
+{
+    API_TRY
+    h->use();
+    if (n < 0) throw std::invalid_argument("n_frames MUST NOT be negative");
+    Staging st(h, mem);
+    const size_t N = h->c.block_len, W = h->c.frame_size();
+    const size_t c = mem == GFDM_MEM_DEVICE ? (size_t)n : chunk_frames(sizeof(cpx) * (N + W), (size_t)n);
+    for (size_t f0 = 0; f0 < (size_t)n; f0 += c) {
+        const size_t nf = std::min(c, (size_t)n - f0);
+        const cpx* di = st.in(in + f0 * W, nf * W, h->stage_in);
+        cpx* dout = st.out(out + f0 * N, nf * N, h->stage_out);
+        launch_remove_cp(dout, di, h->c.block_len, h->c.cp_len, h->c.cs_len, nf, h->stream);
+        h->launches += 1;
+        h->last_kernel = "remove_cp_kernel";
+        st.finish(out + f0 * N, nf * N, h->stage_out);
+    }
+    API_CATCH
+}
+int gfdm_cyclic_prefixer_remove_cyclic_prefix(gfdm_cyclic_prefixer* h, gfdm_complex* out, const gfdm_complex* in)
+{
+    return gfdm_cyclic_prefixer_remove_cyclic_prefix_batch(h, out, in, 1, GFDM_MEM_HOST);
+}
+
+/* ---- preamble_channel_estimator_cc -------------------------------------- */
+struct gfdm_channel_estimator : HandleBase {
+    int M = 0, K = 0, A = 0, dc_free = 0, which = 0;
+    float g[9];
+    FftPlan fft_k, fft_2k;
+    cpx* d_inv0 = nullptr;
+    cpx* d_inv1 = nullptr;
+    float* d_g = nullptr;
+    DeviceBuf fbuf, hbuf, filt, fscratch;
+    int n_est() const { return A + (dc_free ? 1 : 0); }
+};
+
+int gfdm_channel_estimator_create(gfdm_channel_estimator** out, int M, int K, int A, int is_dc_free, int which,
+                                  const gfdm_complex* preamble, int n_preamble)
+{
+    API_TRY
+    if (M < 1 || K < 2 || A < 2 || A > K)
+        throw std::invalid_argument("timeslots MUST be positive and 2 <= active_subcarriers <= fft_len");
+    if (n_preamble < 2 * K) throw std::invalid_argument("preamble MUST hold at least 2 * fft_len samples");
+    if (A + (is_dc_free ? 1 : 0) > K)
+        throw std::invalid_argument("active_subcarriers (+1 if dc free) MUST NOT exceed fft_len");
+    std::unique_ptr<gfdm_channel_estimator> h(new gfdm_channel_estimator);
+    h->M = M; h->K = K; h->A = A; h->dc_free = is_dc_free ? 1 : 0; h->which = which;
+    // initialize_gaussian_filter(sigma_sq = 1, 9 taps), lib/preamble_channel_estimator_cc.cc:86-100
+    float s = 0.0f;
+    for (int i = 0; i < 9; ++i) {
+        const float val = std::pow(float(i - (9 / 2)), 2.0f) / 1.0f;
+        h->g[i] = std::exp(-0.5f * val);
+        s += h->g[i];
+    }
+    for (int i = 0; i < 9; ++i) h->g[i] = h->g[i] / s;
+    h->open();
+    h->fft_k.init(K);
+    h->fft_2k.init(2 * K);
+    h->d_g = upload(std::vector<float>(h->g, h->g + 9));
+    // inv_ref_h = 0.5 / FFT_K(preamble half h)  (:111-119): FFT on the device engine, division on the host
+    std::vector<cf> pre = vec(preamble, 2 * K), F(2 * K);
+    h->fbuf.ensure(sizeof(cpx) * 2 * K);
+    h->hbuf.ensure(sizeof(cpx) * 2 * K);
+    h->fscratch.ensure(sizeof(cpx) * 2 * K);
+    GFDM_CUDA_CHECK(cudaMemcpyAsync(h->hbuf.p, pre.data(), sizeof(cpx) * 2 * K, cudaMemcpyHostToDevice, h->stream));
+    h->launches += fft_exec(h->fft_k, h->fbuf.as<cpx>(), h->hbuf.as<cpx>(), h->fscratch.as<cpx>(), 2, false, 1.0f, h->stream);
+    GFDM_CUDA_CHECK(cudaMemcpyAsync(F.data(), h->fbuf.p, sizeof(cpx) * 2 * K, cudaMemcpyDeviceToHost, h->stream));
+    h->sync();
+    std::vector<cf> inv(2 * K);
+    for (int i = 0; i < 2 * K; ++i) inv[i] = cf(0.5f, 0.0f) / F[i];
+    h->d_inv0 = dev_upload(std::vector<cf>(inv.begin(), inv.begin() + K));
+    h->d_inv1 = dev_upload(std::vector<cf>(inv.begin() + K, inv.end()));
+    *out = h.release();
+    API_CATCH
+}
+void gfdm_channel_estimator_destroy(gfdm_channel_estimator* h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    h->fft_k.destroy(); h->fft_2k.destroy();
+    if (h->d_inv0) cudaFree(h->d_inv0);
+    if (h->d_inv1) cudaFree(h->d_inv1);
+    if (h->d_g) cudaFree(h->d_g);
+    h->fbuf.release(); h->hbuf.release(); h->filt.release(); h->fscratch.release();
+    h->close();
+    delete h;
+}
+int gfdm_channel_estimator_fft_len(const gfdm_channel_estimator* h) { return h->K; }
+int gfdm_channel_estimator_timeslots(const gfdm_channel_estimator* h) { return h->M; }
+int gfdm_channel_estimator_frame_len(const gfdm_channel_estimator* h) { return h->M * h->K; }
+int gfdm_channel_estimator_active_subcarriers(const gfdm_channel_estimator* h) { return h->A; }
+int gfdm_channel_estimator_is_dc_free(const gfdm_channel_estimator* h) { return h->dc_free; }
+int gfdm_channel_estimator_preamble_filter_taps(const gfdm_channel_estimator* h, float* o)
+{
+    memcpy(o, h->g, sizeof(h->g));
+    return GFDM_OK;
+}
+
+// rx [frames][2K] -> H [frames][K]
+static void est_preamble_channel(gfdm_channel_estimator* h, cpx* H, const cpx* rx, size_t frames)
+{
+    const size_t el = frames * 2 * (size_t)h->K;
+    h->fbuf.ensure(el * sizeof(cpx));
+    h->fscratch.ensure(el * sizeof(cpx));
+    h->launches += fft_exec(h->fft_k, h->fbuf.as<cpx>(), rx, h->fscratch.as<cpx>(), 2 * frames, false, 1.0f, h->stream);
+    launch_est_combine(H, h->fbuf.as<cpx>(), h->d_inv0, h->d_inv1, h->K, frames, h->stream);
+    h->launches += 1;
+}
+static void est_frame(gfdm_channel_estimator* h, cpx* fe, const cpx* rx, size_t frames)
+{
+    if (!frames) return;
+    h->hbuf.ensure(frames * (size_t)h->K * sizeof(cpx));
+    h->filt.ensure(frames * (size_t)h->n_est() * sizeof(cpx));
+    est_preamble_channel(h, h->hbuf.as<cpx>(), rx, frames);
+    launch_est_filter(h->filt.as<cpx>(), h->hbuf.as<cpx>(), h->d_g, h->K, h->A, h->dc_free, frames, h->stream);
+    launch_est_interp(fe, h->filt.as<cpx>(), h->M, h->K, h->A, h->dc_free, frames, h->stream);
+    h->launches += 2;
+    h->last_kernel = "fft_k+est_combine+est_filter+est_interp";
+}
+
+enum EstOp { EST_CHANNEL, EST_FILTER, EST_INTERP, EST_ZF, EST_FRAME };
+static int estimator_batch(gfdm_channel_estimator* h, EstOp op, gfdm_complex* out, const gfdm_complex* in, int n, int mem)
+{
+    API_TRY
+    h->use();
+    if (n < 0) throw std::invalid_argument("n_frames MUST NOT be negative");
+    Staging st(h, mem);
+    const size_t K = h->K, N = (size_t)h->M * h->K, ne = h->n_est();
+    size_t in_sz = 0, out_sz = 0;
+    switch (op) {
+    case EST_CHANNEL: in_sz = 2 * K; out_sz = K; break;
+    case EST_FILTER: in_sz = K; out_sz = ne; break;
+    case EST_INTERP: in_sz = ne; out_sz = N; break;
+    case EST_ZF: in_sz = N; out_sz = N; break;
+    case EST_FRAME: in_sz = 2 * K; out_sz = N; break;
+    }
+    const size_t c = mem == GFDM_MEM_DEVICE ? (size_t)n : chunk_frames(sizeof(cpx) * (in_sz + out_sz), (size_t)n);
+    for (size_t f0 = 0; f0 < (size_t)n; f0 += c) {
+        const size_t nf = std::min(c, (size_t)n - f0);
+        const cpx* di = st.in(in + f0 * in_sz, nf * in_sz, h->stage_in);
+        cpx* dout = st.out(out + f0 * out_sz, nf * out_sz, h->stage_out);
+        // interpolation leaves some bins untouched (reference quirk): seed the staged output with the caller's data
+        if (mem == GFDM_MEM_HOST && (op == EST_INTERP || op == EST_FRAME))
+            GFDM_CUDA_CHECK(cudaMemcpyAsync(dout, out + f0 * out_sz, nf * out_sz * sizeof(cpx), cudaMemcpyHostToDevice, h->stream));
+        switch (op) {
+        case EST_CHANNEL:
+            est_preamble_channel(h, dout, di, nf);
+            h->last_kernel = "fft_k+est_combine";
+            break;
+        case EST_FILTER:
+            launch_est_filter(dout, di, h->d_g, h->K, h->A, h->dc_free, nf, h->stream);
+            h->launches += 1;
+            h->last_kernel = "est_filter_kernel";
+            break;
+        case EST_INTERP:
+            launch_est_interp(dout, di, h->M, h->K, h->A, h->dc_free, nf, h->stream);
+            h->launches += 1;
+            h->last_kernel = "est_interp_kernel";
+            break;
+        case EST_ZF:
+            launch_zf_prepare(dout, di, nf * N, h->stream);
+            h->launches += 1;
+            h->last_kernel = "zf_prepare_kernel";
+            break;
+        case EST_FRAME: est_frame(h, dout, di, nf); break;
+        }
+        st.finish(out + f0 * out_sz, nf * out_sz, h->stage_out);
+    }
+    API_CATCH
+}
+int gfdm_channel_estimator_estimate_preamble_channel(gfdm_channel_estimator* h, gfdm_complex* o, const gfdm_complex* rx)
+{
+    return estimator_batch(h, EST_CHANNEL, o, rx, 1, GFDM_MEM_HOST);
+}
+int gfdm_channel_estimator_filter_preamble_estimate(gfdm_channel_estimator* h, gfdm_complex* o, const gfdm_complex* e)
+{
+    return estimator_batch(h, EST_FILTER, o, e, 1, GFDM_MEM_HOST);
+}
+int gfdm_channel_estimator_interpolate_frame(gfdm_channel_estimator* h, gfdm_complex* o, const gfdm_complex* e)
+{
+    return estimator_batch(h, EST_INTERP, o, e, 1, GFDM_MEM_HOST);
+}
+int gfdm_channel_estimator_prepare_for_zf(gfdm_channel_estimator* h, gfdm_complex* o, const gfdm_complex* e)
+{
+    return estimator_batch(h, EST_ZF, o, e, 1, GFDM_MEM_HOST);
+}
+int gfdm_channel_estimator_estimate_frame(gfdm_channel_estimator* h, gfdm_complex* o, const gfdm_complex* rx)
+{
+    return estimator_batch(h, EST_FRAME, o, rx, 1, GFDM_MEM_HOST);
+}
+int gfdm_channel_estimator_estimate_frame_batch(gfdm_channel_estimator* h, gfdm_complex* o, const gfdm_complex* rx,
+                                                int n, int mem)
+{
+    return estimator_batch(h, EST_FRAME, o, rx, n, mem);
+}
+int gfdm_channel_estimator_estimate_snr_batch(gfdm_channel_estimator* h, float* snr, float* cnrs,
+                                              const gfdm_complex* rx, int n, int mem)
+{
+    API_TRY
+    h->use();
+    if (n < 0) throw std::invalid_argument("n_frames MUST NOT be negative");
+    if (n == 0) return GFDM_OK;
+    Staging st(h, mem);
+    const size_t nf = (size_t)n, el = nf * 2 * (size_t)h->K;
+    const cpx* di = st.in(rx, el, h->stage_in);
+    h->fbuf.ensure(el * sizeof(cpx));
+    h->fscratch.ensure(el * sizeof(cpx));
+    h->launches += fft_exec(h->fft_2k, h->fbuf.as<cpx>(), di, h->fscratch.as<cpx>(), nf, false, 1.0f, h->stream);
+    float* d_snr = snr;
+    float* d_cnr = cnrs;
+    if (mem == GFDM_MEM_HOST) {
+        h->stage_out.ensure(sizeof(float) * nf * (size_t)(1 + h->A));
+        d_snr = h->stage_out.as<float>();
+        d_cnr = cnrs ? d_snr + nf : nullptr;
+    }
+    launch_est_snr(d_snr, d_cnr, h->fbuf.as<cpx>(), h->K, h->A, h->dc_free, nf, h->stream);
+    h->launches += 1;
+    h->last_kernel = "fft_2k+est_snr_kernel";
+    if (mem == GFDM_MEM_HOST) {
+        GFDM_CUDA_CHECK(cudaMemcpyAsync(snr, d_snr, sizeof(float) * nf, cudaMemcpyDeviceToHost, h->stream));
+        if (cnrs) GFDM_CUDA_CHECK(cudaMemcpyAsync(cnrs, d_cnr, sizeof(float) * nf * h->A, cudaMemcpyDeviceToHost, h->stream));
+        h->sync();
+    }
+    API_CATCH
+}
+int gfdm_channel_estimator_estimate_snr(gfdm_channel_estimator* h, float* snr, float* cnrs, const gfdm_complex* rx)
+{
+    return gfdm_channel_estimator_estimate_snr_batch(h, snr, cnrs, rx, 1, GFDM_MEM_HOST);
+}
+
+/* ---- transmitter_kernel ------------------------------------------------- */
+struct gfdm_transmitter : HandleBase {
+    MapperCore map;
+    PrefixCore pre;
+    int M = 0, K = 0, L = 0, N = 0;
+    std::vector<cf> taps;
+    cpx* d_taps = nullptr;
+    FftPlan fft_m, fft_n;
+    FusedModem fused;
+    std::vector<int> shifts;
+    int preamble_size = 0;
+    cpx* d_preambles = nullptr; // [n_shifts][preamble_size]
+    DeviceBuf mapped, frame;
+    int out_size() const { return pre.frame_size() + preamble_size; }
+    int shift_index(int s) const
+    {
+        for (size_t i = 0; i < shifts.size(); ++i)
+            if (shifts[i] == s) return (int)i; // first entry wins, as unordered_map::emplace (transmitter_kernel.cc:67-71)
+        throw std::invalid_argument("cyclic_shift has no preamble");
+    }
+};
+
+// map + modulate (lib/transmitter_kernel.cc:78-84): in [frames][nin] -> blk [frames][N]
+static void tx_modulate(gfdm_transmitter* h, cpx* blk, const cpx* in, size_t nin, size_t frames)
+{
+    if (!frames) return;
+    const size_t el = frames * (size_t)h->N;
+    h->mapped.ensure(el * sizeof(cpx));
+    cpx* mp = h->mapped.as<cpx>();
+    launch_map(mp, in, h->map.d_inv, h->M, h->K, h->map.A, h->map.per_timeslot, nin, nin, frames, h->stream);
+    h->launches += 1;
+    if (h->fused.available()) {
+        h->launches += h->fused.modulate(blk, mp, frames, h->stream);
+        return;
+    }
+    h->work_a.ensure(el * sizeof(cpx));
+    h->work_b.ensure(el * sizeof(cpx));
+    cpx* A = h->work_a.as<cpx>();
+    cpx* B = h->work_b.as<cpx>();
+    h->launches += fft_exec(h->fft_m, A, mp, B, frames * h->K, false, 1.0f, h->stream);
+    launch_mod_filter(B, A, h->d_taps, h->M, h->K, h->L, frames, h->stream);
+    h->launches += 1;
+    h->launches += fft_exec(h->fft_n, blk, B, A, frames, true, (float)(1.0 / h->N), h->stream);
+}
+// preamble + CP frame for one shift (lib/transmitter_kernel.cc:86-98): out [frames][out_size]
+static void tx_add_frame(gfdm_transmitter* h, cpx* out, const cpx* blk, int shift, size_t frames)
+{
+    if (!frames) return;
+    const int idx = h->shift_index(shift);
+    h->pre.check_shift(shift);
+    const size_t os = h->out_size();
+    launch_copy_rows(out, h->d_preambles + (size_t)idx * h->preamble_size, h->preamble_size, os, frames, h->stream);
+    launch_add_cp(out + h->preamble_size, blk, h->N, h->pre.cp_len, h->pre.cs_len, h->pre.ramp_len, h->pre.d_front,
+                  h->pre.d_back, shift, os, frames, h->stream);
+    h->launches += 2;
+}
+
+int gfdm_transmitter_create(gfdm_transmitter** out, int M, int K, int A, int cp, int cs, int ramp, const int* smap,
+                            int n_map, int per_timeslot, int L, const gfdm_complex* taps, int n_taps,
+                            const gfdm_complex* w, int n_w, const int* shifts, int n_shifts,
+                            const gfdm_complex* const* preambles, const int* preamble_sizes, int n_preambles)
+{
+    API_TRY
+    if (n_preambles < 1) throw std::invalid_argument("at least one preamble is required");
+    std::unique_ptr<gfdm_transmitter> h(new gfdm_transmitter);
+    // member construction order of the reference: mapper, modulator, prefixer (transmitter_kernel.cc:47-52)
+    h->map.validate(M, K, A, smap, n_map, per_timeslot != 0, true);
+    check_taps((size_t)(n_taps > 0 ? n_taps : 0), M, L);
+    if (L < 1) throw std::invalid_argument("overlap MUST be positive");
+    h->pre.validate(M * K, cp, cs, ramp, vec(w, n_w), 0);
+    if (n_shifts != n_preambles)
+        throw std::invalid_argument("Number of cyclic shifts and number of preambles do not match!");
+    for (int i = 0; i < n_preambles; ++i)
+        if (preamble_sizes[i] != preamble_sizes[0]) throw std::invalid_argument("All preambles must have equal size!");
+    h->M = M; h->K = K; h->L = L; h->N = M * K;
+    h->taps = normalize_taps(vec(taps, n_taps), M);
+    h->shifts.assign(shifts, shifts + n_shifts);
+    h->preamble_size = preamble_sizes[0];
+    h->open();
+    h->map.to_device();
+    h->pre.to_device();
+    h->d_taps = dev_upload(h->taps);
+    h->fused.init_tx(M, K, L, h->taps);
+    if (!h->fused.available()) {
+        h->fft_m.init(M);
+        h->fft_n.init(h->N);
+    }
+    std::vector<cf> all;
+    for (int i = 0; i < n_preambles; ++i) {
+        std::vector<cf> p = vec(preambles[i], preamble_sizes[i]);
+        all.insert(all.end(), p.begin(), p.end());
+    }
+    h->d_preambles = dev_upload(all);
+    *out = h.release();
+    API_CATCH
+}
+void gfdm_transmitter_destroy(gfdm_transmitter* h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    h->map.destroy();
+    h->pre.destroy();
+    if (h->d_taps) cudaFree(h->d_taps);
+    if (h->d_preambles) cudaFree(h->d_preambles);
+    h->fft_m.destroy(); h->fft_n.destroy();
+    h->fused.destroy();
+    h->mapped.release(); h->frame.release();
+    h->close();
+    delete h;
+}
+int gfdm_transmitter_input_vector_size(const gfdm_transmitter* h) { return (int)h->map.block_size; }
+int gfdm_transmitter_output_vector_size(const gfdm_transmitter* h) { return h->out_size(); }
+int gfdm_transmitter_n_cyclic_shifts(const gfdm_transmitter* h) { return (int)h->shifts.size(); }
+int gfdm_transmitter_cyclic_shifts(const gfdm_transmitter* h, int* o)
+{
+    memcpy(o, h->shifts.data(), sizeof(int) * h->shifts.size());
+    return GFDM_OK;
+}
+
+enum TxOp { TX_WORK, TX_WORK_ALL, TX_MODULATE, TX_ADD_FRAME };
+static int transmitter_batch(gfdm_transmitter* h, TxOp op, gfdm_complex* out, const gfdm_complex* in, int nin,
+                             int shift, int n, int mem)
+{
+    API_TRY
+    h->use();
+    if (n < 0) throw std::invalid_argument("n_frames MUST NOT be negative");
+    if (op != TX_ADD_FRAME) {
+        if (nin < 0) throw std::invalid_argument("ninput_size MUST NOT be negative");
+        h->map.check_map_size((size_t)nin);
+    } else {
+        h->shift_index(shift);
+        h->pre.check_shift(shift);
+    }
+    if (op == TX_WORK || op == TX_WORK_ALL)
+        for (int s : h->shifts) h->pre.check_shift(s);
+    Staging st(h, mem);
+    const size_t N = h->N, os = h->out_size(), ns = h->shifts.size();
+    const size_t in_sz = op == TX_ADD_FRAME ? N : (size_t)nin;
+    const size_t out_sz = op == TX_MODULATE ? N : os;
+    const size_t n_ant = op == TX_WORK_ALL ? ns : 1;
+    const size_t c = mem == GFDM_MEM_DEVICE ? (size_t)n : chunk_frames(sizeof(cpx) * (in_sz + out_sz * n_ant + 3 * N), (size_t)n);
+    for (size_t f0 = 0; f0 < (size_t)n; f0 += c) {
+        const size_t nf = std::min(c, (size_t)n - f0);
+        const cpx* di = in_sz ? st.in(in + f0 * in_sz, nf * in_sz, h->stage_in) : nullptr;
+        // HOST staging of the all-antenna form: the chunk is laid out [ant][nf][os] on the device
+        cpx* dout = mem == GFDM_MEM_DEVICE ? reinterpret_cast<cpx*>(out) : st.out(out, nf * out_sz * n_ant, h->stage_out);
+        switch (op) {
+        case TX_MODULATE:
+            tx_modulate(h, mem == GFDM_MEM_DEVICE ? dout + f0 * N : dout, di, in_sz, nf);
+            h->last_kernel = h->fused.available() ? h->fused.mod_name() : "generic:map+fft_m+mod_filter+ifft_n";
+            break;
+        case TX_ADD_FRAME:
+            tx_add_frame(h, mem == GFDM_MEM_DEVICE ? dout + f0 * os : dout, di, shift, nf);
+            h->last_kernel = "copy_rows+add_cp_kernel";
+            break;
+        case TX_WORK:
+        case TX_WORK_ALL: {
+            h->frame.ensure(nf * N * sizeof(cpx));
+            tx_modulate(h, h->frame.as<cpx>(), di, in_sz, nf);
+            for (size_t a = 0; a < n_ant; ++a) {
+                cpx* o = mem == GFDM_MEM_DEVICE ? dout + (a * (size_t)n + f0) * os : dout + a * nf * os;
+                tx_add_frame(h, o, h->frame.as<cpx>(), h->shifts[a], nf);
+            }
+            h->last_kernel = h->fused.available() ? "map+fused_mod+copy_rows+add_cp" : "generic:transmitter";
+            break;
+        }
+        }
+        if (mem == GFDM_MEM_HOST) {
+            for (size_t a = 0; a < n_ant; ++a)
+                GFDM_CUDA_CHECK(cudaMemcpyAsync(out + (a * (size_t)n + f0) * out_sz, dout + a * nf * out_sz,
+                                                nf * out_sz * sizeof(cpx), cudaMemcpyDeviceToHost, h->stream));
+            h->sync();
+        }
+    }
+    API_CATCH
+}
+int gfdm_transmitter_work(gfdm_transmitter* h, gfdm_complex* out, const gfdm_complex* in, int n)
+{
+    return transmitter_batch(h, TX_WORK, out, in, n, 0, 1, GFDM_MEM_HOST);
+}
+int gfdm_transmitter_modulate(gfdm_transmitter* h, gfdm_complex* out, const gfdm_complex* in, int n)
+{
+    return transmitter_batch(h, TX_MODULATE, out, in, n, 0, 1, GFDM_MEM_HOST);
+}
+int gfdm_transmitter_add_frame(gfdm_transmitter* h, gfdm_complex* out, const gfdm_complex* in, int shift)
+{
+    return transmitter_batch(h, TX_ADD_FRAME, out, in, 0, shift, 1, GFDM_MEM_HOST);
+}
+int gfdm_transmitter_work_batch(gfdm_transmitter* h, gfdm_complex* out, const gfdm_complex* in, int nin, int n, int mem)
+{
+    return transmitter_batch(h, TX_WORK, out, in, nin, 0, n, mem);
+}
+int gfdm_transmitter_work_all_batch(gfdm_transmitter* h, gfdm_complex* out, const gfdm_complex* in, int nin, int n,
+                                    int mem)
+{
+    return transmitter_batch(h, TX_WORK_ALL, out, in, nin, 0, n, mem);
+}
+
+} // extern "C"

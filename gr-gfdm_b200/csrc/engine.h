@@ -1,0 +1,50 @@
+// engine.h -- host-callable launchers of the CUDA kernels (one translation unit each).
+#pragma once
+#include "common.cuh"
+
+namespace gfdm {
+
+// ---------------------------------------------------------------- fft_engine.cu
+// Any-length batched c2c DFT (unnormalised), Stockham autosort passes with
+// radix 4/2/3/5/... from the factorisation of n.  Used directly for shapes that
+// have no fused kernel and by the estimator.
+struct FftPlan {
+    int n = 0;
+    std::vector<int> radices;
+    cpx* d_tw = nullptr; // W_n^j = exp(-2 pi i j / n), generated in double
+    void init(int n);
+    void destroy();
+};
+// `batch` contiguous transforms; out != in; scratch holds batch*n elements
+// (only touched when the plan has more than one pass).  Returns #launches.
+int fft_exec(const FftPlan& p, cpx* out, const cpx* in, cpx* scratch, size_t batch, bool inverse,
+             float scale, cudaStream_t s);
+
+// ---------------------------------------------------------------- stage_kernels.cu
+// modulator: X[b*M+m] = sum_i T[((i+h)%L)*M+m] * D[((b-i+h) mod K)*M+m], m < part_len
+void launch_mod_filter(cpx* X, const cpx* D, const cpx* taps, int M, int K, int L, size_t frames, cudaStream_t s);
+// receiver: R[k*M+m] = sum_i T[((i+h)%L)*M+m] * Y[((k+i-h) mod K)*M+m]
+void launch_rx_filter(cpx* R, const cpx* Y, const cpx* taps, int M, int K, int L, size_t frames, cudaStream_t s);
+void launch_eq_divide(cpx* out, const cpx* Y, const cpx* eq, size_t n, cudaStream_t s);
+void launch_neighbor_sum(cpx* out, const cpx* td, int M, int K, size_t frames, cudaStream_t s);
+void launch_ic_subtract(cpx* out, const cpx* fd, const cpx* F, const cpx* ic_taps, int M, int K, size_t frames, cudaStream_t s);
+void launch_decide(cpx* out, const cpx* in, const unsigned char* active, const cpx* points, int n_points, int rule,
+                   int M, int K, size_t frames, cudaStream_t s);
+void launch_phase_rotate(cpx* R, const cpx* decided, const cpx* soft, const int* smap, int n_map, int M, int K,
+                         size_t frames, cudaStream_t s);
+void launch_map(cpx* out, const cpx* in, const int* inv_map, int M, int K, int A, bool per_timeslot, size_t n_in,
+                size_t in_stride, size_t frames, cudaStream_t s);
+void launch_demap(cpx* out, const cpx* in, const int* smap, int M, int K, int A, bool per_timeslot, size_t n_out,
+                  size_t out_stride, size_t frames, cudaStream_t s);
+void launch_add_cp(cpx* out, const cpx* in, int N, int cp, int cs, int ramp, const cpx* front, const cpx* back,
+                   int shift, size_t out_stride, size_t frames, cudaStream_t s);
+void launch_remove_cp(cpx* out, const cpx* in, int N, int cp, int cs, size_t frames, cudaStream_t s);
+void launch_copy_rows(cpx* out, const cpx* row, int len, size_t out_stride, size_t frames, cudaStream_t s);
+void launch_est_combine(cpx* H, const cpx* F, const cpx* inv0, const cpx* inv1, int K, size_t frames, cudaStream_t s);
+void launch_est_filter(cpx* filt, const cpx* H, const float* g, int K, int A, int dc_free, size_t frames, cudaStream_t s);
+void launch_est_interp(cpx* frame, const cpx* filt, int M, int K, int A, int dc_free, size_t frames, cudaStream_t s);
+void launch_est_snr(float* snr, float* cnrs, const cpx* F2, int K, int A, int dc_free, size_t frames, cudaStream_t s);
+void launch_zf_prepare(cpx* out, const cpx* in, size_t n, cudaStream_t s);
+void launch_energy(float* out, const cpx* in, size_t n, cudaStream_t s);
+
+} // namespace gfdm

@@ -1,0 +1,553 @@
+// stage_kernels.cu -- coalesced gather/scatter and elementwise stages.
+//
+// These kernels are (a) the final implementation of the integer / copy paths
+// (resource mapper, cyclic prefix, preamble copy, channel-estimator stages) and
+// (b) the building blocks of the any-shape modulator/receiver pipeline used
+// when no fused kernel exists for (M, K, L).  One thread per OUTPUT element, so
+// every global store is coalesced; scatters of the reference are restated as
+// gathers (no atomics).
+#include "engine.h"
+
+namespace gfdm {
+
+static constexpr unsigned TH = 256;
+
+// ---------------------------------------------------------------------------
+// modulator_kernel_cc::generic_work, lib/modulator_kernel_cc.cc:107-134, as a gather:
+// X[b*M+m] = sum_i T[((i+h)%L)*M+m] * D[((b-i+h) mod K)*M+m]   for m < part_len, else 0
+__global__ void __launch_bounds__(TH) mod_filter_kernel(cpx* __restrict__ X, const cpx* __restrict__ D,
+                                                        const cpx* __restrict__ taps, int M, int K, int L,
+                                                        int part_len, size_t total)
+{
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    const int N = M * K;
+    const size_t f = gid / N;
+    const int r = (int)(gid - f * N);
+    const int b = r / M, m = r - b * M;
+    cpx acc = cmake(0.f, 0.f);
+    if (m < part_len) {
+        const int h = L / 2;
+        const cpx* Df = D + f * N;
+        // same accumulation order as the reference's k-loop would produce for this bin
+        for (int i = L - 1; i >= 0; --i) {
+            int k = (b - i + h) % K;
+            if (k < 0) k += K;
+            acc = cadd(acc, cmul(Df[k * M + m], taps[((i + h) % L) * M + m]));
+        }
+    }
+    X[gid] = acc;
+}
+
+void launch_mod_filter(cpx* X, const cpx* D, const cpx* taps, int M, int K, int L, size_t frames, cudaStream_t s)
+{
+    const size_t total = frames * (size_t)M * K;
+    if (!total) return;
+    const int part_len = (M * L / 2 < M) ? M * L / 2 : M;
+    mod_filter_kernel<<<blocks_for(total, TH), TH, 0, s>>>(X, D, taps, M, K, L, part_len, total);
+    GFDM_CUDA_CHECK(cudaGetLastError());
+}
+
+// receiver_kernel_cc::filter_subcarriers_and_downsample_fd, lib/receiver_kernel_cc.cc:165-192
+__global__ void __launch_bounds__(TH) rx_filter_kernel(cpx* __restrict__ R, const cpx* __restrict__ Y,
+                                                       const cpx* __restrict__ taps, int M, int K, int L,
+                                                       size_t total)
+{
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    const int N = M * K;
+    const size_t f = gid / N;
+    const int r = (int)(gid - f * N);
+    const int k = r / M, m = r - k * M;
+    const int h = L / 2;
+    const cpx* Yf = Y + f * N;
+    cpx acc = cmake(0.f, 0.f);
+    for (int i = 0; i < L; ++i) {
+        const int src = ((k + i + K - h) % K) * M;
+        acc = cadd(acc, cmul(taps[((i + h) % L) * M + m], Yf[src + m]));
+    }
+    R[gid] = acc;
+}
+
+void launch_rx_filter(cpx* R, const cpx* Y, const cpx* taps, int M, int K, int L, size_t frames, cudaStream_t s)
+{
+    const size_t total = frames * (size_t)M * K;
+    if (!total) return;
+    rx_filter_kernel<<<blocks_for(total, TH), TH, 0, s>>>(R, Y, taps, M, K, L, total);
+    GFDM_CUDA_CHECK(cudaGetLastError());
+}
+
+// volk_32fc_x2_divide_32fc, lib/receiver_kernel_cc.cc:315
+__global__ void __launch_bounds__(TH) eq_divide_kernel(cpx* __restrict__ out, const cpx* __restrict__ Y,
+                                                       const cpx* __restrict__ eq, size_t n)
+{
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid < n) out[gid] = cdiv(Y[gid], eq[gid]);
+}
+void launch_eq_divide(cpx* out, const cpx* Y, const cpx* eq, size_t n, cudaStream_t s)
+{
+    if (!n) return;
+    eq_divide_kernel<<<blocks_for(n, TH), TH, 0, s>>>(out, Y, eq, n);
+    GFDM_CUDA_CHECK(cudaGetLastError());
+}
+
+// cancel_sc_interference, lib/receiver_kernel_cc.cc:279-286: td[(k-1)%K] + td[(k+1)%K]
+__global__ void __launch_bounds__(TH) neighbor_sum_kernel(cpx* __restrict__ out, const cpx* __restrict__ td, int M,
+                                                          int K, size_t total)
+{
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    const int N = M * K;
+    const size_t f = gid / N;
+    const int r = (int)(gid - f * N);
+    const int k = r / M, m = r - k * M;
+    const int prev = (k - 1 + K) % K, next = (k + 1) % K;
+    const cpx* t = td + f * N;
+    out[gid] = cadd(t[prev * M + m], t[next * M + m]);
+}
+void launch_neighbor_sum(cpx* out, const cpx* td, int M, int K, size_t frames, cudaStream_t s)
+{
+    const size_t total = frames * (size_t)M * K;
+    if (!total) return;
+    neighbor_sum_kernel<<<blocks_for(total, TH), TH, 0, s>>>(out, td, M, K, total);
+    GFDM_CUDA_CHECK(cudaGetLastError());
+}
+
+// lib/receiver_kernel_cc.cc:288-297: out = fd - ic_taps * F
+__global__ void __launch_bounds__(TH) ic_subtract_kernel(cpx* __restrict__ out, const cpx* __restrict__ fd,
+                                                         const cpx* __restrict__ F, const cpx* __restrict__ ic, int M,
+                                                         size_t total)
+{
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    const int m = (int)(gid % M);
+    out[gid] = csub(fd[gid], cmul(ic[m], F[gid]));
+}
+void launch_ic_subtract(cpx* out, const cpx* fd, const cpx* F, const cpx* ic_taps, int M, int K, size_t frames,
+                        cudaStream_t s)
+{
+    const size_t total = frames * (size_t)M * K;
+    if (!total) return;
+    ic_subtract_kernel<<<blocks_for(total, TH), TH, 0, s>>>(out, fd, F, ic_taps, M, total);
+    GFDM_CUDA_CHECK(cudaGetLastError());
+}
+
+// map_symbols_to_constellation_points, lib/advanced_receiver_kernel_cc.cc:109-123
+__device__ __forceinline__ int decide_symbol(cpx s, const cpx* __restrict__ points, int n_points, int rule)
+{
+    if (rule == 1) return 2 * (s.y > 0.f) + (s.x > 0.f);
+    int best = 0;
+    float dmin = 0.f;
+    for (int i = 0; i < n_points; ++i) {
+        const float dr = __fsub_rn(s.x, points[i].x), di = __fsub_rn(s.y, points[i].y);
+        const float d = __fadd_rn(__fmul_rn(dr, dr), __fmul_rn(di, di));
+        if (i == 0 || d < dmin) {
+            dmin = d;
+            best = i;
+        }
+    }
+    return best;
+}
+
+__global__ void __launch_bounds__(TH) decide_kernel(cpx* __restrict__ out, const cpx* __restrict__ in,
+                                                    const unsigned char* __restrict__ active,
+                                                    const cpx* __restrict__ points, int n_points, int rule, int M,
+                                                    int K, size_t total)
+{
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    const int k = (int)((gid / M) % K);
+    cpx v = cmake(0.f, 0.f);
+    if (active[k]) v = points[decide_symbol(in[gid], points, n_points, rule)];
+    out[gid] = v;
+}
+void launch_decide(cpx* out, const cpx* in, const unsigned char* active, const cpx* points, int n_points, int rule,
+                   int M, int K, size_t frames, cudaStream_t s)
+{
+    const size_t total = frames * (size_t)M * K;
+    if (!total) return;
+    decide_kernel<<<blocks_for(total, TH), TH, 0, s>>>(out, in, active, points, n_points, rule, M, K, total);
+    GFDM_CUDA_CHECK(cudaGetLastError());
+}
+
+// calculate_phase_offset + rotator, lib/advanced_receiver_kernel_cc.cc:61-91.
+// One CTA per frame: block-reduce mean(arg(decided) - arg(soft)) over the map
+// (duplicates in the map count twice, as in the reference), then rotate the
+// kept frequency block in place.
+__global__ void __launch_bounds__(256) phase_rotate_kernel(cpx* __restrict__ R, const cpx* __restrict__ decided,
+                                                           const cpx* __restrict__ soft, const int* __restrict__ smap,
+                                                           int n_map, int M, int K)
+{
+    __shared__ float red[256];
+    __shared__ cpx rot;
+    const size_t f = blockIdx.x;
+    const int N = M * K;
+    const cpx* d = decided + f * N;
+    const cpx* y = soft + f * N;
+    float acc = 0.f;
+    const int total = n_map * M;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const int a = i / M, m = i - a * M;
+        const int pos = smap[a] * M + m;
+        acc += atan2f(d[pos].y, d[pos].x) - atan2f(y[pos].y, y[pos].x);
+    }
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int sft = 128; sft > 0; sft >>= 1) {
+        if ((int)threadIdx.x < sft) red[threadIdx.x] += red[threadIdx.x + sft];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const float ph = red[0] / (float)((size_t)n_map * (size_t)M);
+        float sn, cs;
+        sincosf(ph, &sn, &cs);
+        rot = cmake(cs, sn);
+    }
+    __syncthreads();
+    const cpx w = rot;
+    cpx* r = R + f * N;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) r[i] = cmul(r[i], w);
+}
+void launch_phase_rotate(cpx* R, const cpx* decided, const cpx* soft, const int* smap, int n_map, int M, int K,
+                         size_t frames, cudaStream_t s)
+{
+    if (!frames) return;
+    phase_rotate_kernel<<<(unsigned)frames, 256, 0, s>>>(R, decided, soft, smap, n_map, M, K);
+    GFDM_CUDA_CHECK(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------
+// resource_mapper_kernel_cc::map_to_resources, lib/resource_mapper_kernel_cc.cc:74-134,
+// as a gather over the K x M grid: inv_map[k] = position of k in the sorted map or -1.
+__global__ void __launch_bounds__(TH) map_kernel(cpx* __restrict__ out, const cpx* __restrict__ in,
+                                                 const int* __restrict__ inv_map, int M, int K, int A,
+                                                 int per_timeslot, size_t n_in, size_t in_stride, size_t total)
+{
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    const int N = M * K;
+    const size_t f = gid / N;
+    const int r = (int)(gid - f * N);
+    const int k = r / M, t = r - k * M;
+    const int a = inv_map[k];
+    cpx v = cmake(0.f, 0.f);
+    if (a >= 0) {
+        const size_t src = per_timeslot ? (size_t)t * A + a : (size_t)a * M + t;
+        if (src < n_in) v = in[f * in_stride + src];
+    }
+    out[gid] = v;
+}
+void launch_map(cpx* out, const cpx* in, const int* inv_map, int M, int K, int A, bool per_timeslot, size_t n_in,
+                size_t in_stride, size_t frames, cudaStream_t s)
+{
+    const size_t total = frames * (size_t)M * K;
+    if (!total) return;
+    map_kernel<<<blocks_for(total, TH), TH, 0, s>>>(out, in, inv_map, M, K, A, per_timeslot ? 1 : 0, n_in, in_stride,
+                                                    total);
+    GFDM_CUDA_CHECK(cudaGetLastError());
+}
+
+// demap_from_resources, lib/resource_mapper_kernel_cc.cc:91-106,136-162.  Writes exactly
+// n_out symbols per frame (the reference's one-past write in the per-subcarrier
+// branch is an overflow of the caller's buffer and is deliberately not reproduced).
+__global__ void __launch_bounds__(TH) demap_kernel(cpx* __restrict__ out, const cpx* __restrict__ in,
+                                                   const int* __restrict__ smap, int M, int K, int A, int per_timeslot,
+                                                   size_t n_out, size_t out_stride, size_t total)
+{
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    const size_t f = gid / n_out;
+    const size_t i = gid - f * n_out;
+    int a, t;
+    if (per_timeslot) {
+        t = (int)(i / A);
+        a = (int)(i - (size_t)t * A);
+    } else {
+        a = (int)(i / M);
+        t = (int)(i - (size_t)a * M);
+    }
+    out[f * out_stride + i] = in[f * (size_t)M * K + (size_t)M * smap[a] + t];
+}
+void launch_demap(cpx* out, const cpx* in, const int* smap, int M, int K, int A, bool per_timeslot, size_t n_out,
+                  size_t out_stride, size_t frames, cudaStream_t s)
+{
+    const size_t total = frames * n_out;
+    if (!total) return;
+    demap_kernel<<<blocks_for(total, TH), TH, 0, s>>>(out, in, smap, M, K, A, per_timeslot ? 1 : 0, n_out, out_stride,
+                                                      total);
+    GFDM_CUDA_CHECK(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------
+// add_cyclic_prefix_cc::add_cyclic_prefix, lib/add_cyclic_prefix_cc.cc:67-98:
+// o[i] = x[(i + N - cp - s) mod N], first/last ramp samples times the ramp
+// (complex x complex, unfused, reference operand order -> bit-exact).
+__global__ void __launch_bounds__(TH) add_cp_kernel(cpx* __restrict__ out, const cpx* __restrict__ in, int N, int cp,
+                                                    int cs, int ramp, const cpx* __restrict__ front,
+                                                    const cpx* __restrict__ back, int shift, size_t out_stride,
+                                                    size_t total)
+{
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    const int W = N + cp + cs;
+    const size_t f = gid / W;
+    const int i = (int)(gid - f * W);
+    int src = i + N - cp - shift;
+    while (src >= N) src -= N;
+    cpx v = in[f * N + src];
+    if (i < ramp) v = cmul_rn(v, front[i]);
+    if (i >= W - ramp) v = cmul_rn(v, back[i - (W - ramp)]);
+    out[f * out_stride + i] = v;
+}
+void launch_add_cp(cpx* out, const cpx* in, int N, int cp, int cs, int ramp, const cpx* front, const cpx* back,
+                   int shift, size_t out_stride, size_t frames, cudaStream_t s)
+{
+    const size_t total = frames * (size_t)(N + cp + cs);
+    if (!total) return;
+    add_cp_kernel<<<blocks_for(total, TH), TH, 0, s>>>(out, in, N, cp, cs, ramp, front, back, shift, out_stride, total);
+    GFDM_CUDA_CHECK(cudaGetLastError());
+}
+
+// remove_cyclic_prefix, lib/add_cyclic_prefix_cc.cc:100-104
+__global__ void __launch_bounds__(TH) remove_cp_kernel(cpx* __restrict__ out, const cpx* __restrict__ in, int N,
+                                                       int cp, int W, size_t total)
+{
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    const size_t f = gid / N;
+    const int i = (int)(gid - f * N);
+    out[gid] = in[f * W + cp + i];
+}
+void launch_remove_cp(cpx* out, const cpx* in, int N, int cp, int cs, size_t frames, cudaStream_t s)
+{
+    const size_t total = frames * (size_t)N;
+    if (!total) return;
+    remove_cp_kernel<<<blocks_for(total, TH), TH, 0, s>>>(out, in, N, cp, N + cp + cs, total);
+    GFDM_CUDA_CHECK(cudaGetLastError());
+}
+
+// transmitter_kernel::insert_preamble, lib/transmitter_kernel.cc:86-90
+__global__ void __launch_bounds__(TH) copy_rows_kernel(cpx* __restrict__ out, const cpx* __restrict__ row, int len,
+                                                       size_t out_stride, size_t total)
+{
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    const size_t f = gid / len;
+    const int i = (int)(gid - f * len);
+    out[f * out_stride + i] = row[i];
+}
+void launch_copy_rows(cpx* out, const cpx* row, int len, size_t out_stride, size_t frames, cudaStream_t s)
+{
+    const size_t total = frames * (size_t)len;
+    if (!total) return;
+    copy_rows_kernel<<<blocks_for(total, TH), TH, 0, s>>>(out, row, len, out_stride, total);
+    GFDM_CUDA_CHECK(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------
+// preamble_channel_estimator_cc, lib/preamble_channel_estimator_cc.cc
+// :121-143  H = F0 * inv0 + F1 * inv1   (F = [frames][2][K])
+__global__ void __launch_bounds__(TH) est_combine_kernel(cpx* __restrict__ H, const cpx* __restrict__ F,
+                                                         const cpx* __restrict__ inv0, const cpx* __restrict__ inv1,
+                                                         int K, size_t total)
+{
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    const size_t f = gid / K;
+    const int q = (int)(gid - f * K);
+    const cpx a = cmul_rn(F[f * 2 * K + q], inv0[q]);
+    const cpx b = cmul_rn(F[f * 2 * K + K + q], inv1[q]);
+    H[gid] = cmake(__fadd_rn(b.x, a.x), __fadd_rn(b.y, a.y));
+}
+void launch_est_combine(cpx* H, const cpx* F, const cpx* inv0, const cpx* inv1, int K, size_t frames, cudaStream_t s)
+{
+    const size_t total = frames * (size_t)K;
+    if (!total) return;
+    est_combine_kernel<<<blocks_for(total, TH), TH, 0, s>>>(H, F, inv0, inv1, K, total);
+    GFDM_CUDA_CHECK(cudaGetLastError());
+}
+
+// :145-185  reorder + edge replicate + 9-tap Gaussian correlation
+__device__ __forceinline__ cpx est_padded(const cpx* __restrict__ H, int j, int K, int A, int off)
+{
+    const int G2 = 4, Ah = A / 2;
+    if (j < G2) return H[K - Ah];
+    j -= G2;
+    if (j < Ah) return H[j + K - Ah];
+    if (off && j == Ah) {
+        const cpx a = H[K - 1], b = H[1];
+        return cmake((a.x + b.x) / 2.0f, (a.y + b.y) / 2.0f);
+    }
+    j -= Ah + off;
+    if (j < Ah) return H[off + j];
+    return H[off + Ah - 1];
+}
+__global__ void __launch_bounds__(TH) est_filter_kernel(cpx* __restrict__ filt, const cpx* __restrict__ H,
+                                                        const float* __restrict__ g, int K, int A, int off,
+                                                        size_t total)
+{
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    const int n_taps = A + off;
+    const size_t f = gid / n_taps;
+    const int i = (int)(gid - f * n_taps);
+    const cpx* Hf = H + f * K;
+    float re = 0.f, im = 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+        const cpx v = est_padded(Hf, i + t, K, A, off);
+        re = __fadd_rn(re, __fmul_rn(v.x, g[t]));
+        im = __fadd_rn(im, __fmul_rn(v.y, g[t]));
+    }
+    filt[gid] = cmake(re, im);
+}
+void launch_est_filter(cpx* filt, const cpx* H, const float* g, int K, int A, int dc_free, size_t frames,
+                       cudaStream_t s)
+{
+    const int off = dc_free ? 1 : 0;
+    const size_t total = frames * (size_t)(A + off);
+    if (!total) return;
+    est_filter_kernel<<<blocks_for(total, TH), TH, 0, s>>>(filt, H, g, K, A, off, total);
+    GFDM_CUDA_CHECK(cudaGetLastError());
+}
+
+// :238-274  piecewise-linear K -> N bins; one thread per output bin replays the
+// reference's running float sum (factor += inc, j times) so results match bit
+// for bit; later loops of the reference overwrite earlier ones, hence the
+// reverse priority below.  Bins no loop writes are left untouched.
+__global__ void __launch_bounds__(TH) est_interp_kernel(cpx* __restrict__ frame, const cpx* __restrict__ filt, int M,
+                                                        int K, int A, int off, size_t total)
+{
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    const int N = M * K;
+    const size_t f = gid / N;
+    const int b = (int)(gid - f * N);
+    const int n_est = A + off;
+    const int center = N / 2;
+    const int dead_half = M * (K - A) / 2;
+    const cpx* e = filt + f * n_est;
+    const int half = n_est / 2;
+    int seg = -1, j = 0;
+    cpx fill;
+    bool write = false, is_fill = false;
+    if (b < (n_est - 1 - half) * M) { // last loop: i in [half, n_est-1)
+        seg = half + b / M;
+        j = b % M;
+        write = true;
+    } else if (b >= center + dead_half && b < center + dead_half + half * M) { // i in [0, half)
+        seg = (b - center - dead_half) / M;
+        j = (b - center - dead_half) % M;
+        write = true;
+    } else if (b >= M * A / 2 && b < center) {
+        fill = e[n_est - 1];
+        write = is_fill = true;
+    } else if (b >= center && b < center + dead_half) {
+        fill = e[0];
+        write = is_fill = true;
+    }
+    if (!write) return;
+    if (is_fill) {
+        frame[gid] = fill;
+        return;
+    }
+    const float step = 1.0f / (float)M;
+    const cpx d = csub(e[seg + 1], e[seg]);
+    // (estimate[i+1] - estimate[i]) * gfdm_complex(step, 0): complex x complex, unfused
+    const cpx inc = cmake(__fsub_rn(__fmul_rn(d.x, step), __fmul_rn(d.y, 0.0f)),
+                          __fadd_rn(__fmul_rn(d.x, 0.0f), __fmul_rn(d.y, step)));
+    cpx factor = e[seg];
+    for (int t = 0; t < j; ++t) factor = cmake(__fadd_rn(factor.x, inc.x), __fadd_rn(factor.y, inc.y));
+    frame[gid] = factor;
+}
+void launch_est_interp(cpx* frame, const cpx* filt, int M, int K, int A, int dc_free, size_t frames, cudaStream_t s)
+{
+    const size_t total = frames * (size_t)M * K;
+    if (!total) return;
+    est_interp_kernel<<<blocks_for(total, TH), TH, 0, s>>>(frame, filt, M, K, A, dc_free ? 1 : 0, total);
+    GFDM_CUDA_CHECK(cudaGetLastError());
+}
+
+// :187-235  one CTA per frame; F2 = FFT_2K(rx)
+__global__ void __launch_bounds__(256) est_snr_kernel(float* __restrict__ snr, float* __restrict__ cnrs,
+                                                      const cpx* __restrict__ F2, int K, int A, int off)
+{
+    __shared__ float rs[256], rn[256];
+    __shared__ float s_scale;
+    const size_t f = blockIdx.x;
+    const cpx* F = F2 + f * 2 * K;
+    const int half = A / 2;
+    const int low_offset = (K - A) / 2 + K / 2;
+    float se = 0.f, ne = 0.f;
+    for (int i = threadIdx.x; i < 2 * half; i += blockDim.x) {
+        const int pos = (i < half) ? 2 * (i + off) : 2 * (i - half + low_offset);
+        const cpx a = F[pos], b = F[pos + 1];
+        se += a.x * a.x + a.y * a.y;
+        ne += b.x * b.x + b.y * b.y;
+    }
+    rs[threadIdx.x] = se;
+    rn[threadIdx.x] = ne;
+    __syncthreads();
+    for (int sft = 128; sft > 0; sft >>= 1) {
+        if ((int)threadIdx.x < sft) {
+            rs[threadIdx.x] += rs[threadIdx.x + sft];
+            rn[threadIdx.x] += rn[threadIdx.x + sft];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const float v = (rs[0] - rn[0]) / rn[0];
+        snr[f] = v;
+        s_scale = v / (rs[0] / (float)A);
+    }
+    __syncthreads();
+    if (cnrs) {
+        const float sc = s_scale;
+        for (int i = threadIdx.x; i < 2 * half; i += blockDim.x) {
+            const int pos = (i < half) ? 2 * (i + off) : 2 * (i - half + low_offset);
+            const cpx a = F[pos];
+            cnrs[f * A + i] = (a.x * a.x + a.y * a.y) * sc;
+        }
+    }
+}
+void launch_est_snr(float* snr, float* cnrs, const cpx* F2, int K, int A, int dc_free, size_t frames, cudaStream_t s)
+{
+    if (!frames) return;
+    est_snr_kernel<<<(unsigned)frames, 256, 0, s>>>(snr, cnrs, F2, K, A, dc_free ? 1 : 0);
+    GFDM_CUDA_CHECK(cudaGetLastError());
+}
+
+// prepare_for_zf, :276-282: conj(1 / h)
+__global__ void __launch_bounds__(TH) zf_prepare_kernel(cpx* __restrict__ out, const cpx* __restrict__ in, size_t n)
+{
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid < n) out[gid] = cconj(cdiv(cmake(1.f, 0.f), in[gid]));
+}
+void launch_zf_prepare(cpx* out, const cpx* in, size_t n, cudaStream_t s)
+{
+    if (!n) return;
+    zf_prepare_kernel<<<blocks_for(n, TH), TH, 0, s>>>(out, in, n);
+    GFDM_CUDA_CHECK(cudaGetLastError());
+}
+
+// gfdm_kernel_utils::calculate_signal_energy, lib/gfdm_kernel_utils.cc:59-65 (single CTA)
+__global__ void __launch_bounds__(1024) energy_kernel(float* __restrict__ out, const cpx* __restrict__ in, size_t n)
+{
+    __shared__ float red[1024];
+    float acc = 0.f;
+    for (size_t i = threadIdx.x; i < n; i += blockDim.x) acc += in[i].x * in[i].x + in[i].y * in[i].y;
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int sft = 512; sft > 0; sft >>= 1) {
+        if ((int)threadIdx.x < sft) red[threadIdx.x] += red[threadIdx.x + sft];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = red[0];
+}
+void launch_energy(float* out, const cpx* in, size_t n, cudaStream_t s)
+{
+    energy_kernel<<<1, 1024, 0, s>>>(out, in, n);
+    GFDM_CUDA_CHECK(cudaGetLastError());
+}
+
+} // namespace gfdm
