@@ -73,6 +73,8 @@ struct HandleBase {
     void sync() { GFDM_CUDA_CHECK(cudaStreamSynchronize(stream)); }
 };
 
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
 static std::vector<cf> vec(const gfdm_complex* p, int n)
 {
     return std::vector<cf>(reinterpret_cast<const cf*>(p), reinterpret_cast<const cf*>(p) + (n > 0 ? n : 0));
@@ -275,11 +277,13 @@ struct gfdm_modulator : HandleBase {
 static void modulator_run(gfdm_modulator* h, cpx* out, const cpx* in, size_t frames)
 {
     if (!frames) return;
-    if (h->fused.available()) {
+    if (h->fused.available() && aligned16(in)) { // cp.async.bulk needs 16-byte aligned global addresses
         h->launches += h->fused.modulate(out, in, frames, h->stream);
         h->last_kernel = h->fused.mod_name();
         return;
     }
+    if (h->fft_m.n == 0) h->fft_m.init(h->M);
+    if (h->fft_n.n == 0) h->fft_n.init(h->N);
     const size_t el = frames * (size_t)h->N;
     h->work_a.ensure(el * sizeof(cpx));
     h->work_b.ensure(el * sizeof(cpx));
@@ -303,10 +307,6 @@ int gfdm_modulator_create(gfdm_modulator** out, int M, int K, int L, const gfdm_
     h->open();
     h->d_taps = dev_upload(h->taps);
     h->fused.init_tx(M, K, L, h->taps);
-    if (!h->fused.available()) {
-        h->fft_m.init(M);
-        h->fft_n.init(h->N);
-    }
     *out = h.release();
     API_CATCH
 }
@@ -379,7 +379,6 @@ static void receiver_init(gfdm_receiver* h, int M, int K, int L, const std::vect
     h->d_ic = dev_upload(h->ic_taps);
     h->fused.init_rx(M, K, L, h->taps, h->ic_taps);
     h->fft_m.init(M);
-    if (!h->fused.available()) h->fft_n.init(h->N);
 }
 static void receiver_free(gfdm_receiver* h)
 {
@@ -396,11 +395,12 @@ static void receiver_free(gfdm_receiver* h)
 static void receiver_fd(gfdm_receiver* h, cpx* R, const cpx* in, const cpx* eq, size_t frames)
 {
     if (!frames) return;
-    if (h->fused.available()) {
+    if (h->fused.available() && aligned16(R)) {
         h->launches += h->fused.demodulate(nullptr, R, in, eq, frames, h->stream);
         h->last_kernel = h->fused.rx_name();
         return;
     }
+    if (h->fft_n.n == 0) h->fft_n.init(h->N);
     const size_t el = frames * (size_t)h->N;
     h->work_a.ensure(el * sizeof(cpx));
     h->work_b.ensure(el * sizeof(cpx));
@@ -427,7 +427,7 @@ static void receiver_td(gfdm_receiver* h, cpx* out, const cpx* R, size_t frames)
 static void receiver_run(gfdm_receiver* h, cpx* out, const cpx* in, const cpx* eq, size_t frames)
 {
     if (!frames) return;
-    if (h->fused.available()) {
+    if (h->fused.available() && aligned16(out)) {
         h->launches += h->fused.demodulate(out, nullptr, in, eq, frames, h->stream);
         h->last_kernel = h->fused.rx_name();
         return;
@@ -1169,10 +1169,12 @@ static void tx_modulate(gfdm_transmitter* h, cpx* blk, const cpx* in, size_t nin
     cpx* mp = h->mapped.as<cpx>();
     launch_map(mp, in, h->map.d_inv, h->M, h->K, h->map.A, h->map.per_timeslot, nin, nin, frames, h->stream);
     h->launches += 1;
-    if (h->fused.available()) {
+    if (h->fused.available()) { // `mapped` is our own 256-byte aligned buffer
         h->launches += h->fused.modulate(blk, mp, frames, h->stream);
         return;
     }
+    if (h->fft_m.n == 0) h->fft_m.init(h->M);
+    if (h->fft_n.n == 0) h->fft_n.init(h->N);
     h->work_a.ensure(el * sizeof(cpx));
     h->work_b.ensure(el * sizeof(cpx));
     cpx* A = h->work_a.as<cpx>();
@@ -1221,10 +1223,6 @@ int gfdm_transmitter_create(gfdm_transmitter** out, int M, int K, int A, int cp,
     h->pre.to_device();
     h->d_taps = dev_upload(h->taps);
     h->fused.init_tx(M, K, L, h->taps);
-    if (!h->fused.available()) {
-        h->fft_m.init(M);
-        h->fft_n.init(h->N);
-    }
     std::vector<cf> all;
     for (int i = 0; i < n_preambles; ++i) {
         std::vector<cf> p = vec(preambles[i], preamble_sizes[i]);

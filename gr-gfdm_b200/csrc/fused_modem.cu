@@ -1,13 +1,616 @@
-// fused_modem.cu -- placeholder: no fused shapes registered yet (filled in next).
+// fused_modem.cu -- single-kernel GFDM modulator and receiver, one frame group
+// resident in shared memory per CTA (sm_100a).
+//
+// Factorisation (checked in NumPy by tools/fused_math_check.py).
+// With bin index b*M+m and sample index n1 + K*n2:
+//
+//   modulator  (replaces lib/modulator_kernel_cc.cc:98-141)
+//     D_b[m]   = FFT_M(d_b)                       stage A   thread <-> subcarrier, registers
+//     Z_m[n1]  = IFFT_K over b of D_b[m]          stage B   row FFTs in shared memory
+//     x[n1+K*n2] = IFFT_M over m of C_tx[m][n1]*Z_m[n1]     stage C   thread <-> n1, registers
+//   where C_tx[m][n1] = (sum_i T[((i+h)%L)M+m] e^{+j2pi(i-h)n1/K}) e^{+j2pi m n1/N} / N folds the
+//   L-fold spectral repetition, the pulse-shaping taps, the scatter-add into the N-bin grid,
+//   the N-point twiddle and the 1/N scale into ONE table multiply (a circular shift over b is a
+//   phase ramp over n1).
+//
+//   receiver   (replaces lib/receiver_kernel_cc.cc:165-225,301-334)
+//     U_n1[m]  = FFT_M over n2 of x[n1+K*n2]      stage A'  thread <-> n1, registers
+//     V_m[k]   = FFT_K over n1 of C_rx[m][n1]*U_n1[m]       stage B
+//     y_k      = IFFT_M(R_k)/M, R_k[m] = V_m[k]             stage C'  thread <-> subcarrier
+//   without equalisation C_rx carries the receive taps as well; with equalisation C_rx is the
+//   plain twiddle, Y = V / H_eq is formed bin by bin and the L neighbouring parts are combined
+//   explicitly (the division sits between FFT and filter, receiver_kernel_cc.cc:315-319).
+//
+// Data movement: [k][m]-ordered arrays (modulator input, receiver output) cross HBM through
+// cp.async.bulk (TMA 1D) into / out of shared memory, so every byte moves in 128 B lines;
+// [n2][n1]-ordered arrays (time samples) are accessed directly, lanes = consecutive n1.
+// The CTA is persistent (grid = SMs x occupancy) and the modulator issues the bulk load of the
+// next frame group as soon as the last shared-memory read of the current one has retired.
 #include "fused.h"
+#include "regfft.cuh"
+
+#include <cmath>
+#include <cstring>
+
 namespace gfdm {
-struct FusedImpl {};
-void FusedModem::init_tx(int, int, int, const std::vector<std::complex<float>>&) { impl_ = nullptr; }
-void FusedModem::init_rx(int, int, int, const std::vector<std::complex<float>>&,
-                         const std::vector<std::complex<float>>&) { impl_ = nullptr; }
-int FusedModem::modulate(cpx*, const cpx*, size_t, cudaStream_t) { return 0; }
-int FusedModem::demodulate(cpx*, cpx*, const cpx*, const cpx*, size_t, cudaStream_t) { return 0; }
-const char* FusedModem::mod_name() const { return "none"; }
-const char* FusedModem::rx_name() const { return "none"; }
-void FusedModem::destroy() { impl_ = nullptr; }
+
+// ----------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + 1D bulk async copy (TMA)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* gdst, const void* smem_src, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)),
+                 "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ cpx ldg_nc(const cpx* p)
+{
+    return __ldg(reinterpret_cast<const float2*>(p));
+}
+// streaming global accesses: every input byte is read once, every output byte written once
+__device__ __forceinline__ cpx ldg_stream(const cpx* p)
+{
+    float2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void stg_stream(cpx* p, cpx v)
+{
+    asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
+}
+
+// ----------------------------------------------------------------------------------------
+// compile-time shape of one fused kernel
+template <int M_, int R1_, int R2_, int T_, int IPT_>
+struct Shape {
+    static constexpr int M = M_, R1 = R1_, R2 = R2_, T = T_, IPT = IPT_;
+    static constexpr int K = R1 * R2;
+    static constexpr int N = M * K;
+    static constexpr int F = IPT * T / K; // frames per CTA pass
+    static_assert(IPT * T % K == 0 && F >= 1, "threads x items must cover whole frames");
+    static_assert(32 % R1 == 0 || R1 % 32 == 0, "R1 must divide the warp");
+    static constexpr bool TWO_PASS = R2 > 1;
+    // row stride (complex elements): two-pass rows are padded by one element per R2 block so that
+    // both passes are bank-conflict free; single-pass rows get an odd stride
+    static constexpr int RS = TWO_PASS ? R1 * (R2 + 1) : (K | 1);
+    static constexpr int ROWS = F * M;
+    static constexpr int ROW_ELEMS = ROWS * RS;
+    static constexpr int STAGE_ELEMS = F * N;
+    static constexpr int BUF_ELEMS = ROW_ELEMS > STAGE_ELEMS ? ROW_ELEMS : STAGE_ELEMS;
+    static constexpr int TW_ELEMS = TWO_PASS ? K : 0;
+    static constexpr size_t SMEM_BYTES = sizeof(cpx) * (size_t)(BUF_ELEMS + TW_ELEMS) + 64 /* taps hdr + mbarrier */;
+    __host__ __device__ static constexpr int addr1(int n) { return TWO_PASS ? n + n / R2 : n; } // row-FFT input slot
+};
+
+// Row FFTs over the K-long rows held in shared memory (in place; input at addr1(), output natural).
+template <class S, int DIR>
+__device__ __forceinline__ void row_fft(cpx* __restrict__ buf, const cpx* __restrict__ tw_s, int tid)
+{
+    constexpr int R1 = S::R1, R2 = S::R2, RS = S::RS, T = S::T;
+    if constexpr (!S::TWO_PASS) {
+        for (int it = tid; it < S::ROWS; it += T) {
+            cpx* row = buf + it * RS;
+            cpx a[R1];
+#pragma unroll
+            for (int i = 0; i < R1; ++i) a[i] = row[i];
+            rf::FFTN<R1, DIR>::run(a);
+#pragma unroll
+            for (int i = 0; i < R1; ++i) row[i] = a[i];
+        }
+    } else {
+        // pass 1: item (row, n0): radix-R1 over x[R2*n1 + n0], then W_K^{n0*k1}; in place
+        constexpr int ITEMS1 = S::ROWS * R2;
+        for (int it = tid; it < ITEMS1; it += T) {
+            const int row = it / R2, n0 = it - row * R2;
+            cpx* p = buf + row * RS + n0;
+            cpx a[R1];
+#pragma unroll
+            for (int i = 0; i < R1; ++i) a[i] = p[(R2 + 1) * i];
+            rf::FFTN<R1, DIR>::run(a);
+#pragma unroll
+            for (int i = 1; i < R1; ++i) {
+                cpx w = tw_s[i * R2 + n0];
+                if (DIR > 0) w.y = -w.y;
+                a[i] = cmul(a[i], w);
+            }
+#pragma unroll
+            for (int i = 0; i < R1; ++i) p[(R2 + 1) * i] = a[i];
+        }
+        if constexpr (R1 == R2) __syncwarp(); else __syncthreads();
+        // pass 2: item (row, k1): radix-R2 over A[n0][k1]; result X[k1 + R1*k0] stored at natural index.
+        // A row is owned by one warp (R1 divides 32), so a warp-level barrier orders its reads and writes.
+        constexpr int ITEMS2 = S::ROWS * R1;
+        constexpr int ITERS2 = (ITEMS2 + T - 1) / T;
+#pragma unroll 1
+        for (int ii = 0; ii < ITERS2; ++ii) {
+            const int it = tid + ii * T;
+            const bool act = it < ITEMS2;
+            const int row = it / R1, k1 = it - row * R1;
+            cpx* r = buf + row * RS;
+            cpx b[R2];
+            if (act) {
+#pragma unroll
+                for (int i = 0; i < R2; ++i) b[i] = r[(R2 + 1) * k1 + i];
+                rf::FFTN<R2, DIR>::run(b);
+            }
+            __syncwarp();
+            if (act) {
+#pragma unroll
+                for (int i = 0; i < R2; ++i) r[k1 + R1 * i] = b[i];
+            }
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------
+// Fused modulator.  in/out: [n_frames][N]; table: C_tx [M][K]; tw: W_K^{n0*k1} as [k1][n0].
+template <class S>
+__global__ void __launch_bounds__(S::T, 1) fused_mod_kernel(cpx* __restrict__ out, const cpx* __restrict__ in,
+                                                            const cpx* __restrict__ table, const cpx* __restrict__ tw,
+                                                            int n_frames)
+{
+    constexpr int M = S::M, K = S::K, N = S::N, T = S::T, IPT = S::IPT, F = S::F, RS = S::RS;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    cpx* buf = reinterpret_cast<cpx*>(smem_raw);
+    cpx* tw_s = buf + S::BUF_ELEMS;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + sizeof(cpx) * (S::BUF_ELEMS + S::TW_ELEMS));
+    const int tid = threadIdx.x;
+    const int n_groups = (n_frames + F - 1) / F;
+
+    for (int i = tid; i < S::TW_ELEMS; i += T) tw_s[i] = tw[i];
+    if (tid == 0) mbar_init(bar, 1);
+    __syncthreads();
+
+    int g = blockIdx.x;
+    if (tid == 0 && g < n_groups) {
+        const int fh = min(F, n_frames - g * F);
+        const uint32_t bytes = (uint32_t)fh * N * sizeof(cpx);
+        mbar_expect_tx(bar, bytes);
+        bulk_load(buf, in + (size_t)g * F * N, bytes, bar);
+    }
+    uint32_t phase = 0;
+    for (; g < n_groups; g += gridDim.x) {
+        const int fh = min(F, n_frames - g * F);
+        mbar_wait(bar, phase);
+        phase ^= 1;
+
+        cpx v[IPT][M];
+        // ---- stage A: subcarrier symbols from the staged [k][m] block -> registers
+#pragma unroll
+        for (int j = 0; j < IPT; ++j) {
+            const int it = tid + j * T;
+            const cpx* src = buf + (size_t)it * M; // (f*K + k)*M
+#pragma unroll
+            for (int m = 0; m < M; ++m) v[j][m] = src[m];
+        }
+        __syncthreads(); // staging fully consumed; the row layout may now overwrite it
+#pragma unroll
+        for (int j = 0; j < IPT; ++j) {
+            const int it = tid + j * T;
+            const int f = it / K, k = it - f * K;
+            rf::FFTN<M, -1>::run(v[j]);
+            cpx* dst = buf + (size_t)f * M * RS + S::addr1(k);
+#pragma unroll
+            for (int m = 0; m < M; ++m) dst[m * RS] = v[j][m];
+        }
+        __syncthreads();
+        // ---- stage B: K-point inverse FFT of every row (over the subcarrier index)
+        row_fft<S, +1>(buf, tw_s, tid);
+        __syncthreads();
+        // ---- stage C: column n1 of all rows -> registers
+#pragma unroll
+        for (int j = 0; j < IPT; ++j) {
+            const int it = tid + j * T;
+            const int f = it / K, n1 = it - f * K;
+            const cpx* src = buf + (size_t)f * M * RS + n1;
+#pragma unroll
+            for (int m = 0; m < M; ++m) v[j][m] = src[m * RS];
+        }
+        __syncthreads(); // shared memory is dead: prefetch the next group while stage C computes and stores
+        const int gn = g + gridDim.x;
+        if (tid == 0 && gn < n_groups) {
+            const int fhn = min(F, n_frames - gn * F);
+            const uint32_t bytes = (uint32_t)fhn * N * sizeof(cpx);
+            fence_proxy_async();
+            mbar_expect_tx(bar, bytes);
+            bulk_load(buf, in + (size_t)gn * F * N, bytes, bar);
+        }
+#pragma unroll
+        for (int j = 0; j < IPT; ++j) {
+            const int it = tid + j * T;
+            const int f = it / K, n1 = it - f * K;
+#pragma unroll
+            for (int m = 0; m < M; ++m) v[j][m] = cmul(v[j][m], ldg_nc(table + m * K + n1));
+            rf::FFTN<M, +1>::run(v[j]);
+            if (f < fh) {
+                cpx* dst = out + ((size_t)g * F + f) * N + n1;
+#pragma unroll
+                for (int n2 = 0; n2 < M; ++n2) stg_stream(dst + (size_t)n2 * K, v[j][n2]);
+            }
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------
+// Fused receiver.  in: [n_frames][N] time samples; eq: per-bin channel or nullptr;
+// out: [n_frames][N]; mode 0: soft symbols y (generic_work[_equalize]); mode 1: R (fft_[equalize_]filter_downsample).
+template <class S>
+__global__ void __launch_bounds__(S::T, 1) fused_rx_kernel(cpx* __restrict__ out, const cpx* __restrict__ in,
+                                                           const cpx* __restrict__ eq, const cpx* __restrict__ table,
+                                                           const cpx* __restrict__ tw, const cpx* __restrict__ taps,
+                                                           int L, int mode, int n_frames)
+{
+    constexpr int M = S::M, K = S::K, N = S::N, T = S::T, IPT = S::IPT, F = S::F, RS = S::RS;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    cpx* buf = reinterpret_cast<cpx*>(smem_raw);
+    cpx* tw_s = buf + S::BUF_ELEMS;
+    const int tid = threadIdx.x;
+    const int n_groups = (n_frames + F - 1) / F;
+    const float inv_m = 1.0f / (float)M;
+
+    for (int i = tid; i < S::TW_ELEMS; i += T) tw_s[i] = tw[i];
+    __syncthreads();
+
+    for (int g = blockIdx.x; g < n_groups; g += gridDim.x) {
+        const int fh = min(F, n_frames - g * F);
+        cpx v[IPT][M];
+        // ---- stage A': x[n1 + K*n2] -> registers (lanes = consecutive n1: coalesced), M-point FFT over n2
+#pragma unroll
+        for (int j = 0; j < IPT; ++j) {
+            const int it = tid + j * T;
+            const int f = it / K, n1 = it - f * K;
+            if (f < fh) {
+                const cpx* src = in + ((size_t)g * F + f) * N + n1;
+#pragma unroll
+                for (int n2 = 0; n2 < M; ++n2) v[j][n2] = ldg_stream(src + (size_t)n2 * K);
+            } else {
+#pragma unroll
+                for (int n2 = 0; n2 < M; ++n2) v[j][n2] = cmake(0.f, 0.f);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < IPT; ++j) {
+            const int it = tid + j * T;
+            const int n1 = it % K;
+            rf::FFTN<M, -1>::run(v[j]);
+#pragma unroll
+            for (int m = 0; m < M; ++m) v[j][m] = cmul(v[j][m], ldg_nc(table + m * K + n1));
+        }
+        // the previous group's bulk store must have finished reading shared memory
+        if (tid == 0) bulk_wait_read();
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < IPT; ++j) {
+            const int it = tid + j * T;
+            const int f = it / K, n1 = it - f * K;
+            cpx* dst = buf + (size_t)f * M * RS + S::addr1(n1);
+#pragma unroll
+            for (int m = 0; m < M; ++m) dst[m * RS] = v[j][m];
+        }
+        __syncthreads();
+        // ---- stage B: K-point forward FFT of every row (over n1)
+        row_fft<S, -1>(buf, tw_s, tid);
+        __syncthreads();
+        // ---- stage C': column k of all rows = the subcarrier's M bins
+#pragma unroll
+        for (int j = 0; j < IPT; ++j) {
+            const int it = tid + j * T;
+            const int f = it / K, k = it - f * K;
+            const cpx* src = buf + (size_t)f * M * RS + k;
+#pragma unroll
+            for (int m = 0; m < M; ++m) v[j][m] = src[m * RS];
+        }
+        __syncthreads();
+        if (eq != nullptr) {
+            // Y[b*M+m] back to the linear [b][m] order, divide by the channel, combine the L parts
+#pragma unroll
+            for (int j = 0; j < IPT; ++j) {
+                cpx* dst = buf + (size_t)(tid + j * T) * M;
+#pragma unroll
+                for (int m = 0; m < M; ++m) dst[m] = v[j][m];
+            }
+            __syncthreads();
+            const cpx* eqg = eq + (size_t)g * F * N;
+            for (int i = tid; i < fh * N; i += T) buf[i] = cdiv(buf[i], ldg_stream(eqg + i));
+            __syncthreads();
+            const int h = L / 2;
+#pragma unroll
+            for (int j = 0; j < IPT; ++j) {
+                const int it = tid + j * T;
+                const int f = it / K, k = it - f * K;
+#pragma unroll
+                for (int m = 0; m < M; ++m) v[j][m] = cmake(0.f, 0.f);
+                for (int i = 0; i < L; ++i) {
+                    int kk = k + i - h;
+                    kk = kk < 0 ? kk + K : (kk >= K ? kk - K : kk);
+                    const cpx* src = buf + ((size_t)f * K + kk) * M;
+                    const cpx* tp = taps + ((i + h) % L) * M;
+#pragma unroll
+                    for (int m = 0; m < M; ++m) v[j][m] = cadd(v[j][m], cmul(ldg_nc(tp + m), src[m]));
+                }
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int j = 0; j < IPT; ++j) {
+            if (mode == 0) {
+                rf::FFTN<M, +1>::run(v[j]);
+#pragma unroll
+                for (int m = 0; m < M; ++m) v[j][m] = cscale(v[j][m], inv_m);
+            }
+            cpx* dst = buf + (size_t)(tid + j * T) * M; // linear [k][m] staging of the output
+#pragma unroll
+            for (int m = 0; m < M; ++m) dst[m] = v[j][m];
+        }
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) bulk_store(out + (size_t)g * F * N, buf, (uint32_t)fh * N * sizeof(cpx));
+    }
+    if (tid == 0) bulk_wait_all();
+}
+
+// ----------------------------------------------------------------------------------------
+// host side
+typedef void (*mod_launch_t)(cpx*, const cpx*, const cpx*, const cpx*, int, int, cudaStream_t);
+typedef void (*rx_launch_t)(cpx*, const cpx*, const cpx*, const cpx*, const cpx*, const cpx*, int, int, int, int,
+                            cudaStream_t);
+
+template <class S>
+static void launch_mod(cpx* out, const cpx* in, const cpx* table, const cpx* tw, int n_frames, int grid,
+                       cudaStream_t s)
+{
+    fused_mod_kernel<S><<<grid, S::T, S::SMEM_BYTES, s>>>(out, in, table, tw, n_frames);
+}
+template <class S>
+static void launch_rx(cpx* out, const cpx* in, const cpx* eq, const cpx* table, const cpx* tw, const cpx* taps, int L,
+                      int mode, int n_frames, int grid, cudaStream_t s)
+{
+    fused_rx_kernel<S><<<grid, S::T, S::SMEM_BYTES, s>>>(out, in, eq, table, tw, taps, L, mode, n_frames);
+}
+
+struct ShapeEntry {
+    int M, K, R1, R2, T, F;
+    size_t smem;
+    const char* mod_name;
+    const char* rx_name;
+    mod_launch_t mod;
+    rx_launch_t rx;
+    const void* mod_fn;
+    const void* rx_fn;
+};
+
+template <class S>
+static ShapeEntry make_entry(const char* mn, const char* rn)
+{
+    ShapeEntry e;
+    e.M = S::M; e.K = S::K; e.R1 = S::R1; e.R2 = S::R2; e.T = S::T; e.F = S::F;
+    e.smem = S::SMEM_BYTES;
+    e.mod_name = mn;
+    e.rx_name = rn;
+    e.mod = &launch_mod<S>;
+    e.rx = &launch_rx<S>;
+    e.mod_fn = (const void*)&fused_mod_kernel<S>;
+    e.rx_fn = (const void*)&fused_rx_kernel<S>;
+    return e;
+}
+
+#define GFDM_SHAPE(M, R1, R2, T, IPT)                                                           \
+    make_entry<Shape<M, R1, R2, T, IPT>>("fused_mod_kernel<M=" #M ",K=" #R1 "x" #R2 ",T=" #T ">", \
+                                          "fused_rx_kernel<M=" #M ",K=" #R1 "x" #R2 ",T=" #T ">")
+
+static const std::vector<ShapeEntry>& shape_table()
+{
+    static const std::vector<ShapeEntry> t = {
+        GFDM_SHAPE(5, 16, 1, 256, 1),   // K=16   (BASELINE config 1)
+        GFDM_SHAPE(9, 8, 8, 256, 1),    // K=64   (config 2)
+        GFDM_SHAPE(15, 16, 16, 256, 1), // K=256  (config 4)
+        GFDM_SHAPE(15, 32, 32, 512, 2), // K=1024 (config 3, headline)
+    };
+    return t;
+}
+
+struct FusedImpl {
+    const ShapeEntry* e = nullptr;
+    int M = 0, K = 0, L = 0;
+    cpx* d_table = nullptr;    // tx: C_tx ; rx: C_rx (taps folded)
+    cpx* d_table_eq = nullptr; // rx only: plain twiddle
+    cpx* d_tw = nullptr;
+    cpx* d_taps = nullptr;
+    int mod_grid_cap = 0, rx_grid_cap = 0;
+};
+
+static const ShapeEntry* find_shape(int M, int K)
+{
+    for (const ShapeEntry& e : shape_table())
+        if (e.M == M && e.K == K) return &e;
+    return nullptr;
+}
+
+static int grid_cap(const void* fn, int threads, size_t smem)
+{
+    int dev = 0, sms = 0, per_sm = 0;
+    GFDM_CUDA_CHECK(cudaGetDevice(&dev));
+    GFDM_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    GFDM_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GFDM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem));
+    if (per_sm < 1) throw CudaError("fused kernel does not fit on this device");
+    return sms * per_sm;
+}
+
+static std::vector<cpx> make_tw(int R1, int R2)
+{
+    const int K = R1 * R2;
+    std::vector<cpx> tw((size_t)K);
+    for (int k1 = 0; k1 < R1; ++k1)
+        for (int n0 = 0; n0 < R2; ++n0) {
+            const double ph = -2.0 * M_PI * (double)((long)n0 * k1 % K) / (double)K;
+            tw[(size_t)k1 * R2 + n0] = make_float2((float)std::cos(ph), (float)std::sin(ph));
+        }
+    return tw;
+}
+
+// sign = +1: modulator table (incl. 1/N and part_len); sign = -1: receiver table; with_taps = false: twiddle only
+static std::vector<cpx> make_table(int M, int K, int L, const std::vector<std::complex<float>>& taps, int sign,
+                                   bool with_taps)
+{
+    const int N = M * K, h = L / 2;
+    const int part_len = (M * L / 2 < M) ? M * L / 2 : M;
+    std::vector<cpx> t((size_t)N);
+    for (int m = 0; m < M; ++m)
+        for (int n1 = 0; n1 < K; ++n1) {
+            std::complex<double> G(1.0, 0.0);
+            if (with_taps) {
+                G = 0.0;
+                for (int i = 0; i < L; ++i) {
+                    const std::complex<double> tp(taps[((i + h) % L) * M + m].real(), taps[((i + h) % L) * M + m].imag());
+                    long e = ((long)(i - h) * n1) % K;
+                    if (e < 0) e += K;
+                    G += tp * std::polar(1.0, sign * 2.0 * M_PI * (double)e / (double)K);
+                }
+                if (sign > 0 && m >= part_len) G = 0.0;
+            }
+            const std::complex<double> w = std::polar(1.0, sign * 2.0 * M_PI * (double)((long)m * n1 % N) / (double)N);
+            std::complex<double> c = G * w;
+            if (sign > 0) c /= (double)N;
+            t[(size_t)m * K + n1] = make_float2((float)c.real(), (float)c.imag());
+        }
+    return t;
+}
+
+static std::vector<cpx> to_cpx(const std::vector<std::complex<float>>& v)
+{
+    std::vector<cpx> o(v.size());
+    for (size_t i = 0; i < v.size(); ++i) o[i] = make_float2(v[i].real(), v[i].imag());
+    return o;
+}
+
+void FusedModem::init_tx(int M, int K, int L, const std::vector<std::complex<float>>& taps)
+{
+    destroy();
+    const ShapeEntry* e = find_shape(M, K);
+    if (!e || L < 1) return;
+    FusedImpl* p = new FusedImpl;
+    p->e = e; p->M = M; p->K = K; p->L = L;
+    try {
+        p->mod_grid_cap = grid_cap(e->mod_fn, e->T, e->smem);
+        p->d_table = upload(make_table(M, K, L, taps, +1, true));
+        p->d_tw = upload(make_tw(e->R1, e->R2));
+    } catch (...) {
+        impl_ = p;
+        destroy();
+        throw;
+    }
+    impl_ = p;
+}
+
+void FusedModem::init_rx(int M, int K, int L, const std::vector<std::complex<float>>& taps,
+                         const std::vector<std::complex<float>>&)
+{
+    destroy();
+    const ShapeEntry* e = find_shape(M, K);
+    if (!e || L < 2) return;
+    FusedImpl* p = new FusedImpl;
+    p->e = e; p->M = M; p->K = K; p->L = L;
+    try {
+        p->rx_grid_cap = grid_cap(e->rx_fn, e->T, e->smem);
+        p->d_table = upload(make_table(M, K, L, taps, -1, true));
+        p->d_table_eq = upload(make_table(M, K, L, taps, -1, false));
+        p->d_tw = upload(make_tw(e->R1, e->R2));
+        p->d_taps = upload(to_cpx(taps));
+    } catch (...) {
+        impl_ = p;
+        destroy();
+        throw;
+    }
+    impl_ = p;
+}
+
+int FusedModem::modulate(cpx* out, const cpx* in, size_t frames, cudaStream_t s)
+{
+    const ShapeEntry* e = impl_->e;
+    int launches = 0;
+    const size_t max_chunk = (size_t)1 << 20; // keep frame counts in int range
+    for (size_t f0 = 0; f0 < frames; f0 += max_chunk) {
+        const int nf = (int)std::min(max_chunk, frames - f0);
+        const int groups = (nf + e->F - 1) / e->F;
+        const int grid = groups < impl_->mod_grid_cap ? groups : impl_->mod_grid_cap;
+        e->mod(out + f0 * (size_t)e->M * e->K, in + f0 * (size_t)e->M * e->K, impl_->d_table, impl_->d_tw, nf, grid, s);
+        ++launches;
+    }
+    GFDM_CUDA_CHECK(cudaGetLastError());
+    return launches;
+}
+
+int FusedModem::demodulate(cpx* out_td, cpx* out_fd, const cpx* in, const cpx* eq, size_t frames, cudaStream_t s)
+{
+    const ShapeEntry* e = impl_->e;
+    int launches = 0;
+    const size_t N = (size_t)e->M * e->K;
+    const size_t max_chunk = (size_t)1 << 20;
+    for (int pass = 0; pass < 2; ++pass) {
+        cpx* out = pass == 0 ? out_td : out_fd;
+        if (!out) continue;
+        for (size_t f0 = 0; f0 < frames; f0 += max_chunk) {
+            const int nf = (int)std::min(max_chunk, frames - f0);
+            const int groups = (nf + e->F - 1) / e->F;
+            const int grid = groups < impl_->rx_grid_cap ? groups : impl_->rx_grid_cap;
+            e->rx(out + f0 * N, in + f0 * N, eq ? eq + f0 * N : nullptr, eq ? impl_->d_table_eq : impl_->d_table,
+                  impl_->d_tw, impl_->d_taps, impl_->L, pass, nf, grid, s);
+            ++launches;
+        }
+    }
+    GFDM_CUDA_CHECK(cudaGetLastError());
+    return launches;
+}
+
+const char* FusedModem::mod_name() const { return impl_ ? impl_->e->mod_name : "none"; }
+const char* FusedModem::rx_name() const { return impl_ ? impl_->e->rx_name : "none"; }
+
+void FusedModem::destroy()
+{
+    if (!impl_) return;
+    if (impl_->d_table) cudaFree(impl_->d_table);
+    if (impl_->d_table_eq) cudaFree(impl_->d_table_eq);
+    if (impl_->d_tw) cudaFree(impl_->d_tw);
+    if (impl_->d_taps) cudaFree(impl_->d_taps);
+    delete impl_;
+    impl_ = nullptr;
+}
+
 } // namespace gfdm

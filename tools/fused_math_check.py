@@ -1,0 +1,82 @@
+"""NumPy emulation of the fused-kernel factorisation -- validates the
+algebra the CUDA kernels rely on against the straightforward reference formulas:
+  modulator:  x = M-IFFT_{m->n2} { Ctx[m][n1] * K-IFFT_{b->n1} { M-FFT(d_b)[m] } }
+  receiver :  R_k[m] = K-FFT_{n1->k} { Crx[m][n1] * M-FFT_{n2->m}( x[n1 + K n2] ) },  y_k = M-IFFT(R_k)/M
+with the pulse-shaping filter folded into the twiddle tables, and the two-pass padded
+row-FFT addressing used in shared memory."""
+import numpy as np
+
+def ref_mod(d, taps, M, K, L):
+    D = np.fft.fft(d.reshape(K, M), axis=1)
+    X = np.zeros(M*K, complex); h = L//2; part = min(M*L//2, M)
+    for k in range(K):
+        for i in range(L):
+            src = ((i+h) % L)*M; tgt = ((k+i+K-h) % K)*M
+            X[tgt:tgt+part] += (D[k]*taps[src:src+M])[:part]
+    return np.fft.ifft(X)
+
+def ref_rx_fd(x, taps, M, K, L):
+    Y = np.fft.fft(x); h = L//2; R = np.zeros((K, M), complex)
+    for k in range(K):
+        for i in range(L):
+            src = ((k+i+K-h) % K)*M; tgt = ((i+h) % L)*M
+            R[k] += taps[tgt:tgt+M]*Y[src:src+M]
+    return R
+
+def tx_table(taps, M, K, L):
+    N = M*K; h = L//2; part = min(M*L//2, M)
+    n1 = np.arange(K); C = np.zeros((M, K), complex)
+    for m in range(M):
+        if m >= part: continue
+        G = sum(taps[((i+h) % L)*M+m]*np.exp(2j*np.pi*(i-h)*n1/K) for i in range(L))
+        C[m] = G*np.exp(2j*np.pi*m*n1/N)/N
+    return C
+
+def rx_table(taps, M, K, L):
+    N = M*K; h = L//2
+    n1 = np.arange(K); C = np.zeros((M, K), complex)
+    for m in range(M):
+        G = sum(taps[((i+h) % L)*M+m]*np.exp(-2j*np.pi*(i-h)*n1/K) for i in range(L))
+        C[m] = G*np.exp(-2j*np.pi*m*n1/N)
+    return C
+
+def row_fft_two_pass(row, R1, R2, sign):
+    """in-place two-pass row FFT on the padded layout: element n at n + n//R2; result natural at [i]"""
+    K = R1*R2
+    buf = np.zeros(R1*(R2+1), complex)
+    for n in range(K): buf[n + n//R2] = row[n]
+    # pass 1: item n0: radix-R1 over n1 of x[R2*n1+n0], twiddle W_K^{n0 k1}
+    for n0 in range(R2):
+        v = np.array([buf[(R2+1)*n1+n0] for n1 in range(R1)])
+        A = np.fft.fft(v) if sign < 0 else np.fft.ifft(v)*R1
+        A = A*np.exp(sign*2j*np.pi*n0*np.arange(R1)/K)
+        for k1 in range(R1): buf[(R2+1)*k1+n0] = A[k1]
+    out = np.zeros(R1*(R2+1), complex)
+    for k1 in range(R1):
+        v = np.array([buf[(R2+1)*k1+n0] for n0 in range(R2)])
+        X = np.fft.fft(v) if sign < 0 else np.fft.ifft(v)*R2
+        for k0 in range(R2): out[k1+R1*k0] = X[k0]
+    return out[:K]
+
+def fused_mod(d, C, M, K, plan):
+    D = np.fft.fft(d.reshape(K, M), axis=1)          # stage A: [k][m]
+    rows = D.T.copy()                                 # [m][b]
+    Z = np.stack([row_fft_two_pass(rows[m], *plan, +1) if plan[1] > 1 else np.fft.ifft(rows[m])*K for m in range(M)])
+    Z = Z*C                                           # stage C
+    x = np.fft.ifft(Z, axis=0)*M                      # M-IFFT over m -> [n2][n1]
+    return x.reshape(M*K)                             # x[n1 + K n2]
+
+def fused_rx(x, C, M, K, plan):
+    U = np.fft.fft(x.reshape(M, K), axis=0)           # M-FFT over n2 -> [m][n1]
+    U = U*C
+    V = np.stack([row_fft_two_pass(U[m], *plan, -1) if plan[1] > 1 else np.fft.fft(U[m]) for m in range(M)])
+    return V.T                                        # R[k][m]
+
+rng = np.random.default_rng(0)
+for (M, K, L, plan) in [(5,16,2,(16,1)), (9,64,2,(8,8)), (15,256,2,(16,16)), (15,1024,2,(32,32)), (15,512,2,(32,16)),
+                        (7,128,4,(16,8)), (6,64,1,(8,8)), (15,128,3,(16,8))]:
+    taps = rng.standard_normal(M*L)+1j*rng.standard_normal(M*L)
+    d = rng.standard_normal(M*K)+1j*rng.standard_normal(M*K)
+    e1 = np.abs(fused_mod(d, tx_table(taps,M,K,L), M, K, plan)-ref_mod(d,taps,M,K,L)).max()
+    e2 = np.abs(fused_rx(d, rx_table(taps,M,K,L), M, K, plan)-ref_rx_fd(d,taps,M,K,L)).max() if L >= 2 else 0
+    print((M,K,L,plan), 'mod err %.2e  rx err %.2e' % (e1, e2))
