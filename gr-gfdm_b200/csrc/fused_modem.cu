@@ -96,29 +96,63 @@ __device__ __forceinline__ void stg_stream(cpx* p, cpx v)
 }
 
 // ----------------------------------------------------------------------------------------
+// optional per-stage cycle counters (build with -DGFDM_PROFILE_STAGES; tools/stage_profile.py)
+#ifdef GFDM_PROFILE_STAGES
+__device__ unsigned long long g_stage_cycles[32];
+#define STAGE_INIT() long long t_last = clock64()
+#define STAGE_MARK(i)                                                        \
+    if (threadIdx.x == 0) {                                                  \
+        const long long t_now = clock64();                                   \
+        atomicAdd(&g_stage_cycles[i], (unsigned long long)(t_now - t_last)); \
+        t_last = t_now;                                                      \
+    }
+#else
+#define STAGE_INIT()
+#define STAGE_MARK(i)
+#endif
+
+// ----------------------------------------------------------------------------------------
 // compile-time shape of one fused kernel
-template <int M_, int R1_, int R2_, int T_, int IPT_>
+template <int M_, int R1_, int R2_, int T_, int IPT_, int MINB_>
 struct Shape {
-    static constexpr int M = M_, R1 = R1_, R2 = R2_, T = T_, IPT = IPT_;
+    static constexpr int M = M_, R1 = R1_, R2 = R2_, T = T_, IPT = IPT_, MINB = MINB_;
     static constexpr int K = R1 * R2;
     static constexpr int N = M * K;
     static constexpr int F = IPT * T / K; // frames per CTA pass
     static_assert(IPT * T % K == 0 && F >= 1, "threads x items must cover whole frames");
-    static_assert(32 % R1 == 0 || R1 % 32 == 0, "R1 must divide the warp");
+    static_assert(32 % R1 == 0, "R1 must divide the warp");
+    static_assert(R2 == 1 || ((R2 & (R2 - 1)) == 0 && R2 <= 32), "R2 must be a power of two <= 32");
     static constexpr bool TWO_PASS = R2 > 1;
-    // row stride (complex elements): two-pass rows are padded by one element per R2 block so that
-    // both passes are bank-conflict free; single-pass rows get an odd stride
+    // Rows of the K-point stage.  Two-pass rows are padded by one element per R2 block: element
+    // n = R2*q + r lives at (R2+1)*q + r, which makes pass 1 (lanes = r), pass 2 (lanes = q) and the
+    // producer (lanes = consecutive n) bank-conflict free with compile-time (immediate) offsets -- an
+    // XOR swizzle would save the padding but costs 32 live address registers in the radix-32 passes.
+    // Single-pass rows get an odd stride.
     static constexpr int RS = TWO_PASS ? R1 * (R2 + 1) : (K | 1);
     static constexpr int ROWS = F * M;
     static constexpr int ROW_ELEMS = ROWS * RS;
     static constexpr int STAGE_ELEMS = F * N;
     static constexpr int BUF_ELEMS = ROW_ELEMS > STAGE_ELEMS ? ROW_ELEMS : STAGE_ELEMS;
     static constexpr int TW_ELEMS = TWO_PASS ? K : 0;
-    static constexpr size_t SMEM_BYTES = sizeof(cpx) * (size_t)(BUF_ELEMS + TW_ELEMS) + 64 /* taps hdr + mbarrier */;
-    __host__ __device__ static constexpr int addr1(int n) { return TWO_PASS ? n + n / R2 : n; } // row-FFT input slot
+    // per-CTA shared memory budget in complex elements (228 KB per SM, 1 KB per CTA reserved)
+    static constexpr int TAPS_ELEMS = 64; // receive taps of the equalising path (L*M <= 64)
+    static constexpr int BUDGET_ELEMS = ((233472 / MINB) - 1024) / 8 - 8 - TAPS_ELEMS;
+    static constexpr int P_MAX = BUDGET_ELEMS - BUF_ELEMS - TW_ELEMS;
+    static_assert(P_MAX >= 0, "frame group does not fit in shared memory");
+    // the folded filter/twiddle table stays resident when the whole next group fits beside it
+    static constexpr bool TBL_SMEM = P_MAX >= F * N + N;
+    static constexpr int TBL_ELEMS = TBL_SMEM ? N : 0;
+    static constexpr int P_AVAIL = P_MAX - TBL_ELEMS;
+    // prefetch region P: modulator -> the first PF staged elements of the next group,
+    //                    receiver  -> the first PR sample rows (n2) of every frame of the next group
+    static constexpr int PF = (F * N) < (P_AVAIL / (2 * M)) * 2 * M ? (F * N) : (P_AVAIL / (2 * M)) * 2 * M;
+    static constexpr int PR = M < P_AVAIL / (F * K) ? M : P_AVAIL / (F * K);
+    static constexpr int P_ELEMS = PF > F * PR * K ? PF : F * PR * K;
+    static constexpr size_t SMEM_BYTES = sizeof(cpx) * (size_t)(BUF_ELEMS + TW_ELEMS + TBL_ELEMS + P_ELEMS + TAPS_ELEMS) + 64;
+    __host__ __device__ static constexpr int swz(int n) { return TWO_PASS ? n + n / R2 : n; } // row-FFT input slot
 };
 
-// Row FFTs over the K-long rows held in shared memory (in place; input at addr1(), output natural).
+// Row FFTs over the K-long rows held in shared memory (in place; input at swz(), output natural).
 template <class S, int DIR>
 __device__ __forceinline__ void row_fft(cpx* __restrict__ buf, const cpx* __restrict__ tw_s, int tid)
 {
@@ -143,14 +177,23 @@ __device__ __forceinline__ void row_fft(cpx* __restrict__ buf, const cpx* __rest
 #pragma unroll
             for (int i = 0; i < R1; ++i) a[i] = p[(R2 + 1) * i];
             rf::FFTN<R1, DIR>::run(a);
+            // twiddle + store in chunks of 8; the empty asm keeps the chunks in program order so that
+            // at most 8 twiddles are live next to the 2*R1 data registers (no spills in this hot loop)
+            p[0] = a[0];
 #pragma unroll
-            for (int i = 1; i < R1; ++i) {
-                cpx w = tw_s[i * R2 + n0];
-                if (DIR > 0) w.y = -w.y;
-                a[i] = cmul(a[i], w);
+            for (int c = 0; c < R1; c += 8) {
+                cpx w[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    if (c + i > 0 && c + i < R1) w[i] = tw_s[(c + i) * R2 + n0];
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    if (c + i > 0 && c + i < R1) {
+                        if (DIR > 0) w[i].y = -w[i].y;
+                        p[(R2 + 1) * (c + i)] = cmul(a[c + i], w[i]);
+                    }
+                asm volatile("" ::: "memory");
             }
-#pragma unroll
-            for (int i = 0; i < R1; ++i) p[(R2 + 1) * i] = a[i];
         }
         if constexpr (R1 == R2) __syncwarp(); else __syncthreads();
         // pass 2: item (row, k1): radix-R2 over A[n0][k1]; result X[k1 + R1*k0] stored at natural index.
@@ -159,80 +202,124 @@ __device__ __forceinline__ void row_fft(cpx* __restrict__ buf, const cpx* __rest
         constexpr int ITERS2 = (ITEMS2 + T - 1) / T;
 #pragma unroll 1
         for (int ii = 0; ii < ITERS2; ++ii) {
-            const int it = tid + ii * T;
-            const bool act = it < ITEMS2;
+            int it = tid + ii * T;
+            if constexpr (ITEMS2 % 32 == 0) {
+                if (it >= ITEMS2) break; // whole warps drop out together
+            } else {
+                // surplus lanes of the last warp redo the last item (same reads, same values written):
+                // no divergence around the warp barrier and b[] stays in registers
+                it = it < ITEMS2 ? it : ITEMS2 - 1;
+            }
             const int row = it / R1, k1 = it - row * R1;
             cpx* r = buf + row * RS;
             cpx b[R2];
-            if (act) {
 #pragma unroll
-                for (int i = 0; i < R2; ++i) b[i] = r[(R2 + 1) * k1 + i];
-                rf::FFTN<R2, DIR>::run(b);
-            }
+            for (int i = 0; i < R2; ++i) b[i] = r[(R2 + 1) * k1 + i];
+            rf::FFTN<R2, DIR>::run(b);
             __syncwarp();
-            if (act) {
 #pragma unroll
-                for (int i = 0; i < R2; ++i) r[k1 + R1 * i] = b[i];
-            }
+            for (int i = 0; i < R2; ++i) r[k1 + R1 * i] = b[i];
         }
     }
 }
 
 // ----------------------------------------------------------------------------------------
 // Fused modulator.  in/out: [n_frames][N]; table: C_tx [M][K]; tw: W_K^{n0*k1} as [k1][n0].
+// Shared memory: R = row buffer (also holds the tail of the staged input), P = prefetch region
+// holding the head of the NEXT group's staged input, loaded by TMA while this group is processed.
 template <class S>
-__global__ void __launch_bounds__(S::T, 1) fused_mod_kernel(cpx* __restrict__ out, const cpx* __restrict__ in,
-                                                            const cpx* __restrict__ table, const cpx* __restrict__ tw,
-                                                            int n_frames)
+__global__ void __launch_bounds__(S::T, S::MINB) fused_mod_kernel(cpx* __restrict__ out, const cpx* __restrict__ in,
+                                                                  const cpx* __restrict__ table,
+                                                                  const cpx* __restrict__ tw, int n_frames)
 {
-    constexpr int M = S::M, K = S::K, N = S::N, T = S::T, IPT = S::IPT, F = S::F, RS = S::RS;
+    constexpr int M = S::M, K = S::K, N = S::N, T = S::T, IPT = S::IPT, F = S::F, RS = S::RS, PF = S::PF;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     cpx* buf = reinterpret_cast<cpx*>(smem_raw);
     cpx* tw_s = buf + S::BUF_ELEMS;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + sizeof(cpx) * (S::BUF_ELEMS + S::TW_ELEMS));
+    cpx* tbl_s = tw_s + S::TW_ELEMS;
+    cpx* pre = tbl_s + S::TBL_ELEMS;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(pre + S::P_ELEMS + S::TAPS_ELEMS);
+    uint64_t* bar_p = bars;     // head of the staged input (region P)
+    uint64_t* bar_r = bars + 1; // tail of the staged input (region R)
     const int tid = threadIdx.x;
     const int n_groups = (n_frames + F - 1) / F;
 
     for (int i = tid; i < S::TW_ELEMS; i += T) tw_s[i] = tw[i];
-    if (tid == 0) mbar_init(bar, 1);
+    for (int i = tid; i < S::TBL_ELEMS; i += T) tbl_s[i] = table[i];
+    if (tid == 0) {
+        mbar_init(bar_p, 1);
+        mbar_init(bar_r, 1);
+    }
     __syncthreads();
+
+    // issue the bulk loads of group gg: head -> P, tail -> R
+    auto load_head = [&](int gg) {
+        const int el = min(F, n_frames - gg * F) * N;
+        const uint32_t bytes = (uint32_t)min(el, PF) * sizeof(cpx);
+        mbar_expect_tx(bar_p, bytes);
+        bulk_load(pre, in + (size_t)gg * F * N, bytes, bar_p);
+    };
+    auto load_tail = [&](int gg) {
+        const int el = min(F, n_frames - gg * F) * N;
+        const uint32_t bytes = (uint32_t)max(el - PF, 0) * sizeof(cpx);
+        mbar_expect_tx(bar_r, bytes);
+        if (bytes) bulk_load(buf, in + (size_t)gg * F * N + PF, bytes, bar_r);
+    };
 
     int g = blockIdx.x;
     if (tid == 0 && g < n_groups) {
-        const int fh = min(F, n_frames - g * F);
-        const uint32_t bytes = (uint32_t)fh * N * sizeof(cpx);
-        mbar_expect_tx(bar, bytes);
-        bulk_load(buf, in + (size_t)g * F * N, bytes, bar);
+        load_head(g);
+        load_tail(g);
     }
     uint32_t phase = 0;
+    STAGE_INIT();
     for (; g < n_groups; g += gridDim.x) {
         const int fh = min(F, n_frames - g * F);
-        mbar_wait(bar, phase);
+        const int gn = g + gridDim.x;
+        mbar_wait(bar_p, phase);
+        if (PF < F * N) mbar_wait(bar_r, phase);
         phase ^= 1;
+        STAGE_MARK(0) // wait for the bulk loads
 
         cpx v[IPT][M];
         // ---- stage A: subcarrier symbols from the staged [k][m] block -> registers
 #pragma unroll
         for (int j = 0; j < IPT; ++j) {
-            const int it = tid + j * T;
-            const cpx* src = buf + (size_t)it * M; // (f*K + k)*M
+            const int e = (tid + j * T) * M; // (f*K + k)*M
+            const cpx* src = (e < PF) ? pre + e : buf + (e - PF);
 #pragma unroll
             for (int m = 0; m < M; ++m) v[j][m] = src[m];
         }
-        __syncthreads(); // staging fully consumed; the row layout may now overwrite it
+        __syncthreads(); // staging fully consumed: P may be refilled, R may take the rows
+        if (tid == 0 && gn < n_groups) {
+            fence_proxy_async();
+            load_head(gn);
+        }
+        STAGE_MARK(1) // stage A reads
 #pragma unroll
         for (int j = 0; j < IPT; ++j) {
             const int it = tid + j * T;
             const int f = it / K, k = it - f * K;
             rf::FFTN<M, -1>::run(v[j]);
-            cpx* dst = buf + (size_t)f * M * RS + S::addr1(k);
+            cpx* dst = buf + (size_t)f * M * RS + S::swz(k);
 #pragma unroll
             for (int m = 0; m < M; ++m) dst[m * RS] = v[j][m];
         }
         __syncthreads();
+        STAGE_MARK(2) // stage A FFT + row writes
         // ---- stage B: K-point inverse FFT of every row (over the subcarrier index)
         row_fft<S, +1>(buf, tw_s, tid);
+        STAGE_MARK(3) // row FFT (warp 0's own time)
         __syncthreads();
+        STAGE_MARK(4) // barrier after row FFT
+        // table column of the first item (unless resident): issued after the barrier so that the
+        // compiler cannot hoist it into the register-hungry radix-32 passes; the column reads hide it
+        cpx tc[M];
+        if constexpr (!S::TBL_SMEM) {
+            const int n1 = tid % K;
+#pragma unroll
+            for (int m = 0; m < M; ++m) tc[m] = ldg_nc(table + m * K + n1);
+        }
         // ---- stage C: column n1 of all rows -> registers
 #pragma unroll
         for (int j = 0; j < IPT; ++j) {
@@ -242,21 +329,28 @@ __global__ void __launch_bounds__(S::T, 1) fused_mod_kernel(cpx* __restrict__ ou
 #pragma unroll
             for (int m = 0; m < M; ++m) v[j][m] = src[m * RS];
         }
-        __syncthreads(); // shared memory is dead: prefetch the next group while stage C computes and stores
-        const int gn = g + gridDim.x;
+        __syncthreads(); // R is dead: fetch the tail of the next group while stage C computes and stores
         if (tid == 0 && gn < n_groups) {
-            const int fhn = min(F, n_frames - gn * F);
-            const uint32_t bytes = (uint32_t)fhn * N * sizeof(cpx);
             fence_proxy_async();
-            mbar_expect_tx(bar, bytes);
-            bulk_load(buf, in + (size_t)gn * F * N, bytes, bar);
+            load_tail(gn);
         }
+        STAGE_MARK(5) // stage C reads
 #pragma unroll
         for (int j = 0; j < IPT; ++j) {
             const int it = tid + j * T;
             const int f = it / K, n1 = it - f * K;
+            if constexpr (S::TBL_SMEM) {
 #pragma unroll
-            for (int m = 0; m < M; ++m) v[j][m] = cmul(v[j][m], ldg_nc(table + m * K + n1));
+                for (int m = 0; m < M; ++m) v[j][m] = cmul(v[j][m], tbl_s[m * K + n1]);
+            } else {
+#pragma unroll
+                for (int m = 0; m < M; ++m) v[j][m] = cmul(v[j][m], tc[m]);
+                if (j + 1 < IPT) { // next item's column: in flight while this item's IFFT and stores run
+                    const int n1n = (tid + (j + 1) * T) % K;
+#pragma unroll
+                    for (int m = 0; m < M; ++m) tc[m] = ldg_nc(table + m * K + n1n);
+                }
+            }
             rf::FFTN<M, +1>::run(v[j]);
             if (f < fh) {
                 cpx* dst = out + ((size_t)g * F + f) * N + n1;
@@ -264,69 +358,147 @@ __global__ void __launch_bounds__(S::T, 1) fused_mod_kernel(cpx* __restrict__ ou
                 for (int n2 = 0; n2 < M; ++n2) stg_stream(dst + (size_t)n2 * K, v[j][n2]);
             }
         }
+        STAGE_MARK(6) // stage C compute + stores
     }
 }
 
 // ----------------------------------------------------------------------------------------
 // Fused receiver.  in: [n_frames][N] time samples; eq: per-bin channel or nullptr;
 // out: [n_frames][N]; mode 0: soft symbols y (generic_work[_equalize]); mode 1: R (fft_[equalize_]filter_downsample).
+// Shared memory: R = row buffer / output staging (bulk-stored), P = the first PR sample rows of every
+// frame of the NEXT group (TMA prefetch); the remaining rows are prefetched into registers.
 template <class S>
-__global__ void __launch_bounds__(S::T, 1) fused_rx_kernel(cpx* __restrict__ out, const cpx* __restrict__ in,
-                                                           const cpx* __restrict__ eq, const cpx* __restrict__ table,
-                                                           const cpx* __restrict__ tw, const cpx* __restrict__ taps,
-                                                           int L, int mode, int n_frames)
+__global__ void __launch_bounds__(S::T, S::MINB) fused_rx_kernel(cpx* __restrict__ out, const cpx* __restrict__ in,
+                                                                 const cpx* __restrict__ eq,
+                                                                 const cpx* __restrict__ table,
+                                                                 const cpx* __restrict__ tw,
+                                                                 const cpx* __restrict__ taps, int L, int mode,
+                                                                 int n_frames)
 {
-    constexpr int M = S::M, K = S::K, N = S::N, T = S::T, IPT = S::IPT, F = S::F, RS = S::RS;
+    constexpr int M = S::M, K = S::K, N = S::N, T = S::T, IPT = S::IPT, F = S::F, RS = S::RS, PR = S::PR;
+    constexpr int XR = M - PR > 0 ? M - PR : 1;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     cpx* buf = reinterpret_cast<cpx*>(smem_raw);
     cpx* tw_s = buf + S::BUF_ELEMS;
+    cpx* tbl_s = tw_s + S::TW_ELEMS;
+    cpx* pre = tbl_s + S::TBL_ELEMS;
+    cpx* taps_s = pre + S::P_ELEMS;
+    uint64_t* bar_p = reinterpret_cast<uint64_t*>(taps_s + S::TAPS_ELEMS);
     const int tid = threadIdx.x;
     const int n_groups = (n_frames + F - 1) / F;
     const float inv_m = 1.0f / (float)M;
 
     for (int i = tid; i < S::TW_ELEMS; i += T) tw_s[i] = tw[i];
+    for (int i = tid; i < S::TBL_ELEMS; i += T) tbl_s[i] = table[i];
+    for (int i = tid; i < L * M && i < S::TAPS_ELEMS; i += T) taps_s[i] = taps[i];
+    if (tid == 0) mbar_init(bar_p, 1);
     __syncthreads();
 
-    for (int g = blockIdx.x; g < n_groups; g += gridDim.x) {
+    // sample rows n2 < PR of every frame of group gg -> P (one bulk copy per frame, or one per group)
+    auto load_head = [&](int gg) {
+        const int fhh = min(F, n_frames - gg * F);
+        if (PR == M) {
+            const uint32_t bytes = (uint32_t)fhh * N * sizeof(cpx);
+            mbar_expect_tx(bar_p, bytes);
+            bulk_load(pre, in + (size_t)gg * F * N, bytes, bar_p);
+        } else {
+            constexpr uint32_t bytes = (uint32_t)PR * K * sizeof(cpx);
+            mbar_expect_tx(bar_p, bytes * fhh);
+            for (int f = 0; f < fhh; ++f)
+                bulk_load(pre + (size_t)f * PR * K, in + ((size_t)gg * F + f) * N, bytes, bar_p);
+        }
+    };
+    // sample rows n2 >= PR -> registers
+    cpx xr[IPT][XR];
+    auto load_rest = [&](int gg) {
+        if constexpr (PR < M) {
+            const int fhh = min(F, n_frames - gg * F);
+#pragma unroll
+            for (int j = 0; j < IPT; ++j) {
+                const int it = tid + j * T;
+                const int f = it / K, n1 = it - f * K;
+                const cpx* src = in + ((size_t)gg * F + f) * N + n1;
+#pragma unroll
+                for (int r = 0; r < M - PR; ++r)
+                    xr[j][r] = f < fhh ? ldg_stream(src + (size_t)(PR + r) * K) : cmake(0.f, 0.f);
+            }
+        }
+    };
+
+    int g = blockIdx.x;
+    if (g < n_groups) {
+        if (tid == 0) load_head(g);
+        load_rest(g);
+    }
+    uint32_t phase = 0;
+    STAGE_INIT();
+    for (; g < n_groups; g += gridDim.x) {
         const int fh = min(F, n_frames - g * F);
+        const int gn = g + gridDim.x;
         cpx v[IPT][M];
-        // ---- stage A': x[n1 + K*n2] -> registers (lanes = consecutive n1: coalesced), M-point FFT over n2
+        STAGE_MARK(15) // loop top (bulk store issue)
+        mbar_wait(bar_p, phase);
+        phase ^= 1;
+        STAGE_MARK(16) // wait for the bulk load
+        // ---- stage A': x[n1 + K*n2] -> registers (lanes = consecutive n1), M-point FFT over n2
 #pragma unroll
         for (int j = 0; j < IPT; ++j) {
             const int it = tid + j * T;
             const int f = it / K, n1 = it - f * K;
-            if (f < fh) {
-                const cpx* src = in + ((size_t)g * F + f) * N + n1;
+            const cpx* src = pre + (size_t)f * PR * K + n1;
 #pragma unroll
-                for (int n2 = 0; n2 < M; ++n2) v[j][n2] = ldg_stream(src + (size_t)n2 * K);
-            } else {
+            for (int n2 = 0; n2 < M; ++n2) v[j][n2] = n2 < PR ? src[n2 * K] : xr[j][n2 - PR < XR ? n2 - PR : 0];
+        }
+        __syncthreads(); // P consumed: refill it with the next group
+        if (tid == 0 && gn < n_groups) {
+            fence_proxy_async();
+            load_head(gn);
+        }
+        STAGE_MARK(17) // stage A' reads
+        cpx tc[M];
+        if constexpr (!S::TBL_SMEM) { // table column of the first item: in flight during its M-point FFT
+            const int n1 = tid % K;
 #pragma unroll
-                for (int n2 = 0; n2 < M; ++n2) v[j][n2] = cmake(0.f, 0.f);
-            }
+            for (int m = 0; m < M; ++m) tc[m] = ldg_nc(table + m * K + n1);
         }
 #pragma unroll
         for (int j = 0; j < IPT; ++j) {
             const int it = tid + j * T;
             const int n1 = it % K;
             rf::FFTN<M, -1>::run(v[j]);
+            if constexpr (S::TBL_SMEM) {
 #pragma unroll
-            for (int m = 0; m < M; ++m) v[j][m] = cmul(v[j][m], ldg_nc(table + m * K + n1));
+                for (int m = 0; m < M; ++m) v[j][m] = cmul(v[j][m], tbl_s[m * K + n1]);
+            } else {
+#pragma unroll
+                for (int m = 0; m < M; ++m) v[j][m] = cmul(v[j][m], tc[m]);
+                if (j + 1 < IPT) {
+                    const int n1n = (tid + (j + 1) * T) % K;
+#pragma unroll
+                    for (int m = 0; m < M; ++m) tc[m] = ldg_nc(table + m * K + n1n);
+                }
+            }
         }
-        // the previous group's bulk store must have finished reading shared memory
+        // the previous group's bulk store must have finished reading R
         if (tid == 0) bulk_wait_read();
         __syncthreads();
+        STAGE_MARK(18) // M-FFT + table, wait for the previous store
 #pragma unroll
         for (int j = 0; j < IPT; ++j) {
             const int it = tid + j * T;
             const int f = it / K, n1 = it - f * K;
-            cpx* dst = buf + (size_t)f * M * RS + S::addr1(n1);
+            cpx* dst = buf + (size_t)f * M * RS + S::swz(n1);
 #pragma unroll
             for (int m = 0; m < M; ++m) dst[m * RS] = v[j][m];
         }
         __syncthreads();
+        STAGE_MARK(19) // row writes
         // ---- stage B: K-point forward FFT of every row (over n1)
         row_fft<S, -1>(buf, tw_s, tid);
+        STAGE_MARK(20) // row FFT
+        if (gn < n_groups) load_rest(gn); // tail rows of the next group: in flight during stage C'
         __syncthreads();
+        STAGE_MARK(21) // barrier after row FFT
         // ---- stage C': column k of all rows = the subcarrier's M bins
 #pragma unroll
         for (int j = 0; j < IPT; ++j) {
@@ -337,6 +509,7 @@ __global__ void __launch_bounds__(S::T, 1) fused_rx_kernel(cpx* __restrict__ out
             for (int m = 0; m < M; ++m) v[j][m] = src[m * RS];
         }
         __syncthreads();
+        STAGE_MARK(22) // stage C' reads
         if (eq != nullptr) {
             // Y[b*M+m] back to the linear [b][m] order, divide by the channel, combine the L parts
 #pragma unroll
@@ -347,7 +520,25 @@ __global__ void __launch_bounds__(S::T, 1) fused_rx_kernel(cpx* __restrict__ out
             }
             __syncthreads();
             const cpx* eqg = eq + (size_t)g * F * N;
-            for (int i = tid; i < fh * N; i += T) buf[i] = cdiv(buf[i], ldg_stream(eqg + i));
+            {
+                // F*N/T = IPT*M bins per thread, consecutive lanes on consecutive bins: issue every
+                // channel load before the first division so that their latencies overlap
+                constexpr int PER = IPT * M;
+                cpx hq[PER];
+#pragma unroll
+                for (int q = 0; q < PER; ++q) {
+                    const int i = tid + q * T;
+                    hq[q] = i < fh * N ? ldg_stream(eqg + i) : cmake(1.f, 0.f);
+                }
+#pragma unroll
+                for (int q = 0; q < PER; ++q) {
+                    const int i = tid + q * T;
+                    const cpx y = buf[i], hh = hq[q];
+                    const float rden = __fdividef(1.0f, hh.x * hh.x + hh.y * hh.y);
+                    const cpx num = cmulc(y, hh); // y * conj(h) / |h|^2, volk_32fc_x2_divide_32fc
+                    buf[i] = cmake(num.x * rden, num.y * rden);
+                }
+            }
             __syncthreads();
             const int h = L / 2;
 #pragma unroll
@@ -360,13 +551,16 @@ __global__ void __launch_bounds__(S::T, 1) fused_rx_kernel(cpx* __restrict__ out
                     int kk = k + i - h;
                     kk = kk < 0 ? kk + K : (kk >= K ? kk - K : kk);
                     const cpx* src = buf + ((size_t)f * K + kk) * M;
-                    const cpx* tp = taps + ((i + h) % L) * M;
+                    const cpx* tp = taps_s + ((i + h) % L) * M;
 #pragma unroll
-                    for (int m = 0; m < M; ++m) v[j][m] = cadd(v[j][m], cmul(ldg_nc(tp + m), src[m]));
+                    for (int m = 0; m < M; ++m) v[j][m] = cadd(v[j][m], cmul(tp[m], src[m]));
                 }
             }
             __syncthreads();
         }
+        // output staging in the linear [k][m] order; item j covers the contiguous slice
+        // [j*T*M, (j+1)*T*M), which is bulk-stored as soon as it is complete so that the first
+        // slice drains to HBM while the next item's M-point IFFT runs
 #pragma unroll
         for (int j = 0; j < IPT; ++j) {
             if (mode == 0) {
@@ -374,13 +568,17 @@ __global__ void __launch_bounds__(S::T, 1) fused_rx_kernel(cpx* __restrict__ out
 #pragma unroll
                 for (int m = 0; m < M; ++m) v[j][m] = cscale(v[j][m], inv_m);
             }
-            cpx* dst = buf + (size_t)(tid + j * T) * M; // linear [k][m] staging of the output
+            cpx* dst = buf + (size_t)(tid + j * T) * M;
 #pragma unroll
             for (int m = 0; m < M; ++m) dst[m] = v[j][m];
+            fence_proxy_async();
+            __syncthreads();
+            if (tid == 0) {
+                const int e0 = j * T * M, e1 = min((j + 1) * T * M, fh * N);
+                if (e1 > e0) bulk_store(out + (size_t)g * F * N + e0, buf + e0, (uint32_t)(e1 - e0) * sizeof(cpx));
+            }
         }
-        fence_proxy_async();
-        __syncthreads();
-        if (tid == 0) bulk_store(out + (size_t)g * F * N, buf, (uint32_t)fh * N * sizeof(cpx));
+        STAGE_MARK(23) // M-IFFT + output staging + store issue
     }
     if (tid == 0) bulk_wait_all();
 }
@@ -430,17 +628,17 @@ static ShapeEntry make_entry(const char* mn, const char* rn)
     return e;
 }
 
-#define GFDM_SHAPE(M, R1, R2, T, IPT)                                                           \
-    make_entry<Shape<M, R1, R2, T, IPT>>("fused_mod_kernel<M=" #M ",K=" #R1 "x" #R2 ",T=" #T ">", \
-                                          "fused_rx_kernel<M=" #M ",K=" #R1 "x" #R2 ",T=" #T ">")
+#define GFDM_SHAPE(M, R1, R2, T, IPT, MINB)                                                            \
+    make_entry<Shape<M, R1, R2, T, IPT, MINB>>("fused_mod_kernel<M=" #M ",K=" #R1 "x" #R2 ",T=" #T ">", \
+                                                "fused_rx_kernel<M=" #M ",K=" #R1 "x" #R2 ",T=" #T ">")
 
 static const std::vector<ShapeEntry>& shape_table()
 {
     static const std::vector<ShapeEntry> t = {
-        GFDM_SHAPE(5, 16, 1, 256, 1),   // K=16   (BASELINE config 1)
-        GFDM_SHAPE(9, 8, 8, 256, 1),    // K=64   (config 2)
-        GFDM_SHAPE(15, 16, 16, 256, 1), // K=256  (config 4)
-        GFDM_SHAPE(15, 32, 32, 512, 2), // K=1024 (config 3, headline)
+        GFDM_SHAPE(5, 16, 1, 256, 1, 3),   // K=16   (BASELINE config 1)
+        GFDM_SHAPE(9, 8, 8, 256, 1, 3),    // K=64   (config 2)
+        GFDM_SHAPE(15, 16, 16, 256, 1, 2), // K=256  (config 4)
+        GFDM_SHAPE(15, 32, 32, 512, 2, 1), // K=1024 (config 3, headline)
     };
     return t;
 }
@@ -544,7 +742,7 @@ void FusedModem::init_rx(int M, int K, int L, const std::vector<std::complex<flo
 {
     destroy();
     const ShapeEntry* e = find_shape(M, K);
-    if (!e || L < 2) return;
+    if (!e || L < 2 || L * M > 64) return; // the kernel keeps at most 64 receive taps in shared memory
     FusedImpl* p = new FusedImpl;
     p->e = e; p->M = M; p->K = K; p->L = L;
     try {
@@ -601,6 +799,18 @@ int FusedModem::demodulate(cpx* out_td, cpx* out_fd, const cpx* in, const cpx* e
 
 const char* FusedModem::mod_name() const { return impl_ ? impl_->e->mod_name : "none"; }
 const char* FusedModem::rx_name() const { return impl_ ? impl_->e->rx_name : "none"; }
+
+#ifdef GFDM_PROFILE_STAGES
+extern "C" __attribute__((visibility("default"))) int gfdm_debug_stage_cycles(unsigned long long* out32, int reset)
+{
+    if (out32 && cudaMemcpyFromSymbol(out32, g_stage_cycles, sizeof(g_stage_cycles)) != cudaSuccess) return 1;
+    if (reset) {
+        unsigned long long z[32] = { 0 };
+        if (cudaMemcpyToSymbol(g_stage_cycles, z, sizeof(z)) != cudaSuccess) return 1;
+    }
+    return 0;
+}
+#endif
 
 void FusedModem::destroy()
 {
