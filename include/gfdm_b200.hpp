@@ -1,0 +1,558 @@
+// gfdm_b200.hpp -- host C++ layer of the B200 GFDM engine.
+//
+// Header-only classes in namespace gr::gfdm with the class names, constructor
+// signatures and method names of gr-gfdm's GNU-Radio-free kernel layer, each a thin
+// owner of one C-ABI handle (include/gfdm_b200.h).  A program written against the
+// reference's headers compiles against these by switching the include path to
+// <repo>/include (the forwarding headers include/gfdm/*.h carry the original file
+// names) and linking libgfdm_b200.so instead of libgnuradio-gfdm.
+//
+//   reference class (header)                                   -> here
+//   gfdm_kernel_utils        include/gfdm/gfdm_kernel_utils.h:36-52
+//   modulator_kernel_cc      include/gfdm/modulator_kernel_cc.h:41-51
+//   receiver_kernel_cc       include/gfdm/receiver_kernel_cc.h:53-89
+//   advanced_receiver_kernel_cc  include/gfdm/advanced_receiver_kernel_cc.h:37-61
+//   resource_mapper_kernel_cc    include/gfdm/resource_mapper_kernel_cc.h:38-58
+//   add_cyclic_prefix_cc     include/gfdm/add_cyclic_prefix_cc.h:38-57
+//   preamble_channel_estimator_cc include/gfdm/preamble_channel_estimator_cc.h:44-77
+//   transmitter_kernel       include/gfdm/transmitter_kernel.h:43-69
+//
+// Error convention: GFDM_ERR_INVALID_ARGUMENT is rethrown as std::invalid_argument
+// with the reference's message, everything else as std::runtime_error.
+// Additions over the reference: every class has `*_batch(out, in, n_frames, mem)`
+// (frame f at base + f*size, GFDM_MEM_HOST or GFDM_MEM_DEVICE), `set_stream`, `sync`.
+// advanced_receiver_kernel_cc takes a plain `constellation` value instead of
+// gr::digital::constellation_sptr (points() + decision rule).
+#ifndef INCLUDED_GFDM_B200_HPP
+#define INCLUDED_GFDM_B200_HPP
+
+#include "gfdm_b200.h"
+
+#include <complex>
+#include <cstddef>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+namespace gr {
+namespace gfdm {
+
+namespace detail {
+inline void check(int status)
+{
+    if (status == GFDM_OK) return;
+    const std::string msg = gfdm_last_error();
+    if (status == GFDM_ERR_INVALID_ARGUMENT) throw std::invalid_argument(msg);
+    throw std::runtime_error(msg);
+}
+typedef std::complex<float> cf;
+inline const gfdm_complex* c(const cf* p) { return reinterpret_cast<const gfdm_complex*>(p); }
+inline gfdm_complex* c(cf* p) { return reinterpret_cast<gfdm_complex*>(p); }
+
+// owner of one C handle; movable, not copyable (the reference classes own FFTW plans the same way)
+template <class H, void (*Destroy)(H*)>
+class handle
+{
+public:
+    handle() : d_h(nullptr) {}
+    ~handle() { reset(); }
+    handle(handle&& o) noexcept : d_h(o.d_h) { o.d_h = nullptr; }
+    handle& operator=(handle&& o) noexcept
+    {
+        if (this != &o) {
+            reset();
+            d_h = o.d_h;
+            o.d_h = nullptr;
+        }
+        return *this;
+    }
+    handle(const handle&) = delete;
+    handle& operator=(const handle&) = delete;
+    H* get() const { return d_h; }
+    H** out() { return &d_h; }
+    void reset()
+    {
+        if (d_h) Destroy(d_h);
+        d_h = nullptr;
+    }
+
+private:
+    H* d_h;
+};
+} // namespace detail
+
+// ---------------------------------------------------------------------------
+class gfdm_kernel_utils
+{
+public:
+    typedef std::complex<float> gfdm_complex;
+    // lib/gfdm_kernel_utils.cc:59-65
+    float calculate_signal_energy(const gfdm_complex* p_in, const int ninput_size)
+    {
+        float e = 0.0f;
+        detail::check(gfdm_calculate_signal_energy(&e, detail::c(p_in), ninput_size));
+        return e;
+    }
+};
+
+// mixin: stream control shared by all kernels (no reference counterpart)
+template <class Derived>
+class stream_control
+{
+public:
+    void set_stream(void* cuda_stream) { detail::check(gfdm_set_stream(self()->raw(), cuda_stream)); }
+    void sync() { detail::check(gfdm_sync(self()->raw())); }
+    long long launch_count() const { return gfdm_launch_count(self()->raw()); }
+    const char* last_kernel() const { return gfdm_last_kernel(self()->raw()); }
+
+private:
+    const Derived* self() const { return static_cast<const Derived*>(this); }
+};
+
+// ---------------------------------------------------------------------------
+// lib/modulator_kernel_cc.cc:30-141
+class modulator_kernel_cc : public gfdm_kernel_utils, public stream_control<modulator_kernel_cc>
+{
+public:
+    modulator_kernel_cc(int n_timeslots, int n_subcarriers, int overlap, std::vector<gfdm_complex> frequency_taps)
+        : d_n_taps(frequency_taps.size())
+    {
+        detail::check(gfdm_modulator_create(d_h.out(), n_timeslots, n_subcarriers, overlap,
+                                            detail::c(frequency_taps.data()), (int)frequency_taps.size()));
+    }
+    void generic_work(gfdm_complex* p_out, const gfdm_complex* p_in)
+    {
+        detail::check(gfdm_modulator_work(d_h.get(), detail::c(p_out), detail::c(p_in)));
+    }
+    void generic_work_batch(gfdm_complex* p_out, const gfdm_complex* p_in, int n_frames, int mem = GFDM_MEM_HOST)
+    {
+        detail::check(gfdm_modulator_work_batch(d_h.get(), detail::c(p_out), detail::c(p_in), n_frames, mem));
+    }
+    int block_size() const { return gfdm_modulator_block_size(d_h.get()); }
+    std::vector<gfdm_complex> filter_taps() const
+    {
+        std::vector<gfdm_complex> t(d_n_taps);
+        detail::check(gfdm_modulator_filter_taps(d_h.get(), detail::c(t.data())));
+        return t;
+    }
+    void* raw() const { return d_h.get(); }
+
+private:
+    detail::handle<gfdm_modulator, gfdm_modulator_destroy> d_h;
+    size_t d_n_taps;
+};
+
+// ---------------------------------------------------------------------------
+// lib/receiver_kernel_cc.cc:31-334
+class receiver_kernel_cc : public gfdm_kernel_utils, public stream_control<receiver_kernel_cc>
+{
+public:
+    receiver_kernel_cc(int n_timeslots, int n_subcarriers, int overlap, std::vector<gfdm_complex> frequency_taps)
+        : d_n_taps(frequency_taps.size())
+    {
+        detail::check(gfdm_receiver_create(d_h.out(), n_timeslots, n_subcarriers, overlap,
+                                           detail::c(frequency_taps.data()), (int)frequency_taps.size()));
+    }
+    void generic_work(gfdm_complex* out, const gfdm_complex* in)
+    {
+        detail::check(gfdm_receiver_work(d_h.get(), detail::c(out), detail::c(in)));
+    }
+    void generic_work_equalize(gfdm_complex* out, const gfdm_complex* in, const gfdm_complex* f_eq_in)
+    {
+        detail::check(gfdm_receiver_work_equalize(d_h.get(), detail::c(out), detail::c(in), detail::c(f_eq_in)));
+    }
+    // f_eq_in may be null (no equalisation); it advances per frame like `in`
+    void generic_work_batch(gfdm_complex* out, const gfdm_complex* in, const gfdm_complex* f_eq_in, int n_frames,
+                            int mem = GFDM_MEM_HOST)
+    {
+        detail::check(
+            gfdm_receiver_work_batch(d_h.get(), detail::c(out), detail::c(in), detail::c(f_eq_in), n_frames, mem));
+    }
+    void fft_filter_downsample(gfdm_complex* p_out, const gfdm_complex* p_in)
+    {
+        detail::check(gfdm_receiver_fft_filter_downsample(d_h.get(), detail::c(p_out), detail::c(p_in)));
+    }
+    void fft_equalize_filter_downsample(gfdm_complex* p_out, const gfdm_complex* p_in, const gfdm_complex* f_eq_in)
+    {
+        detail::check(gfdm_receiver_fft_equalize_filter_downsample(d_h.get(), detail::c(p_out), detail::c(p_in),
+                                                                   detail::c(f_eq_in)));
+    }
+    void fft_filter_downsample_batch(gfdm_complex* p_out, const gfdm_complex* p_in, const gfdm_complex* f_eq_in,
+                                     int n_frames, int mem = GFDM_MEM_HOST)
+    {
+        detail::check(gfdm_receiver_fft_filter_downsample_batch(d_h.get(), detail::c(p_out), detail::c(p_in),
+                                                                detail::c(f_eq_in), n_frames, mem));
+    }
+    void transform_subcarriers_to_td(gfdm_complex* p_out, const gfdm_complex* p_in)
+    {
+        detail::check(gfdm_receiver_transform_subcarriers_to_td(d_h.get(), detail::c(p_out), detail::c(p_in)));
+    }
+    void transform_subcarriers_to_td_batch(gfdm_complex* p_out, const gfdm_complex* p_in, int n_frames,
+                                           int mem = GFDM_MEM_HOST)
+    {
+        detail::check(gfdm_receiver_transform_subcarriers_to_td_batch(d_h.get(), detail::c(p_out), detail::c(p_in),
+                                                                      n_frames, mem));
+    }
+    void cancel_sc_interference(gfdm_complex* p_out, const gfdm_complex* p_td_in, const gfdm_complex* p_fd_in)
+    {
+        detail::check(gfdm_receiver_cancel_sc_interference(d_h.get(), detail::c(p_out), detail::c(p_td_in),
+                                                           detail::c(p_fd_in)));
+    }
+    void cancel_sc_interference_batch(gfdm_complex* p_out, const gfdm_complex* p_td_in, const gfdm_complex* p_fd_in,
+                                      int n_frames, int mem = GFDM_MEM_HOST)
+    {
+        detail::check(gfdm_receiver_cancel_sc_interference_batch(d_h.get(), detail::c(p_out), detail::c(p_td_in),
+                                                                 detail::c(p_fd_in), n_frames, mem));
+    }
+
+    // ---- legacy 2-D interface (lib/receiver_kernel_cc.cc:130-163,194-209,227-272): the same
+    //      stages on vector<vector<>>, [subcarrier][timeslot]; thin adapters over the flat calls.
+    typedef std::vector<std::vector<gfdm_complex>> matrix;
+    void filter_superposition(matrix& out, const gfdm_complex* in)
+    {
+        std::vector<gfdm_complex> flat((size_t)block_size());
+        fft_filter_downsample(flat.data(), in);
+        vectorize_2d(out, flat.data());
+    }
+    void demodulate_subcarrier(matrix& out, matrix& sc_fdomain)
+    {
+        std::vector<gfdm_complex> fd((size_t)block_size()), td((size_t)block_size());
+        serialize_output(fd.data(), sc_fdomain);
+        transform_subcarriers_to_td(td.data(), fd.data());
+        vectorize_2d(out, td.data());
+    }
+    void serialize_output(gfdm_complex out[], matrix& sc_symbols)
+    {
+        const int M = timeslots(), K = subcarriers();
+        for (int k = 0; k < K; ++k)
+            for (int m = 0; m < M; ++m) out[(size_t)k * M + m] = sc_symbols[k][m];
+    }
+    void vectorize_2d(matrix& out_vector, const gfdm_complex* p_in)
+    {
+        const int M = timeslots(), K = subcarriers();
+        for (int k = 0; k < K; ++k)
+            for (int m = 0; m < M; ++m) out_vector[k][m] = p_in[(size_t)k * M + m];
+    }
+    void remove_sc_interference(matrix& sc_symbols, matrix& sc_fdomain)
+    {
+        std::vector<gfdm_complex> td((size_t)block_size()), fd((size_t)block_size()), res((size_t)block_size());
+        serialize_output(td.data(), sc_symbols);
+        serialize_output(fd.data(), sc_fdomain);
+        cancel_sc_interference(res.data(), td.data(), fd.data());
+        vectorize_2d(sc_symbols, res.data());
+    }
+
+    int block_size() const { return gfdm_receiver_block_size(d_h.get()); }
+    int timeslots() const { return gfdm_receiver_timeslots(d_h.get()); }
+    int subcarriers() const { return gfdm_receiver_subcarriers(d_h.get()); }
+    int overlap() const { return gfdm_receiver_overlap(d_h.get()); }
+    std::vector<gfdm_complex> filter_taps() const
+    {
+        std::vector<gfdm_complex> t(d_n_taps);
+        detail::check(gfdm_receiver_filter_taps(d_h.get(), detail::c(t.data())));
+        return t;
+    }
+    std::vector<gfdm_complex> ic_filter_taps() const
+    {
+        std::vector<gfdm_complex> t((size_t)timeslots());
+        detail::check(gfdm_receiver_ic_filter_taps(d_h.get(), detail::c(t.data())));
+        return t;
+    }
+    void* raw() const { return d_h.get(); }
+
+private:
+    detail::handle<gfdm_receiver, gfdm_receiver_destroy> d_h;
+    size_t d_n_taps;
+};
+
+// ---------------------------------------------------------------------------
+// GNU-Radio-free stand-in for gr::digital::constellation_sptr: the two things the reference
+// uses are points() and decision_maker() (lib/advanced_receiver_kernel_cc.cc:114-120).
+struct constellation {
+    std::vector<std::complex<float>> points;
+    int decision_rule; // gfdm_decision_rule
+    static constellation qpsk() // gr::digital::constellation_qpsk: idx = 2*(im>0) + (re>0)
+    {
+        const float a = 0.70710678118654752440f;
+        return constellation{ { { -a, -a }, { a, -a }, { -a, a }, { a, a } }, GFDM_DECISION_QPSK_SIGN };
+    }
+    static constellation nearest(std::vector<std::complex<float>> pts)
+    {
+        return constellation{ std::move(pts), GFDM_DECISION_NEAREST };
+    }
+};
+
+// lib/advanced_receiver_kernel_cc.cc:32-123
+class advanced_receiver_kernel_cc : public stream_control<advanced_receiver_kernel_cc>
+{
+public:
+    typedef std::complex<float> gr_complex;
+    advanced_receiver_kernel_cc(int timeslots, int subcarriers, int overlap, std::vector<gr_complex> frequency_taps,
+                                std::vector<int> subcarrier_map, int ic_iter, const constellation& constellation_,
+                                int do_phase_compensation)
+    {
+        gfdm_constellation c;
+        c.points = detail::c(constellation_.points.data());
+        c.n_points = (int)constellation_.points.size();
+        c.decision_rule = constellation_.decision_rule;
+        detail::check(gfdm_advanced_receiver_create(d_h.out(), timeslots, subcarriers, overlap,
+                                                    detail::c(frequency_taps.data()), (int)frequency_taps.size(),
+                                                    subcarrier_map.data(), (int)subcarrier_map.size(), ic_iter, &c,
+                                                    do_phase_compensation));
+    }
+    void generic_work(gr_complex* p_out, const gr_complex* p_in)
+    {
+        detail::check(gfdm_advanced_receiver_work(d_h.get(), detail::c(p_out), detail::c(p_in)));
+    }
+    void generic_work_equalize(gr_complex* out, const gr_complex* in, const gr_complex* f_eq_in)
+    {
+        detail::check(
+            gfdm_advanced_receiver_work_equalize(d_h.get(), detail::c(out), detail::c(in), detail::c(f_eq_in)));
+    }
+    void generic_work_batch(gr_complex* out, const gr_complex* in, const gr_complex* f_eq_in, int n_frames,
+                            int mem = GFDM_MEM_HOST)
+    {
+        detail::check(gfdm_advanced_receiver_work_batch(d_h.get(), detail::c(out), detail::c(in), detail::c(f_eq_in),
+                                                        n_frames, mem));
+    }
+    void set_ic(int ic_iter) { detail::check(gfdm_advanced_receiver_set_ic(d_h.get(), ic_iter)); }
+    int get_ic(void) { return gfdm_advanced_receiver_get_ic(d_h.get()); }
+    int block_size() { return gfdm_advanced_receiver_block_size(d_h.get()); }
+    void set_phase_compensation(int do_phase_compensation)
+    {
+        detail::check(gfdm_advanced_receiver_set_phase_compensation(d_h.get(), do_phase_compensation));
+    }
+    int get_phase_compensation() { return gfdm_advanced_receiver_get_phase_compensation(d_h.get()); }
+    void* raw() const { return d_h.get(); }
+
+private:
+    detail::handle<gfdm_advanced_receiver, gfdm_advanced_receiver_destroy> d_h;
+};
+
+// ---------------------------------------------------------------------------
+// lib/resource_mapper_kernel_cc.cc:30-162
+class resource_mapper_kernel_cc : public stream_control<resource_mapper_kernel_cc>
+{
+public:
+    typedef std::complex<float> gfdm_complex;
+    resource_mapper_kernel_cc(int timeslots, int subcarriers, int active_subcarriers, std::vector<int> subcarrier_map,
+                              bool per_timeslot = true, bool is_mapper = true)
+    {
+        detail::check(gfdm_resource_mapper_create(d_h.out(), timeslots, subcarriers, active_subcarriers,
+                                                  subcarrier_map.data(), (int)subcarrier_map.size(),
+                                                  per_timeslot ? 1 : 0, is_mapper ? 1 : 0));
+    }
+    size_t frame_size() { return gfdm_resource_mapper_frame_size(d_h.get()); }
+    size_t block_size() { return gfdm_resource_mapper_block_size(d_h.get()); }
+    size_t input_vector_size() { return gfdm_resource_mapper_input_vector_size(d_h.get()); }
+    size_t output_vector_size() { return gfdm_resource_mapper_output_vector_size(d_h.get()); }
+    void map_to_resources(gfdm_complex* p_out, const gfdm_complex* p_in, const size_t ninput_size)
+    {
+        detail::check(gfdm_resource_mapper_map_to_resources(d_h.get(), detail::c(p_out), detail::c(p_in), ninput_size));
+    }
+    void demap_from_resources(gfdm_complex* p_out, const gfdm_complex* p_in, const size_t noutput_size)
+    {
+        detail::check(
+            gfdm_resource_mapper_demap_from_resources(d_h.get(), detail::c(p_out), detail::c(p_in), noutput_size));
+    }
+    void map_to_resources_batch(gfdm_complex* p_out, const gfdm_complex* p_in, size_t size_per_frame, int n_frames,
+                                int mem = GFDM_MEM_HOST)
+    {
+        detail::check(gfdm_resource_mapper_map_to_resources_batch(d_h.get(), detail::c(p_out), detail::c(p_in),
+                                                                  size_per_frame, n_frames, mem));
+    }
+    void demap_from_resources_batch(gfdm_complex* p_out, const gfdm_complex* p_in, size_t size_per_frame, int n_frames,
+                                    int mem = GFDM_MEM_HOST)
+    {
+        detail::check(gfdm_resource_mapper_demap_from_resources_batch(d_h.get(), detail::c(p_out), detail::c(p_in),
+                                                                      size_per_frame, n_frames, mem));
+    }
+    void* raw() const { return d_h.get(); }
+
+private:
+    detail::handle<gfdm_resource_mapper, gfdm_resource_mapper_destroy> d_h;
+};
+
+// ---------------------------------------------------------------------------
+// lib/add_cyclic_prefix_cc.cc:30-104
+class add_cyclic_prefix_cc : public stream_control<add_cyclic_prefix_cc>
+{
+public:
+    typedef std::complex<float> gfdm_complex;
+    add_cyclic_prefix_cc(int block_len, int cp_len, int cs_len, int ramp_len, std::vector<gfdm_complex> window_taps,
+                         int cyclic_shift = 0)
+    {
+        detail::check(gfdm_cyclic_prefixer_create(d_h.out(), block_len, cp_len, cs_len, ramp_len,
+                                                  detail::c(window_taps.data()), (int)window_taps.size(),
+                                                  cyclic_shift));
+    }
+    void generic_work(gfdm_complex* p_out, const gfdm_complex* p_in)
+    {
+        detail::check(gfdm_cyclic_prefixer_work(d_h.get(), detail::c(p_out), detail::c(p_in)));
+    }
+    void add_cyclic_prefix(gfdm_complex* out, const gfdm_complex* in, const int cyclic_shift)
+    {
+        detail::check(gfdm_cyclic_prefixer_add_cyclic_prefix(d_h.get(), detail::c(out), detail::c(in), cyclic_shift));
+    }
+    void remove_cyclic_prefix(gfdm_complex* p_out, const gfdm_complex* p_in)
+    {
+        detail::check(gfdm_cyclic_prefixer_remove_cyclic_prefix(d_h.get(), detail::c(p_out), detail::c(p_in)));
+    }
+    void add_cyclic_prefix_batch(gfdm_complex* out, const gfdm_complex* in, int cyclic_shift, int n_frames,
+                                 int mem = GFDM_MEM_HOST)
+    {
+        detail::check(gfdm_cyclic_prefixer_add_cyclic_prefix_batch(d_h.get(), detail::c(out), detail::c(in),
+                                                                   cyclic_shift, n_frames, mem));
+    }
+    void remove_cyclic_prefix_batch(gfdm_complex* out, const gfdm_complex* in, int n_frames, int mem = GFDM_MEM_HOST)
+    {
+        detail::check(
+            gfdm_cyclic_prefixer_remove_cyclic_prefix_batch(d_h.get(), detail::c(out), detail::c(in), n_frames, mem));
+    }
+    int block_size() { return gfdm_cyclic_prefixer_block_size(d_h.get()); }
+    int frame_size() { return gfdm_cyclic_prefixer_frame_size(d_h.get()); }
+    int cyclic_shift() const { return gfdm_cyclic_prefixer_cyclic_shift(d_h.get()); }
+    void* raw() const { return d_h.get(); }
+
+private:
+    detail::handle<gfdm_cyclic_prefixer, gfdm_cyclic_prefixer_destroy> d_h;
+};
+
+// ---------------------------------------------------------------------------
+// lib/preamble_channel_estimator_cc.cc:34-294
+class preamble_channel_estimator_cc : public gfdm_kernel_utils, public stream_control<preamble_channel_estimator_cc>
+{
+public:
+    preamble_channel_estimator_cc(int timeslots, int fft_len, int active_subcarriers, bool is_dc_free,
+                                  int which_estimator, std::vector<gfdm_complex> preamble)
+    {
+        detail::check(gfdm_channel_estimator_create(d_h.out(), timeslots, fft_len, active_subcarriers,
+                                                    is_dc_free ? 1 : 0, which_estimator, detail::c(preamble.data()),
+                                                    (int)preamble.size()));
+    }
+    int fft_len() { return gfdm_channel_estimator_fft_len(d_h.get()); }
+    int timeslots() { return gfdm_channel_estimator_timeslots(d_h.get()); }
+    int frame_len() { return gfdm_channel_estimator_frame_len(d_h.get()); }
+    int active_subcarriers() { return gfdm_channel_estimator_active_subcarriers(d_h.get()); }
+    bool is_dc_free() { return gfdm_channel_estimator_is_dc_free(d_h.get()) != 0; }
+    std::vector<float> preamble_filter_taps()
+    {
+        std::vector<float> t(9);
+        detail::check(gfdm_channel_estimator_preamble_filter_taps(d_h.get(), t.data()));
+        return t;
+    }
+    void estimate_preamble_channel(gfdm_complex* fd_preamble_channel, const gfdm_complex* rx_preamble)
+    {
+        detail::check(gfdm_channel_estimator_estimate_preamble_channel(d_h.get(), detail::c(fd_preamble_channel),
+                                                                       detail::c(rx_preamble)));
+    }
+    void filter_preamble_estimate(gfdm_complex* filtered, const gfdm_complex* estimate)
+    {
+        detail::check(
+            gfdm_channel_estimator_filter_preamble_estimate(d_h.get(), detail::c(filtered), detail::c(estimate)));
+    }
+    void interpolate_frame(gfdm_complex* frame_estimate, const gfdm_complex* estimate)
+    {
+        detail::check(
+            gfdm_channel_estimator_interpolate_frame(d_h.get(), detail::c(frame_estimate), detail::c(estimate)));
+    }
+    void estimate_frame(gfdm_complex* frame_estimate, const gfdm_complex* rx_preamble)
+    {
+        detail::check(
+            gfdm_channel_estimator_estimate_frame(d_h.get(), detail::c(frame_estimate), detail::c(rx_preamble)));
+    }
+    void estimate_frame_batch(gfdm_complex* frame_estimate, const gfdm_complex* rx_preamble, int n_frames,
+                              int mem = GFDM_MEM_HOST)
+    {
+        detail::check(gfdm_channel_estimator_estimate_frame_batch(d_h.get(), detail::c(frame_estimate),
+                                                                  detail::c(rx_preamble), n_frames, mem));
+    }
+    void prepare_for_zf(gfdm_complex* transformed_frame, const gfdm_complex* frame_estimate)
+    {
+        detail::check(
+            gfdm_channel_estimator_prepare_for_zf(d_h.get(), detail::c(transformed_frame), detail::c(frame_estimate)));
+    }
+    float estimate_snr(std::vector<float>& cnrs, const gfdm_complex* rx_preamble)
+    {
+        float snr = 0.0f;
+        cnrs.resize((size_t)active_subcarriers());
+        detail::check(gfdm_channel_estimator_estimate_snr(d_h.get(), &snr, cnrs.data(), detail::c(rx_preamble)));
+        return snr;
+    }
+    void estimate_snr_batch(float* snr_lin, float* cnrs, const gfdm_complex* rx_preamble, int n_frames,
+                            int mem = GFDM_MEM_HOST)
+    {
+        detail::check(
+            gfdm_channel_estimator_estimate_snr_batch(d_h.get(), snr_lin, cnrs, detail::c(rx_preamble), n_frames, mem));
+    }
+    void* raw() const { return d_h.get(); }
+
+private:
+    detail::handle<gfdm_channel_estimator, gfdm_channel_estimator_destroy> d_h;
+};
+
+// ---------------------------------------------------------------------------
+// lib/transmitter_kernel.cc:34-107
+class transmitter_kernel : public stream_control<transmitter_kernel>
+{
+public:
+    typedef std::complex<float> gfdm_complex;
+    transmitter_kernel(int timeslots, int subcarriers, int active_subcarriers, int cp_len, int cs_len, int ramp_len,
+                       std::vector<int> subcarrier_map, bool per_timeslot, int overlap,
+                       std::vector<gfdm_complex> frequency_taps, std::vector<gfdm_complex> window_taps,
+                       std::vector<int> cyclic_shifts, std::vector<std::vector<gfdm_complex>> preambles)
+        : d_cyclic_shifts(cyclic_shifts)
+    {
+        std::vector<const ::gfdm_complex*> ptrs;
+        std::vector<int> sizes;
+        for (const auto& p : preambles) {
+            ptrs.push_back(detail::c(p.data()));
+            sizes.push_back((int)p.size());
+        }
+        detail::check(gfdm_transmitter_create(
+            d_h.out(), timeslots, subcarriers, active_subcarriers, cp_len, cs_len, ramp_len, subcarrier_map.data(),
+            (int)subcarrier_map.size(), per_timeslot ? 1 : 0, overlap, detail::c(frequency_taps.data()),
+            (int)frequency_taps.size(), detail::c(window_taps.data()), (int)window_taps.size(), cyclic_shifts.data(),
+            (int)cyclic_shifts.size(), ptrs.data(), sizes.data(), (int)preambles.size()));
+    }
+    int input_vector_size() { return gfdm_transmitter_input_vector_size(d_h.get()); }
+    int output_vector_size() { return gfdm_transmitter_output_vector_size(d_h.get()); }
+    void generic_work(gfdm_complex* p_out, const gfdm_complex* p_in, const int ninput_size)
+    {
+        detail::check(gfdm_transmitter_work(d_h.get(), detail::c(p_out), detail::c(p_in), ninput_size));
+    }
+    void modulate(gfdm_complex* out, const gfdm_complex* in, const int ninput_size)
+    {
+        detail::check(gfdm_transmitter_modulate(d_h.get(), detail::c(out), detail::c(in), ninput_size));
+    }
+    void add_frame(gfdm_complex* out, const gfdm_complex* in, const int cyclic_shift)
+    {
+        detail::check(gfdm_transmitter_add_frame(d_h.get(), detail::c(out), detail::c(in), cyclic_shift));
+    }
+    // frames of cyclic_shifts()[0]: out[n_frames][output_vector_size()]
+    void generic_work_batch(gfdm_complex* p_out, const gfdm_complex* p_in, int ninput_size, int n_frames,
+                            int mem = GFDM_MEM_HOST)
+    {
+        detail::check(
+            gfdm_transmitter_work_batch(d_h.get(), detail::c(p_out), detail::c(p_in), ninput_size, n_frames, mem));
+    }
+    // every antenna (the loop of lib/transmitter_cc_impl.cc:165-177): out[n_shifts][n_frames][output_vector_size()]
+    void generic_work_all_batch(gfdm_complex* p_out, const gfdm_complex* p_in, int ninput_size, int n_frames,
+                                int mem = GFDM_MEM_HOST)
+    {
+        detail::check(
+            gfdm_transmitter_work_all_batch(d_h.get(), detail::c(p_out), detail::c(p_in), ninput_size, n_frames, mem));
+    }
+    const std::vector<int>& cyclic_shifts() const { return d_cyclic_shifts; }
+    void* raw() const { return d_h.get(); }
+
+private:
+    detail::handle<gfdm_transmitter, gfdm_transmitter_destroy> d_h;
+    std::vector<int> d_cyclic_shifts;
+};
+
+} // namespace gfdm
+} // namespace gr
+
+#endif /* INCLUDED_GFDM_B200_HPP */
