@@ -277,7 +277,7 @@ struct gfdm_modulator : HandleBase {
 static void modulator_run(gfdm_modulator* h, cpx* out, const cpx* in, size_t frames)
 {
     if (!frames) return;
-    if (h->fused.available() && aligned16(in)) { // cp.async.bulk needs 16-byte aligned global addresses
+    if (h->fused.available() && aligned16(in) && aligned16(out)) { // cp.async.bulk / 128-bit accesses need 16-byte aligned addresses
         h->launches += h->fused.modulate(out, in, frames, h->stream);
         h->last_kernel = h->fused.mod_name();
         return;
@@ -395,7 +395,7 @@ static void receiver_free(gfdm_receiver* h)
 static void receiver_fd(gfdm_receiver* h, cpx* R, const cpx* in, const cpx* eq, size_t frames)
 {
     if (!frames) return;
-    if (h->fused.available() && aligned16(R)) {
+    if (h->fused.available() && aligned16(R) && aligned16(in) && aligned16(eq)) {
         h->launches += h->fused.demodulate(nullptr, R, in, eq, frames, h->stream);
         h->last_kernel = h->fused.rx_name();
         return;
@@ -427,7 +427,7 @@ static void receiver_td(gfdm_receiver* h, cpx* out, const cpx* R, size_t frames)
 static void receiver_run(gfdm_receiver* h, cpx* out, const cpx* in, const cpx* eq, size_t frames)
 {
     if (!frames) return;
-    if (h->fused.available() && aligned16(out)) {
+    if (h->fused.available() && aligned16(out) && aligned16(in) && aligned16(eq)) {
         h->launches += h->fused.demodulate(out, nullptr, in, eq, frames, h->stream);
         h->last_kernel = h->fused.rx_name();
         return;

@@ -107,7 +107,9 @@ int main(int argc, char** argv)
     dem.demodulate_subcarrier(td, fd);
     std::vector<cf> y2(N);
     dem.serialize_output(y2.data(), td);
-    if (memcmp(y.data(), y2.data(), sizeof(cf) * N) != 0) { printf("FAIL legacy 2-D path differs\n"); return 3; }
+    double err = 0, nrm = 0;   // the 2-D path runs the stages separately: same result up to fp32 rounding
+    for (int i = 0; i < N; ++i) { err += std::norm(y[i] - y2[i]); nrm += std::norm(y[i]); }
+    if (!(err <= 1e-10 * nrm)) { printf("FAIL legacy 2-D path differs (%g)\n", err / nrm); return 3; }
     f = fopen(argv[3], "wb"); fwrite(y.data(), sizeof(cf), y.size(), f); fclose(f);
     printf("OK %d launches\n", (int)(mod.launch_count() + dem.launch_count()));
     return 0;
@@ -141,7 +143,7 @@ def test_cpp_layer_round_trip(cpp_probe, port):
     exe, d = cpp_probe
     M, K, L = 5, 16, 2
     taps = design.get_frequency_domain_filter('rrc', .5, M, K, L).astype(np.complex64)
-    sym = design.get_random_qpsk(M * K, np.random.RandomState(5)).astype(np.complex64)
+    sym = design.get_random_qpsk(M * K, rng=np.random.RandomState(5)).astype(np.complex64)
     taps.tofile(d / 'taps.bin')
     sym.tofile(d / 'sym.bin')
     out = subprocess.run([exe, str(d / 'taps.bin'), str(d / 'sym.bin'), str(d / 'y.bin')], capture_output=True, text=True)
@@ -156,7 +158,7 @@ def test_cpp_layer_round_trip(cpp_probe, port):
 def test_modulator_demodulator_like_qa_python_bindings(gp, port, M, K, L):
     """python/qa_python_bindings.py:66-240 -- modulate / demodulate / stages, complex128 input is cast."""
     taps = design.get_frequency_domain_filter('rrc', .5, M, K, L)
-    d = design.get_random_qpsk(M * K, np.random.RandomState(M + K))  # complex128 on purpose (forcecast)
+    d = design.get_random_qpsk(M * K, rng=np.random.RandomState(M + K))  # complex128 on purpose (forcecast)
     mod, dem = gp.Modulator(M, K, L, taps), gp.Demodulator(M, K, L, np.conj(taps))
     omod, odem = capi.Modulator(M, K, L, taps, lib=port), capi.Demodulator(M, K, L, np.conj(taps), lib=port)
     assert mod.block_size() == M * K and (dem.timeslots(), dem.subcarriers(), dem.overlap()) == (M, K, L)
@@ -188,7 +190,7 @@ def test_mapper_prefixer_estimator_transmitter_bindings(gp, port):
     """qa_python_bindings.py:242-529 (Cyclic_prefixer, Resource_mapper, Preamble_channel_estimator) + Transmitter."""
     cfg = design.get_gfdm_configuration()
     rng = np.random.RandomState(3)
-    d = design.get_random_qpsk(cfg.timeslots * cfg.active_subcarriers, rng)
+    d = design.get_random_qpsk(cfg.timeslots * cfg.active_subcarriers, rng=rng)
     mp, omp = gp.Resource_mapper(cfg.timeslots, cfg.subcarriers, cfg.active_subcarriers, list(cfg.subcarrier_map), True), \
         capi.Resource_mapper(cfg.timeslots, cfg.subcarriers, cfg.active_subcarriers, cfg.subcarrier_map, True, lib=port)
     grid = mp.map_to_resources(d)
@@ -196,7 +198,7 @@ def test_mapper_prefixer_estimator_transmitter_bindings(gp, port):
     assert np.array_equal(mp.demap_from_resources(grid), d.astype(np.complex64))
     pf = gp.Cyclic_prefixer(cfg.block_len, cfg.cp_len, cfg.cs_len, cfg.ramp_len, cfg.window_taps)
     opf = capi.Cyclic_prefixer(cfg.block_len, cfg.cp_len, cfg.cs_len, cfg.ramp_len, cfg.window_taps, lib=port)
-    x = design.get_random_qpsk(cfg.block_len, rng)
+    x = design.get_random_qpsk(cfg.block_len, rng=rng)
     fr = pf.add_cyclic_prefix(x)
     assert fr.shape == (pf.frame_size(),) and np.array_equal(fr, opf.add_cyclic_prefix(x))
     assert np.array_equal(pf.remove_cyclic_prefix(fr), fr[cfg.cp_len:cfg.cp_len + cfg.block_len])
@@ -206,7 +208,7 @@ def test_mapper_prefixer_estimator_transmitter_bindings(gp, port):
     h = est.estimate_frame(cfg.core_preamble)
     assert h.shape == (est.frame_len(),)
     assert np.abs(h - 1).max() < 1e-5, 'flat channel gives all ones (qa_channel_estimator_cc.py:63-86)'
-    rxp = cfg.core_preamble * (0.5 + 0.2j) + 0.01 * design.get_random_qpsk(2 * cfg.subcarriers, rng)
+    rxp = cfg.core_preamble * (0.5 + 0.2j) + 0.01 * design.get_random_qpsk(2 * cfg.subcarriers, rng=rng)
     assert_complex_close(est.estimate_frame(rxp), oest.estimate_frame(rxp), what='estimate_frame')
     assert abs(est.estimate_snr(rxp) - oest.estimate_snr(rxp)) <= 1e-3 * abs(oest.estimate_snr(rxp))
     tx = gp.Transmitter(cfg.timeslots, cfg.subcarriers, cfg.active_subcarriers, cfg.cp_len, cfg.cs_len, cfg.ramp_len,
@@ -228,7 +230,7 @@ def test_advanced_receiver_binding(gp, port):
     smap = list(range(4, 52))
     rng = np.random.RandomState(11)
     sym = np.zeros((K, M), np.complex64)
-    sym[smap] = design.get_random_qpsk(len(smap) * M, rng).reshape(len(smap), M)
+    sym[smap] = design.get_random_qpsk(len(smap) * M, rng=rng).reshape(len(smap), M)
     x = capi.Modulator(M, K, L, taps, lib=port).modulate(sym.ravel())
     ar = gp.Advanced_receiver(M, K, L, np.conj(taps), smap, 3)
     oar = capi.Advanced_receiver(M, K, L, np.conj(taps), smap, 3, lib=port)

@@ -80,3 +80,60 @@ for (M, K, L, plan) in [(5,16,2,(16,1)), (9,64,2,(8,8)), (15,256,2,(16,16)), (15
     e1 = np.abs(fused_mod(d, tx_table(taps,M,K,L), M, K, plan)-ref_mod(d,taps,M,K,L)).max()
     e2 = np.abs(fused_rx(d, rx_table(taps,M,K,L), M, K, plan)-ref_rx_fd(d,taps,M,K,L)).max() if L >= 2 else 0
     print((M,K,L,plan), 'mod err %.2e  rx err %.2e' % (e1, e2))
+
+
+# ---------------------------------------------------------------------------------------------
+# v3 kernels: commuted form, row FFTs IN PLACE on the [k][t]-ordered frame, XOR-swizzled exchange.
+#   modulator: S[k*M+t] = d           -> rows t: K-IFFT over k (in place)  -> column n1: FFT_M, *Ctx, IFFT_M -> x
+#   receiver : column n1: FFT_M(x), *Crx, IFFT_M/M -> S[n1*M+t] -> rows t: K-FFT over n1 (in place) -> S = y[k][t]
+def row_fft_inplace_xor(S, M, t, R, sign, single):
+    """row t of the frame held as S[q*M + t], q = 0..K-1; natural order in and out."""
+    K = R if single else R * R
+    if single:
+        v = np.array([S[q * M + t] for q in range(K)])
+        X = np.fft.fft(v) if sign < 0 else np.fft.ifft(v) * K
+        for q in range(K): S[q * M + t] = X[q]
+        return
+    regs = {}
+    for n0 in range(R):   # pass 1, lane n0: registers a[i] = x[R*i + n0]
+        a = np.array([S[(R * i + n0) * M + t] for i in range(R)])
+        A = np.fft.fft(a) if sign < 0 else np.fft.ifft(a) * R
+        regs[n0] = A * np.exp(sign * 2j * np.pi * n0 * np.arange(R) / K)
+    for n0 in range(R):   # exchange write (after every lane has read): slot R*k1 + (n0 ^ k1)
+        for k1 in range(R): S[(R * k1 + (n0 ^ k1)) * M + t] = regs[n0][k1]
+    regs2 = {}
+    for k1 in range(R):   # pass 2, lane k1: registers b[n0]
+        b = np.array([S[(R * k1 + (n0 ^ k1)) * M + t] for n0 in range(R)])
+        regs2[k1] = np.fft.fft(b) if sign < 0 else np.fft.ifft(b) * R
+    for k1 in range(R):   # natural-order write (after every lane has read)
+        for k0 in range(R): S[(k1 + R * k0) * M + t] = regs2[k1][k0]
+
+
+def v3_mod(d, C, M, K, R, single):
+    S = d.astype(complex).copy()
+    for t in range(M): row_fft_inplace_xor(S, M, t, R, +1, single)
+    x = np.zeros(M * K, complex)
+    for n1 in range(K):
+        v = np.fft.fft(S[n1 * M:(n1 + 1) * M]) * C[:, n1]
+        x[n1 + K * np.arange(M)] = np.fft.ifft(v) * M
+    return x
+
+
+def v3_rx(x, C, M, K, R, single, td=True):
+    S = np.zeros(M * K, complex)
+    for n1 in range(K):
+        v = np.fft.fft(x[n1 + K * np.arange(M)]) * C[:, n1]
+        S[n1 * M:(n1 + 1) * M] = np.fft.ifft(v) if td else v
+    for t in range(M): row_fft_inplace_xor(S, M, t, R, -1, single)
+    return S.reshape(K, M)
+
+
+print('v3 (commuted, in place):')
+for (M, K, L, R, single) in [(5, 16, 2, 16, True), (9, 64, 2, 8, False), (15, 256, 2, 16, False), (15, 1024, 2, 32, False)]:
+    taps = rng.standard_normal(M * L) + 1j * rng.standard_normal(M * L)
+    d = rng.standard_normal(M * K) + 1j * rng.standard_normal(M * K)
+    e1 = np.abs(v3_mod(d, tx_table(taps, M, K, L), M, K, R, single) - ref_mod(d, taps, M, K, L)).max()
+    Rfd = ref_rx_fd(d, taps, M, K, L)
+    e2 = np.abs(v3_rx(d, rx_table(taps, M, K, L), M, K, R, single, td=False) - Rfd).max()
+    e3 = np.abs(v3_rx(d, rx_table(taps, M, K, L), M, K, R, single, td=True) - np.fft.ifft(Rfd, axis=1)).max()
+    print((M, K, L, R), 'mod err %.2e  rx fd err %.2e  rx td err %.2e' % (e1, e2, e3))
