@@ -580,6 +580,11 @@ struct gfdm_advanced_receiver : gfdm_receiver {
 static void advanced_run(gfdm_advanced_receiver* h, cpx* out, const cpx* in, const cpx* eq, size_t frames)
 {
     if (!frames) return;
+    if (h->fused.sic_available() && h->ic_iter >= 0 && aligned16(out) && aligned16(in) && aligned16(eq)) {
+        h->launches += h->fused.demodulate_sic(out, in, eq, frames, h->ic_iter, h->phase_comp, h->stream);
+        h->last_kernel = h->fused.sic_name();
+        return;
+    }
     const size_t el = frames * (size_t)h->N;
     h->freq_block.ensure(el * sizeof(cpx));
     h->ic_time.ensure(el * sizeof(cpx));
@@ -623,6 +628,7 @@ int gfdm_advanced_receiver_create(gfdm_advanced_receiver** out, int M, int K, in
     h->d_active = upload(active);
     h->d_smap = upload(h->smap);
     h->d_points = dev_upload(vec(c->points, c->n_points));
+    if (h->fused.available()) h->fused.init_sic(h->ic_taps, vec(c->points, c->n_points), h->rule, h->smap);
     *out = h.release();
     API_CATCH
 }

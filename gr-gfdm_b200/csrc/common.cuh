@@ -57,6 +57,25 @@ __device__ __forceinline__ cpx cmul_rn(cpx a, cpx b)
                        __fadd_rn(__fmul_rn(a.x, b.y), __fmul_rn(a.y, b.x)));
 }
 
+// Hard decision of gr::digital::constellation::decision_maker (call site
+// lib/advanced_receiver_kernel_cc.cc:114-120): rule 1 = constellation_qpsk's sign rule, otherwise
+// nearest point, first minimum wins (unfused arithmetic so that ties break like the CPU oracle).
+__device__ __forceinline__ int decide_symbol(cpx s, const cpx* __restrict__ points, int n_points, int rule)
+{
+    if (rule == 1) return 2 * (s.y > 0.f) + (s.x > 0.f);
+    int best = 0;
+    float dmin = 0.f;
+    for (int i = 0; i < n_points; ++i) {
+        const float dr = __fsub_rn(s.x, points[i].x), di = __fsub_rn(s.y, points[i].y);
+        const float d = __fadd_rn(__fmul_rn(dr, dr), __fmul_rn(di, di));
+        if (i == 0 || d < dmin) {
+            dmin = d;
+            best = i;
+        }
+    }
+    return best;
+}
+
 // growable device buffer owned by a handle
 struct DeviceBuf {
     void* p = nullptr;

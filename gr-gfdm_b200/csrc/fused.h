@@ -21,6 +21,14 @@ public:
     int modulate(cpx* out, const cpx* in, size_t frames, cudaStream_t s);
     // out_td (soft symbols) and/or out_fd (fft_filter_downsample result) may be null; eq may be null
     int demodulate(cpx* out_td, cpx* out_fd, const cpx* in, const cpx* eq, size_t frames, cudaStream_t s);
+    // advanced receiver: successive interference cancellation resident in the receiver kernel.
+    // Call after init_rx; returns false when the shape / constellation has no fused path.
+    bool init_sic(const std::vector<std::complex<float>>& ic_taps, const std::vector<std::complex<float>>& points,
+                  int rule, const std::vector<int>& subcarrier_map);
+    bool sic_available() const;
+    int demodulate_sic(cpx* out, const cpx* in, const cpx* eq, size_t frames, int ic_iter, int phase_comp,
+                       cudaStream_t s);
+    const char* sic_name() const;
     const char* mod_name() const;
     const char* rx_name() const;
     void destroy();

@@ -31,6 +31,7 @@
 
 #include <cmath>
 #include <cstring>
+#include <string>
 
 namespace gfdm {
 
@@ -135,7 +136,10 @@ struct Shape {
     static constexpr int BUF_ELEMS = ROW_ELEMS > STAGE_ELEMS ? ROW_ELEMS : STAGE_ELEMS;
     static constexpr int TW_ELEMS = TWO_PASS ? K : 0;
     // per-CTA shared memory budget in complex elements (228 KB per SM, 1 KB per CTA reserved)
-    static constexpr int TAPS_ELEMS = 64; // receive taps of the equalising path (L*M <= 64)
+    // small constants of the receiver: [0,64) receive taps of the equalising path (L*M <= 64),
+    // [64,96) interference-cancellation taps, [96,160) constellation points, [160,192) reduction scratch
+    static constexpr int TAPS_ELEMS = 192;
+    static constexpr int IC_OFF = 64, PTS_OFF = 96, RED_OFF = 160, MAX_POINTS = 64;
     static constexpr int BUDGET_ELEMS = ((233472 / MINB) - 1024) / 8 - 8 - TAPS_ELEMS;
     static constexpr int P_MAX = BUDGET_ELEMS - BUF_ELEMS - TW_ELEMS;
     static_assert(P_MAX >= 0, "frame group does not fit in shared memory");
@@ -367,13 +371,23 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_mod_kernel(cpx* __restric
 // out: [n_frames][N]; mode 0: soft symbols y (generic_work[_equalize]); mode 1: R (fft_[equalize_]filter_downsample).
 // Shared memory: R = row buffer / output staging (bulk-stored), P = the first PR sample rows of every
 // frame of the NEXT group (TMA prefetch); the remaining rows are prefetched into registers.
-template <class S>
+// successive interference cancellation resident in the receiver kernel
+// (lib/advanced_receiver_kernel_cc.cc:56-123, lib/receiver_kernel_cc.cc:274-299)
+struct SicArgs {
+    const cpx* ic_taps;          // [M]
+    const cpx* points;           // constellation points
+    const unsigned char* count;  // [K] multiplicity of subcarrier k in the subcarrier map (0 = inactive)
+    int n_points, rule, ic_iter, phase_comp;
+    float inv_map_total;         // 1 / (map.size() * M)
+};
+
+template <class S, bool SIC>
 __global__ void __launch_bounds__(S::T, S::MINB) fused_rx_kernel(cpx* __restrict__ out, const cpx* __restrict__ in,
                                                                  const cpx* __restrict__ eq,
                                                                  const cpx* __restrict__ table,
                                                                  const cpx* __restrict__ tw,
                                                                  const cpx* __restrict__ taps, int L, int mode,
-                                                                 int n_frames)
+                                                                 int n_frames, SicArgs sic)
 {
     constexpr int M = S::M, K = S::K, N = S::N, T = S::T, IPT = S::IPT, F = S::F, RS = S::RS, PR = S::PR;
     constexpr int XR = M - PR > 0 ? M - PR : 1;
@@ -390,7 +404,12 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_rx_kernel(cpx* __restrict
 
     for (int i = tid; i < S::TW_ELEMS; i += T) tw_s[i] = tw[i];
     for (int i = tid; i < S::TBL_ELEMS; i += T) tbl_s[i] = table[i];
-    for (int i = tid; i < L * M && i < S::TAPS_ELEMS; i += T) taps_s[i] = taps[i];
+    for (int i = tid; i < L * M && i < S::IC_OFF; i += T) taps_s[i] = taps[i];
+    if constexpr (SIC) {
+        static_assert(IPT == 1, "the cancellation loop keeps one subcarrier per thread in registers");
+        for (int i = tid; i < M && i < 32; i += T) taps_s[S::IC_OFF + i] = sic.ic_taps[i];
+        for (int i = tid; i < sic.n_points && i < S::MAX_POINTS; i += T) taps_s[S::PTS_OFF + i] = sic.points[i];
+    }
     if (tid == 0) mbar_init(bar_p, 1);
     __syncthreads();
 
@@ -558,12 +577,75 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_rx_kernel(cpx* __restrict
             }
             __syncthreads();
         }
+        if constexpr (SIC) {
+            // v[0] = R_k (kept frequency block of this thread's subcarrier); iterate decide -> re-modulate the
+            // neighbours -> subtract -> back to time domain without leaving the SM
+            const int f = tid / K, k = tid - f * K;
+            const cpx* ic_s = taps_s + S::IC_OFF;
+            const cpx* pts_s = taps_s + S::PTS_OFF;
+            float* red_s = reinterpret_cast<float*>(taps_s + S::RED_OFF); // 64 floats
+            const int cnt = sic.count[k];
+            cpx y[M];
+#pragma unroll
+            for (int m = 0; m < M; ++m) y[m] = v[0][m];
+            rf::FFTN<M, +1>::run(y);
+#pragma unroll
+            for (int m = 0; m < M; ++m) y[m] = cscale(y[m], inv_m);
+            for (int it = 0; it < sic.ic_iter; ++it) {
+                cpx d[M];
+#pragma unroll
+                for (int m = 0; m < M; ++m)
+                    d[m] = cnt ? pts_s[decide_symbol(y[m], pts_s, sic.n_points, sic.rule)] : cmake(0.f, 0.f);
+                if (sic.phase_comp > 0 && it == 0) {
+                    // calculate_phase_offset (:78-91): mean over the map of arg(decided) - arg(soft); deterministic
+                    // tree: lanes of a frame -> per-warp partial -> fixed-order sum
+                    float part = 0.f;
+                    if (cnt) {
+#pragma unroll
+                        for (int m = 0; m < M; ++m) part += atan2f(d[m].y, d[m].x) - atan2f(y[m].y, y[m].x);
+                        part *= (float)cnt;
+                    }
+                    constexpr int G = K < 32 ? K : 32;       // lanes of one frame inside a warp
+                    constexpr int NP = K / G;                 // partials per frame
+#pragma unroll
+                    for (int o = G / 2; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+                    if ((tid & (G - 1)) == 0) red_s[tid / G] = part;
+                    __syncthreads();
+                    float phi = 0.f;
+                    for (int q = 0; q < NP; ++q) phi += red_s[f * NP + q];
+                    phi *= sic.inv_map_total;
+                    float sn, cs;
+                    sincosf(phi, &sn, &cs);
+                    const cpx rot = cmake(cs, sn);
+#pragma unroll
+                    for (int m = 0; m < M; ++m) v[0][m] = cmul(v[0][m], rot); // the kept block stays rotated (:61-71)
+                }
+                cpx* mine = buf + (size_t)tid * M;
+#pragma unroll
+                for (int m = 0; m < M; ++m) mine[m] = d[m];
+                __syncthreads();
+                const int kp = k == 0 ? K - 1 : k - 1, kn = k == K - 1 ? 0 : k + 1;
+                const cpx* prev = buf + ((size_t)f * K + kp) * M;
+                const cpx* next = buf + ((size_t)f * K + kn) * M;
+#pragma unroll
+                for (int m = 0; m < M; ++m) d[m] = cadd(prev[m], next[m]);
+                __syncthreads();
+                rf::FFTN<M, -1>::run(d);
+#pragma unroll
+                for (int m = 0; m < M; ++m) y[m] = csub(v[0][m], cmul(ic_s[m], d[m]));
+                rf::FFTN<M, +1>::run(y);
+#pragma unroll
+                for (int m = 0; m < M; ++m) y[m] = cscale(y[m], inv_m);
+            }
+#pragma unroll
+            for (int m = 0; m < M; ++m) v[0][m] = y[m];
+        }
         // output staging in the linear [k][m] order; item j covers the contiguous slice
         // [j*T*M, (j+1)*T*M), which is bulk-stored as soon as it is complete so that the first
         // slice drains to HBM while the next item's M-point IFFT runs
 #pragma unroll
         for (int j = 0; j < IPT; ++j) {
-            if (mode == 0) {
+            if (!SIC && mode == 0) {
                 rf::FFTN<M, +1>::run(v[j]);
 #pragma unroll
                 for (int m = 0; m < M; ++m) v[j][m] = cscale(v[j][m], inv_m);
@@ -595,11 +677,21 @@ static void launch_mod(cpx* out, const cpx* in, const cpx* table, const cpx* tw,
 {
     fused_mod_kernel<S><<<grid, S::T, S::SMEM_BYTES, s>>>(out, in, table, tw, n_frames);
 }
+typedef void (*sic_launch_t)(cpx*, const cpx*, const cpx*, const cpx*, const cpx*, const cpx*, int, int, int,
+                             SicArgs, cudaStream_t);
 template <class S>
 static void launch_rx(cpx* out, const cpx* in, const cpx* eq, const cpx* table, const cpx* tw, const cpx* taps, int L,
                       int mode, int n_frames, int grid, cudaStream_t s)
 {
-    fused_rx_kernel<S><<<grid, S::T, S::SMEM_BYTES, s>>>(out, in, eq, table, tw, taps, L, mode, n_frames);
+    fused_rx_kernel<S, false><<<grid, S::T, S::SMEM_BYTES, s>>>(out, in, eq, table, tw, taps, L, mode, n_frames,
+                                                                 SicArgs{});
+}
+template <class S>
+static void launch_sic(cpx* out, const cpx* in, const cpx* eq, const cpx* table, const cpx* tw, const cpx* taps, int L,
+                       int n_frames, int grid, SicArgs sic, cudaStream_t s)
+{
+    if constexpr (S::IPT == 1)
+        fused_rx_kernel<S, true><<<grid, S::T, S::SMEM_BYTES, s>>>(out, in, eq, table, tw, taps, L, 0, n_frames, sic);
 }
 
 struct ShapeEntry {
@@ -609,8 +701,11 @@ struct ShapeEntry {
     const char* rx_name;
     mod_launch_t mod;
     rx_launch_t rx;
+    sic_launch_t sic; // null when the shape keeps more than one subcarrier per thread
     const void* mod_fn;
     const void* rx_fn;
+    const void* sic_fn;
+    const char* sic_name;
 };
 
 template <class S>
@@ -624,7 +719,14 @@ static ShapeEntry make_entry(const char* mn, const char* rn)
     e.mod = &launch_mod<S>;
     e.rx = &launch_rx<S>;
     e.mod_fn = (const void*)&fused_mod_kernel<S>;
-    e.rx_fn = (const void*)&fused_rx_kernel<S>;
+    e.rx_fn = (const void*)&fused_rx_kernel<S, false>;
+    e.sic = nullptr;
+    e.sic_fn = nullptr;
+    e.sic_name = "none";
+    if constexpr (S::IPT == 1) {
+        e.sic = &launch_sic<S>;
+        e.sic_fn = (const void*)&fused_rx_kernel<S, true>;
+    }
     return e;
 }
 
@@ -650,7 +752,13 @@ struct FusedImpl {
     cpx* d_table_eq = nullptr; // rx only: plain twiddle
     cpx* d_tw = nullptr;
     cpx* d_taps = nullptr;
-    int mod_grid_cap = 0, rx_grid_cap = 0;
+    int mod_grid_cap = 0, rx_grid_cap = 0, sic_grid_cap = 0;
+    // interference cancellation (advanced receiver)
+    cpx* d_ic = nullptr;
+    cpx* d_points = nullptr;
+    unsigned char* d_count = nullptr;
+    SicArgs sic{};
+    std::string sic_name;
 };
 
 static const ShapeEntry* find_shape(int M, int K)
@@ -797,6 +905,56 @@ int FusedModem::demodulate(cpx* out_td, cpx* out_fd, const cpx* in, const cpx* e
     return launches;
 }
 
+bool FusedModem::init_sic(const std::vector<std::complex<float>>& ic_taps,
+                          const std::vector<std::complex<float>>& points, int rule, const std::vector<int>& subcarrier_map)
+{
+    if (!impl_ || !impl_->e->sic) return false;
+    const ShapeEntry* e = impl_->e;
+    if ((int)ic_taps.size() != e->M || e->M > 32 || points.empty() || points.size() > 64) return false;
+    std::vector<unsigned char> count((size_t)e->K, 0);
+    for (int k : subcarrier_map) {
+        if (k < 0 || k >= e->K || count[k] == 255) return false;
+        ++count[k];
+    }
+    impl_->sic_grid_cap = grid_cap(e->sic_fn, e->T, e->smem);
+    impl_->d_ic = upload(to_cpx(ic_taps));
+    impl_->d_points = upload(to_cpx(points));
+    impl_->d_count = upload(count);
+    impl_->sic.ic_taps = impl_->d_ic;
+    impl_->sic.points = impl_->d_points;
+    impl_->sic.count = impl_->d_count;
+    impl_->sic.n_points = (int)points.size();
+    impl_->sic.rule = rule;
+    impl_->sic.inv_map_total = subcarrier_map.empty() ? 0.f : 1.0f / (float)(subcarrier_map.size() * (size_t)e->M);
+    impl_->sic_name = std::string(e->rx_name) + "+sic";
+    return true;
+}
+
+bool FusedModem::sic_available() const { return impl_ && impl_->d_count != nullptr; }
+
+int FusedModem::demodulate_sic(cpx* out, const cpx* in, const cpx* eq, size_t frames, int ic_iter, int phase_comp,
+                               cudaStream_t s)
+{
+    const ShapeEntry* e = impl_->e;
+    int launches = 0;
+    const size_t N = (size_t)e->M * e->K;
+    const size_t max_chunk = (size_t)1 << 20;
+    SicArgs a = impl_->sic;
+    a.ic_iter = ic_iter;
+    a.phase_comp = phase_comp;
+    for (size_t f0 = 0; f0 < frames; f0 += max_chunk) {
+        const int nf = (int)std::min(max_chunk, frames - f0);
+        const int groups = (nf + e->F - 1) / e->F;
+        const int grid = groups < impl_->sic_grid_cap ? groups : impl_->sic_grid_cap;
+        e->sic(out + f0 * N, in + f0 * N, eq ? eq + f0 * N : nullptr, eq ? impl_->d_table_eq : impl_->d_table, impl_->d_tw,
+               impl_->d_taps, impl_->L, nf, grid, a, s);
+        ++launches;
+    }
+    GFDM_CUDA_CHECK(cudaGetLastError());
+    return launches;
+}
+
+const char* FusedModem::sic_name() const { return sic_available() ? impl_->sic_name.c_str() : "none"; }
 const char* FusedModem::mod_name() const { return impl_ ? impl_->e->mod_name : "none"; }
 const char* FusedModem::rx_name() const { return impl_ ? impl_->e->rx_name : "none"; }
 
@@ -819,6 +977,9 @@ void FusedModem::destroy()
     if (impl_->d_table_eq) cudaFree(impl_->d_table_eq);
     if (impl_->d_tw) cudaFree(impl_->d_tw);
     if (impl_->d_taps) cudaFree(impl_->d_taps);
+    if (impl_->d_ic) cudaFree(impl_->d_ic);
+    if (impl_->d_points) cudaFree(impl_->d_points);
+    if (impl_->d_count) cudaFree(impl_->d_count);
     delete impl_;
     impl_ = nullptr;
 }

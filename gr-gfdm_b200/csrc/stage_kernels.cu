@@ -132,23 +132,7 @@ void launch_ic_subtract(cpx* out, const cpx* fd, const cpx* F, const cpx* ic_tap
     GFDM_CUDA_CHECK(cudaGetLastError());
 }
 
-// map_symbols_to_constellation_points, lib/advanced_receiver_kernel_cc.cc:109-123
-__device__ __forceinline__ int decide_symbol(cpx s, const cpx* __restrict__ points, int n_points, int rule)
-{
-    if (rule == 1) return 2 * (s.y > 0.f) + (s.x > 0.f);
-    int best = 0;
-    float dmin = 0.f;
-    for (int i = 0; i < n_points; ++i) {
-        const float dr = __fsub_rn(s.x, points[i].x), di = __fsub_rn(s.y, points[i].y);
-        const float d = __fadd_rn(__fmul_rn(dr, dr), __fmul_rn(di, di));
-        if (i == 0 || d < dmin) {
-            dmin = d;
-            best = i;
-        }
-    }
-    return best;
-}
-
+// map_symbols_to_constellation_points, lib/advanced_receiver_kernel_cc.cc:109-123 (decide_symbol: common.cuh)
 __global__ void __launch_bounds__(TH) decide_kernel(cpx* __restrict__ out, const cpx* __restrict__ in,
                                                     const unsigned char* __restrict__ active,
                                                     const cpx* __restrict__ points, int n_points, int rule, int M,
