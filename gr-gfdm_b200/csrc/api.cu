@@ -49,6 +49,10 @@ struct HandleBase {
     const char* last_kernel = "none";
     DeviceBuf stage_in, stage_in2, stage_out; // HOST-pointer staging
     DeviceBuf work_a, work_b, work_c;         // pipeline scratch
+    // pipelined HOST batches (host_pipeline below): two chunk slots, copy engines on their own streams
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    cudaEvent_t ev_in[2] = { nullptr, nullptr }, ev_run[2] = { nullptr, nullptr }, ev_out[2] = { nullptr, nullptr };
+    DeviceBuf slot_in0[2], slot_in1[2], slot_out[2];
 
     void open()
     {
@@ -66,6 +70,16 @@ struct HandleBase {
     {
         stage_in.release(); stage_in2.release(); stage_out.release();
         work_a.release(); work_b.release(); work_c.release();
+        for (int i = 0; i < 2; ++i) {
+            slot_in0[i].release(); slot_in1[i].release(); slot_out[i].release();
+            if (ev_in[i]) cudaEventDestroy(ev_in[i]);
+            if (ev_run[i]) cudaEventDestroy(ev_run[i]);
+            if (ev_out[i]) cudaEventDestroy(ev_out[i]);
+            ev_in[i] = ev_run[i] = ev_out[i] = nullptr;
+        }
+        if (s_h2d) cudaStreamDestroy(s_h2d);
+        if (s_d2h) cudaStreamDestroy(s_d2h);
+        s_h2d = s_d2h = nullptr;
         if (own_stream && stream) cudaStreamDestroy(stream);
         stream = nullptr;
     }
@@ -144,6 +158,81 @@ struct Staging {
 static size_t chunk_frames(size_t bytes_per_frame, size_t n)
 {
     const size_t budget = (size_t)256 << 20;
+    size_t c = budget / (bytes_per_frame ? bytes_per_frame : 1);
+    if (c < 1) c = 1;
+    return c < n ? c : n;
+}
+
+// Pipelined HOST batch: the batch is cut into chunks of `chunk` frames; the host->device copy of chunk
+// i+1 (stream s_h2d), the kernels of chunk i (the handle's stream) and the device->host copy of chunk
+// i-1 (stream s_d2h) run concurrently, so both PCIe directions stay busy.  run(dout, d0, d1, f0, nf)
+// enqueues the kernels of one chunk on h->stream.  Synchronous for the caller, like generic_work.
+// seed_out: the staged output starts as the caller's data (kernels that leave elements untouched).
+template <class Run>
+static void host_pipeline(HandleBase* h, size_t n, size_t chunk, const gfdm_complex* in0, size_t in0_sz,
+                          const gfdm_complex* in1, size_t in1_sz, gfdm_complex* out, size_t out_sz, bool seed_out,
+                          Run run)
+{
+    if (!n) return;
+    if (chunk < 1) chunk = 1;
+    if (!h->s_h2d) {
+        GFDM_CUDA_CHECK(cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
+        GFDM_CUDA_CHECK(cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            GFDM_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
+            GFDM_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_run[i], cudaEventDisableTiming));
+            GFDM_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_out[i], cudaEventDisableTiming));
+        }
+    }
+    const size_t c0 = std::min(chunk, n);
+    for (int i = 0; i < 2; ++i) {
+        if (in0 && in0_sz) h->slot_in0[i].ensure(c0 * in0_sz * sizeof(cpx));
+        if (in1 && in1_sz) h->slot_in1[i].ensure(c0 * in1_sz * sizeof(cpx));
+        h->slot_out[i].ensure(std::max<size_t>(c0 * out_sz, 1) * sizeof(cpx));
+    }
+    // work queued earlier on the handle's stream may still use the slots (a DEVICE call followed by a HOST call)
+    GFDM_CUDA_CHECK(cudaEventRecord(h->ev_run[0], h->stream));
+    GFDM_CUDA_CHECK(cudaStreamWaitEvent(h->s_h2d, h->ev_run[0], 0));
+    size_t idx = 0;
+    for (size_t f0 = 0; f0 < n; f0 += chunk, ++idx) {
+        const size_t nf = std::min(chunk, n - f0);
+        const int sl = (int)(idx & 1);
+        cpx* d0 = nullptr;
+        cpx* d1 = nullptr;
+        cpx* dout = h->slot_out[sl].as<cpx>();
+        // inputs of this slot are free once the kernels of chunk idx-2 have run
+        if (idx >= 2) GFDM_CUDA_CHECK(cudaStreamWaitEvent(h->s_h2d, h->ev_run[sl], 0));
+        if (in0 && in0_sz) {
+            d0 = h->slot_in0[sl].as<cpx>();
+            GFDM_CUDA_CHECK(cudaMemcpyAsync(d0, in0 + f0 * in0_sz, nf * in0_sz * sizeof(cpx), cudaMemcpyHostToDevice, h->s_h2d));
+        }
+        if (in1 && in1_sz) {
+            d1 = h->slot_in1[sl].as<cpx>();
+            GFDM_CUDA_CHECK(cudaMemcpyAsync(d1, in1 + f0 * in1_sz, nf * in1_sz * sizeof(cpx), cudaMemcpyHostToDevice, h->s_h2d));
+        }
+        if (seed_out) {
+            // the output slot is free once chunk idx-2 has been copied back
+            if (idx >= 2) GFDM_CUDA_CHECK(cudaStreamWaitEvent(h->s_h2d, h->ev_out[sl], 0));
+            GFDM_CUDA_CHECK(cudaMemcpyAsync(dout, out + f0 * out_sz, nf * out_sz * sizeof(cpx), cudaMemcpyHostToDevice, h->s_h2d));
+        }
+        GFDM_CUDA_CHECK(cudaEventRecord(h->ev_in[sl], h->s_h2d));
+        GFDM_CUDA_CHECK(cudaStreamWaitEvent(h->stream, h->ev_in[sl], 0));
+        if (idx >= 2) GFDM_CUDA_CHECK(cudaStreamWaitEvent(h->stream, h->ev_out[sl], 0));
+        run(dout, d0, d1, f0, nf);
+        GFDM_CUDA_CHECK(cudaEventRecord(h->ev_run[sl], h->stream));
+        GFDM_CUDA_CHECK(cudaStreamWaitEvent(h->s_d2h, h->ev_run[sl], 0));
+        if (out_sz)
+            GFDM_CUDA_CHECK(cudaMemcpyAsync(out + f0 * out_sz, dout, nf * out_sz * sizeof(cpx), cudaMemcpyDeviceToHost, h->s_d2h));
+        GFDM_CUDA_CHECK(cudaEventRecord(h->ev_out[sl], h->s_d2h));
+    }
+    GFDM_CUDA_CHECK(cudaStreamSynchronize(h->s_d2h));
+    GFDM_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+}
+
+// frames per pipeline chunk: 32 MB of host traffic per chunk keeps fill/drain below a millisecond
+static size_t pipe_chunk(size_t bytes_per_frame, size_t n)
+{
+    const size_t budget = (size_t)32 << 20;
     size_t c = budget / (bytes_per_frame ? bytes_per_frame : 1);
     if (c < 1) c = 1;
     return c < n ? c : n;
@@ -336,14 +425,8 @@ int gfdm_modulator_work_batch(gfdm_modulator* h, gfdm_complex* out, const gfdm_c
     if (mem == GFDM_MEM_DEVICE) {
         modulator_run(h, reinterpret_cast<cpx*>(out), reinterpret_cast<const cpx*>(in), (size_t)n);
     } else {
-        const size_t c = chunk_frames(2 * sizeof(cpx) * h->N, (size_t)n);
-        for (size_t f0 = 0; f0 < (size_t)n; f0 += c) {
-            const size_t nf = std::min(c, (size_t)n - f0), el = nf * h->N;
-            const cpx* di = st.in(in + f0 * h->N, el, h->stage_in);
-            cpx* dout = st.out(out, el, h->stage_out);
-            modulator_run(h, dout, di, nf);
-            st.finish(out + f0 * h->N, el, h->stage_out);
-        }
+        host_pipeline(h, (size_t)n, pipe_chunk(2 * sizeof(cpx) * h->N, (size_t)n), in, h->N, nullptr, 0, out, h->N, false,
+                      [&](cpx* dout, const cpx* d0, const cpx*, size_t, size_t nf) { modulator_run(h, dout, d0, nf); });
     }
     API_CATCH
 }
@@ -496,12 +579,7 @@ static int receiver_batch(gfdm_receiver* h, RxOp op, gfdm_complex* out, const gf
     if (op == RX_CANCEL && !in1) throw std::invalid_argument("fd_in MUST NOT be NULL");
     Staging st(h, mem);
     const size_t N = h->N;
-    const size_t c = mem == GFDM_MEM_DEVICE ? (size_t)n : chunk_frames(3 * sizeof(cpx) * N, (size_t)n);
-    for (size_t f0 = 0; f0 < (size_t)n; f0 += c) {
-        const size_t nf = std::min(c, (size_t)n - f0), el = nf * N;
-        const cpx* d0 = st.in(in0 + f0 * N, el, h->stage_in);
-        const cpx* d1 = st.in(in1 ? in1 + f0 * N : nullptr, el, h->stage_in2);
-        cpx* dout = st.out(out + f0 * N, el, h->stage_out);
+    auto run = [&](cpx* dout, const cpx* d0, const cpx* d1, size_t, size_t nf) {
         switch (op) {
         case RX_WORK: receiver_run(h, dout, d0, d1, nf); break;
         case RX_FD: receiver_fd(h, dout, d0, d1, nf); break;
@@ -511,8 +589,11 @@ static int receiver_batch(gfdm_receiver* h, RxOp op, gfdm_complex* out, const gf
             break;
         case RX_CANCEL: receiver_cancel(h, dout, d0, d1, nf); break;
         }
-        st.finish(out + f0 * N, el, h->stage_out);
-    }
+    };
+    if (mem == GFDM_MEM_DEVICE)
+        run(reinterpret_cast<cpx*>(out), reinterpret_cast<const cpx*>(in0), reinterpret_cast<const cpx*>(in1), 0, (size_t)n);
+    else
+        host_pipeline(h, (size_t)n, pipe_chunk((in1 ? 3 : 2) * sizeof(cpx) * N, (size_t)n), in0, N, in1, N, out, N, false, run);
     API_CATCH
 }
 int gfdm_receiver_work_batch(gfdm_receiver* h, gfdm_complex* out, const gfdm_complex* in, const gfdm_complex* eq,
@@ -656,15 +737,11 @@ int gfdm_advanced_receiver_work_batch(gfdm_advanced_receiver* h, gfdm_complex* o
     if (n < 0) throw std::invalid_argument("n_frames MUST NOT be negative");
     Staging st(h, mem);
     const size_t N = h->N;
-    const size_t c = mem == GFDM_MEM_DEVICE ? (size_t)n : chunk_frames(6 * sizeof(cpx) * N, (size_t)n);
-    for (size_t f0 = 0; f0 < (size_t)n; f0 += c) {
-        const size_t nf = std::min(c, (size_t)n - f0), el = nf * N;
-        const cpx* d0 = st.in(in + f0 * N, el, h->stage_in);
-        const cpx* d1 = st.in(eq ? eq + f0 * N : nullptr, el, h->stage_in2);
-        cpx* dout = st.out(out + f0 * N, el, h->stage_out);
-        advanced_run(h, dout, d0, d1, nf);
-        st.finish(out + f0 * N, el, h->stage_out);
-    }
+    auto run = [&](cpx* dout, const cpx* d0, const cpx* d1, size_t, size_t nf) { advanced_run(h, dout, d0, d1, nf); };
+    if (mem == GFDM_MEM_DEVICE)
+        run(reinterpret_cast<cpx*>(out), reinterpret_cast<const cpx*>(in), reinterpret_cast<const cpx*>(eq), 0, (size_t)n);
+    else
+        host_pipeline(h, (size_t)n, pipe_chunk((eq ? 3 : 2) * sizeof(cpx) * N, (size_t)n), in, N, eq, N, out, N, false, run);
     API_CATCH
 }
 int gfdm_advanced_receiver_work(gfdm_advanced_receiver* h, gfdm_complex* out, const gfdm_complex* in)
