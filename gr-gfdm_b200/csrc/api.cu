@@ -478,7 +478,7 @@ static void receiver_free(gfdm_receiver* h)
 static void receiver_fd(gfdm_receiver* h, cpx* R, const cpx* in, const cpx* eq, size_t frames)
 {
     if (!frames) return;
-    if (h->fused.available() && aligned16(R) && aligned16(in) && aligned16(eq)) {
+    if (h->fused.available() && (!eq || h->fused.supports_eq()) && aligned16(R) && aligned16(in) && aligned16(eq)) {
         h->launches += h->fused.demodulate(nullptr, R, in, eq, frames, h->stream);
         h->last_kernel = h->fused.rx_name();
         return;
@@ -510,7 +510,7 @@ static void receiver_td(gfdm_receiver* h, cpx* out, const cpx* R, size_t frames)
 static void receiver_run(gfdm_receiver* h, cpx* out, const cpx* in, const cpx* eq, size_t frames)
 {
     if (!frames) return;
-    if (h->fused.available() && aligned16(out) && aligned16(in) && aligned16(eq)) {
+    if (h->fused.available() && (!eq || h->fused.supports_eq()) && aligned16(out) && aligned16(in) && aligned16(eq)) {
         h->launches += h->fused.demodulate(out, nullptr, in, eq, frames, h->stream);
         h->last_kernel = h->fused.rx_name();
         return;

@@ -10,6 +10,25 @@ namespace gfdm {
 
 struct FusedImpl;
 
+// host helpers shared by fused_modem.cu and fused_twopass.cu
+int fused_grid_cap(const void* fn, int threads, size_t smem); // persistent grid = SMs x resident CTAs
+std::vector<cpx> make_row_twiddles(int R1, int R2);           // W_K^{n0*k1} as [k1][n0], K = R1*R2
+// folded filter/twiddle table C[m][n1]; sign +1: modulator, -1: receiver
+std::vector<std::complex<double>> make_fold_table_d(int M, int K, int L, const std::vector<std::complex<float>>& taps,
+                                                    int sign, bool with_taps);
+std::vector<cpx> make_fold_table(int M, int K, int L, const std::vector<std::complex<float>>& taps, int sign,
+                                 bool with_taps);
+
+// two-pass kernels for frames larger than shared memory (fused_twopass.cu)
+struct TwoPass;
+bool twopass_supported(int M, int K);
+TwoPass* twopass_create_tx(int M, int K, int L, const std::vector<std::complex<float>>& taps);
+TwoPass* twopass_create_rx(int M, int K, int L, const std::vector<std::complex<float>>& taps);
+int twopass_modulate(TwoPass* t, cpx* out, const cpx* in, size_t frames, cudaStream_t s);
+int twopass_demodulate(TwoPass* t, cpx* out, const cpx* in, int mode, size_t frames, cudaStream_t s); // mode 0: y, 1: R
+const char* twopass_name(const TwoPass* t);
+void twopass_destroy(TwoPass* t);
+
 class FusedModem {
 public:
     // taps: already normalised, L*M entries, FFT order
@@ -17,6 +36,8 @@ public:
     void init_rx(int M, int K, int L, const std::vector<std::complex<float>>& taps,
                  const std::vector<std::complex<float>>& ic_taps);
     bool available() const { return impl_ != nullptr; }
+    // the one-tap equaliser is fused for single-pass shapes only
+    bool supports_eq() const;
     // in/out: [frames][N] device pointers; returns the number of kernel launches
     int modulate(cpx* out, const cpx* in, size_t frames, cudaStream_t s);
     // out_td (soft symbols) and/or out_fd (fft_filter_downsample result) may be null; eq may be null

@@ -1,0 +1,528 @@
+// fused_twopass.cu -- modulator and receiver for frames LARGER than shared memory (K = 2*K1;
+// BASELINE config 5: K = 2048, M = 15, N = 30720 complex = 245,760 B > 227 KB per SM).
+//
+// One CTA still owns a whole frame, but visits it in two passes.  The K-point transform over the
+// subcarrier index is split by decimation in frequency (tools/fused_math_check.py, "two-pass"):
+// pass p in {0,1} computes the K1-point transform whose results are the outputs of parity p, so a pass
+// needs a K1-row buffer only (the C3 kernel's shared-memory budget), reads the frame once (pass 0 from
+// HBM, pass 1 from L2 -- 36 MB of live frames for 148 CTAs against 126 MB of L2) and writes half of
+// the output.  HBM traffic stays at the algorithmic 16*N bytes per frame.
+//
+//   modulator (lib/modulator_kernel_cc.cc:98-141), W = e^{+j2pi/K}
+//     E^p_b'        = (d_b' + (-1)^p d_{b'+K1}) W^{p b'}              radix-2 butterfly on the raw symbols
+//     Z_m[2n'+p]    = IFFT_K1 over b' of FFT_M(E^p_b')[m]             stage A, row FFTs (stage B)
+//     x[2n'+p+K n2] = IFFT_M over m of C_tx[m][2n'+p] Z_m[2n'+p]      stage C
+//   receiver (lib/receiver_kernel_cc.cc:165-225,301-307), W = e^{-j2pi/K}
+//     U_n1          = FFT_M over n2 of x[n1 + K n2]                   both halves n1 = n', n'+K1 per pass
+//     B^p_m[n']     = Tlo^p[m][n'] U_n'[m] + Thi^p[m][n'] U_{n'+K1}[m]
+//                     Tlo^p = C_rx[m][n'] W^{p n'},  Thi^p = (-1)^p C_rx[m][n'+K1] W^{p n'}
+//     R_{2k'+p}[m]  = FFT_K1 over n' of B^p_m[n'];   y_{2k'+p} = IFFT_M(R_{2k'+p}) / M
+//
+// Shared memory per CTA (same carve-up as fused_modem.cu): row buffer `buf` (M rows of K1, padded),
+// the row-FFT twiddles and the staging region P.  Input moves by cp.async.bulk (TMA 1D) and is prefetched
+// one pass ahead wherever a region is free; the pieces that cannot be resident early are fetched one
+// compute step ahead.  The equalising / interference-cancelling variants are not provided for this shape
+// (the filter needs both parities of Y); those entry points use the staged path of api.cu.
+#include "fused.h"
+#include "fused_dev.cuh"
+
+#include <cmath>
+#include <string>
+
+namespace gfdm {
+
+// ----------------------------------------------------------------------------------------
+// modulator.  in/out: [n_frames][N], N = M*2*K1; tableP: [2][M][K1] = C_tx[m][2n'+p]; tw: row-FFT
+// twiddles of the K1-point transform; w2: W^{b'} = e^{+j2pi b'/K}, b' < K1.
+// Pieces of the staged frame (T*M elements each): LO0 = k < T, LO1 = T <= k < K1, HI0 = K1 <= k < K1+T,
+// HI1 = k >= K1+T.  P holds LO0 and the first HA elements of HI1, buf holds LO1|HI0 (contiguous in
+// HBM: one copy); the rest of HI1 lands on LO0's place as soon as step 0 has consumed it.
+template <class S>
+__global__ void __launch_bounds__(S::T, 1) fused_mod2_kernel(cpx* __restrict__ out, const cpx* __restrict__ in,
+                                                            const cpx* __restrict__ tableP,
+                                                            const cpx* __restrict__ tw, const cpx* __restrict__ w2,
+                                                            cpx* __restrict__ scratch, int n_frames)
+{
+    constexpr int M = S::M, K1 = S::K, K = 2 * K1, N = M * K, T = S::T, RS = S::RS;
+    static_assert(S::F == 1 && S::IPT == 2 && S::TWO_PASS, "two-pass kernels: one half-frame per CTA pass, two items per thread");
+    constexpr int PIECE = T * M;                                      // elements of one piece
+    constexpr int HA = ((S::P_ELEMS - PIECE) / (2 * M)) * (2 * M);    // head of HI1 that fits beside LO0 (whole record pairs)
+    constexpr int HB = PIECE - HA;                                    // late part of HI1
+    static_assert(HA > 0 && HB > 0 && HB <= PIECE && 2 * PIECE <= S::BUF_ELEMS, "staging does not fit");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    cpx* buf = reinterpret_cast<cpx*>(smem_raw);
+    cpx* tw_s = buf + S::BUF_ELEMS;
+    cpx* pre = tw_s + S::TW_ELEMS + S::TBL_ELEMS;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(pre + S::P_ELEMS + S::TAPS_ELEMS);
+    uint64_t* bar_p = bars;     // LO0 + head of HI1 (region P)
+    uint64_t* bar_r = bars + 1; // LO1 | HI0 (region buf)
+    uint64_t* bar_l = bars + 2; // late part of HI1
+    const int tid = threadIdx.x;
+
+    for (int i = tid; i < S::TW_ELEMS; i += T) tw_s[i] = tw[i];
+    if (tid == 0) {
+        mbar_init(bar_p, 1);
+        mbar_init(bar_r, 1);
+        mbar_init(bar_l, 1);
+    }
+    const cpx wj0 = w2[tid], wj1 = w2[tid + T];
+    // the frame is read twice (pass 0 keeps it in L2, pass 1 releases it); the even samples of pass 0
+    // wait in this CTA's L2-resident scratch so that pass 1 can write whole 16-byte sample pairs
+    // (the policies are re-created where they are used: one instruction each, no live registers)
+    __syncthreads();
+
+    // `first`: pass 0 of the frame reads it from HBM (keep it in L2); pass 1 reads it again (then drop it)
+    auto load_p = [&](int g, bool first) {
+        const cpx* f = in + (size_t)g * N;
+        const uint64_t pol = first ? l2_policy_evict_last() : l2_policy_evict_first();
+        mbar_expect_tx(bar_p, (uint32_t)(PIECE + HA) * sizeof(cpx));
+        bulk_load_hint(pre, f, PIECE * sizeof(cpx), bar_p, pol);
+        bulk_load_hint(pre + PIECE, f + 3 * PIECE, HA * sizeof(cpx), bar_p, pol);
+        if (first) bulk_prefetch_l2(f + 3 * PIECE + HA, HB * sizeof(cpx)); // the late piece has one step to arrive
+    };
+    auto load_r = [&](int g, bool first) {
+        mbar_expect_tx(bar_r, (uint32_t)(2 * PIECE) * sizeof(cpx));
+        bulk_load_hint(buf, in + (size_t)g * N + PIECE, 2 * PIECE * sizeof(cpx), bar_r,
+                       first ? l2_policy_evict_last() : l2_policy_evict_first());
+    };
+    auto load_l = [&](int g, bool first) {
+        mbar_expect_tx(bar_l, (uint32_t)HB * sizeof(cpx));
+        bulk_load_hint(pre, in + (size_t)g * N + 3 * PIECE + HA, HB * sizeof(cpx), bar_l,
+                       first ? l2_policy_evict_last() : l2_policy_evict_first());
+    };
+
+    int g = blockIdx.x;
+    if (tid == 0 && g < n_frames) {
+        load_p(g, true);
+        load_r(g, true);
+    }
+    uint32_t phase = 0;
+    STAGE_INIT();
+    for (; g < n_frames; g += gridDim.x) {
+#pragma unroll 1
+        for (int p = 0; p < 2; ++p) {
+            const int gn = p == 0 ? g : g + gridDim.x; // frame of the next pass
+            const bool has_next = gn < n_frames;
+            const float sgn = p ? -1.f : 1.f;
+            mbar_wait(bar_p, phase);
+            mbar_wait(bar_r, phase);
+            STAGE_MARK(0) // wait for the bulk loads
+            cpx v[2][M];
+            // ---- step 0: b' = tid, lo record in P (LO0), hi record in buf (HI0)
+            {
+                const cpx* lo = pre + tid * M;
+                const cpx* hi = buf + PIECE + tid * M;
+#pragma unroll
+                for (int m = 0; m < M; ++m) {
+                    const cpx a = lo[m], b = hi[m];
+                    v[0][m] = cmake(fmaf(sgn, b.x, a.x), fmaf(sgn, b.y, a.y));
+                }
+            }
+            __syncthreads(); // LO0 consumed: its place takes the late part of HI1
+            if (tid == 0) {
+                fence_proxy_async();
+                load_l(g, p == 0);
+            }
+            if (p) {
+#pragma unroll
+                for (int m = 0; m < M; ++m) v[0][m] = cmul(v[0][m], wj0);
+            }
+            rf::FFTN<M, -1>::run(v[0]);
+            STAGE_MARK(1) // step 0
+            mbar_wait(bar_l, phase);
+            // ---- step 1: b' = T + tid, lo record in buf (LO1), hi record in P (head after LO0, late part at 0)
+            {
+                const cpx* lo = buf + tid * M;
+                const int e = tid * M;
+                const cpx* hi = e < HA ? pre + PIECE + e : pre + (e - HA);
+#pragma unroll
+                for (int m = 0; m < M; ++m) {
+                    const cpx a = lo[m], b = hi[m];
+                    v[1][m] = cmake(fmaf(sgn, b.x, a.x), fmaf(sgn, b.y, a.y));
+                }
+            }
+            __syncthreads(); // staging fully consumed: P takes the next pass, buf takes the rows
+            if (tid == 0 && has_next) {
+                fence_proxy_async();
+                load_p(gn, p == 1);
+            }
+            if (p) {
+#pragma unroll
+                for (int m = 0; m < M; ++m) v[1][m] = cmul(v[1][m], wj1);
+            }
+            rf::FFTN<M, -1>::run(v[1]);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                cpx* dst = buf + S::swz(tid + j * T);
+#pragma unroll
+                for (int m = 0; m < M; ++m) dst[m * RS] = v[j][m];
+            }
+            __syncthreads();
+            STAGE_MARK(2) // step 1 + row writes
+            // ---- stage B: K1-point inverse FFT of every row
+            row_fft<S, +1>(buf, tw_s, tid);
+            STAGE_MARK(3) // row FFT
+            __syncthreads();
+            const cpx* tbl = tableP + (size_t)p * M * K1;
+            cpx tc[M];
+#pragma unroll
+            for (int m = 0; m < M; ++m) tc[m] = ldg_nc(tbl + m * K1 + tid);
+            // ---- stage C: column n' of all rows -> registers
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const cpx* src = buf + tid + j * T;
+#pragma unroll
+                for (int m = 0; m < M; ++m) v[j][m] = src[m * RS];
+            }
+            __syncthreads(); // rows are dead: buf takes LO1|HI0 of the next pass
+            if (tid == 0 && has_next) {
+                fence_proxy_async();
+                load_r(gn, p == 1);
+            }
+            STAGE_MARK(4) // stage C reads
+            cpx* sc = scratch + (size_t)blockIdx.x * (M * K1) + tid;
+#pragma unroll
+            for (int m = 0; m < M; ++m) v[0][m] = cmul(v[0][m], tc[m]);
+#pragma unroll
+            for (int m = 0; m < M; ++m) tc[m] = ldg_nc(tbl + m * K1 + tid + T);
+            rf::FFTN<M, +1>::run(v[0]);
+            if (p == 0) {
+                // even samples -> scratch [n2][n'] (whole lines, kept in L2 until pass 1 collects them)
+                const uint64_t pol_keep = l2_policy_evict_last();
+#pragma unroll
+                for (int n2 = 0; n2 < M; ++n2) stg_hint(sc + n2 * K1, v[0][n2], pol_keep);
+#pragma unroll
+                for (int m = 0; m < M; ++m) v[1][m] = cmul(v[1][m], tc[m]);
+                rf::FFTN<M, +1>::run(v[1]);
+#pragma unroll
+                for (int n2 = 0; n2 < M; ++n2) stg_hint(sc + T + n2 * K1, v[1][n2], pol_keep);
+            } else {
+                // odd samples join the even ones: one 16-byte store per sample pair.  The even samples of item 0
+                // are fetched while item 1's M-point IFFT runs, those of item 1 while item 0 is stored.
+                const uint64_t pol_drop = l2_policy_evict_first();
+#pragma unroll
+                for (int m = 0; m < M; ++m) v[1][m] = cmul(v[1][m], tc[m]);
+                cpx ev[M];
+#pragma unroll
+                for (int n2 = 0; n2 < M; ++n2) ev[n2] = ldg_hint(sc + n2 * K1, pol_drop);
+                rf::FFTN<M, +1>::run(v[1]);
+                cpx* dst = out + (size_t)g * N + 2 * tid;
+#pragma unroll
+                for (int n2 = 0; n2 < M; ++n2) {
+                    stg_stream4(dst + (size_t)n2 * K, ev[n2], v[0][n2]);
+                    ev[n2] = ldg_hint(sc + T + n2 * K1, pol_drop);
+                }
+#pragma unroll
+                for (int n2 = 0; n2 < M; ++n2) stg_stream4(dst + 2 * T + (size_t)n2 * K, ev[n2], v[1][n2]);
+            }
+            STAGE_MARK(5) // stage C compute + stores
+            phase ^= 1;
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------
+// receiver.  in: [n_frames][N] time samples; out: [n_frames][N]; mode 0: soft symbols, mode 1: R.
+// tables: [2 (p)][2 (half)][M][K1] = Tlo^p, Thi^p.  A pass has four steps (item j, half h): the thread's
+// sample column n1 = tid + j*T + h*K1, i.e. M quarter rows of T samples, each moved by one bulk copy.
+// Homes of the quarter rows (n2 = sample row) -- chosen so that every copy is issued at least one compute
+// step before its data is needed, except step 1 of the next pass (issued when the output staging is done):
+//   step 0 (j0,lo): P[n2*T]                                           issued after step 3 of the previous pass
+//   step 1 (j0,hi): upper half of row-buffer row n2                   issued at the end of the previous pass
+//   step 2 (j1,lo): n2 < NE: P[M*T + n2*T]   (issued after step 2 of the previous pass)
+//                   n2 >= NE: P[(n2-NE)*T]   (issued after step 0 of this pass)
+//   step 3 (j1,hi): n2 < NE: P[(M-NE)*T + n2*T]   (after step 0);  n2 >= NE: upper half of row n2-NE (after step 1)
+// Item 0's rows occupy the lower halves of the padded rows, item 1's the upper halves.
+template <class S>
+__global__ void __launch_bounds__(S::T, 1) fused_rx2_kernel(cpx* __restrict__ out, const cpx* __restrict__ in,
+                                                           const cpx* __restrict__ tables,
+                                                           const cpx* __restrict__ tw, int mode, int n_frames)
+{
+    constexpr int M = S::M, K1 = S::K, K = 2 * K1, N = M * K, T = S::T, RS = S::RS;
+    static_assert(S::F == 1 && S::IPT == 2 && S::TWO_PASS, "two-pass kernels: one half-frame per CTA pass, two items per thread");
+    constexpr int UP = RS / 2;                          // first slot of the upper half of a padded row
+    constexpr int NE = (S::P_ELEMS - M * T) / T;        // quarter rows of step 2 that fit beside step 0 in P
+    static_assert(S::swz(T - 1) < UP && UP + T <= RS, "row halves");
+    constexpr int N1A = (T * M - UP - T) / RS + 1;      // rows whose upper half lies inside item 0's output staging
+    static_assert(NE >= 1 && NE < M && M <= T / 32 && M * T * 2 <= S::BUF_ELEMS, "staging does not fit");
+    static_assert(N1A >= 1 && N1A < M && (N1A - 1) * RS + UP + T <= T * M && (M - NE - 1) * RS + UP + T <= S::BUF_ELEMS, "row halves");
+    constexpr uint32_t QBYTES = T * sizeof(cpx);
+    constexpr uint32_t STEP_BYTES = M * QBYTES;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    cpx* buf = reinterpret_cast<cpx*>(smem_raw);
+    cpx* tw_s = buf + S::BUF_ELEMS;
+    cpx* pre = tw_s + S::TW_ELEMS + S::TBL_ELEMS;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(pre + S::P_ELEMS + S::TAPS_ELEMS); // one per step
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const float inv_m = 1.0f / (float)M;
+
+    for (int i = tid; i < S::TW_ELEMS; i += T) tw_s[i] = tw[i];
+    if (tid == 0)
+        for (int s = 0; s < 4; ++s) mbar_init(bars + s, 1);
+    __syncthreads();
+
+    // quarter row n2 of step s of frame gg -> its home; issued by lane 0 of warp n2
+    auto qsrc = [&](int gg, int s, int n2) {
+        return in + (size_t)gg * N + (size_t)n2 * K + (s & 1) * K1 + (s >> 1) * T;
+    };
+    auto home = [&](int s, int n2) -> cpx* {
+        switch (s) {
+        case 0: return pre + n2 * T;
+        case 1: return buf + n2 * RS + UP;
+        case 2: return n2 < NE ? pre + (M + n2) * T : pre + (n2 - NE) * T;
+        default: return n2 < NE ? pre + (M - NE + n2) * T : buf + (n2 - NE) * RS + UP;
+        }
+    };
+    // issue the copies [n_lo, n_hi) of step s; `arm`: first issue point of this step's phase
+    // `first`: pass 0 of frame gg (from HBM, keep in L2 for pass 1); otherwise the second and last read
+    auto issue = [&](int gg, int s, int n_lo, int n_hi, bool arm, bool first) {
+        if (arm && tid == 0) mbar_expect_tx(bars + s, STEP_BYTES);
+        if (lane == 0 && warp >= n_lo && warp < n_hi) {
+            fence_proxy_async();
+            bulk_load_hint(home(s, warp), qsrc(gg, s, warp), QBYTES, bars + s,
+                           first ? l2_policy_evict_last() : l2_policy_evict_first());
+        }
+    };
+    // copy-out index math: element i = tid + q*T of a staged item is element e of record r
+    const int r0 = tid / M, e0 = tid - r0 * M;
+
+    int g = blockIdx.x;
+    if (g < n_frames) {
+        issue(g, 0, 0, M, true, true);
+        issue(g, 1, 0, M, true, true);
+        issue(g, 2, 0, NE, true, true);
+    }
+    uint32_t phase = 0;
+    STAGE_INIT();
+    for (; g < n_frames; g += gridDim.x) {
+#pragma unroll 1
+        for (int p = 0; p < 2; ++p) {
+            const int gn = p == 0 ? g : g + gridDim.x;
+            const bool has_next = gn < n_frames;
+            const cpx* tbl = tables + (size_t)p * 2 * M * K1;
+            cpx v[2][M];
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                const int j = s >> 1, h = s & 1;
+                cpx tc[M], x[M];
+                {
+                    const cpx* tcol = tbl + (size_t)h * M * K1 + tid + j * T;
+#pragma unroll
+                    for (int m = 0; m < M; ++m) tc[m] = ldg_nc(tcol + m * K1);
+                }
+                mbar_wait(bars + s, phase);
+#pragma unroll
+                for (int n2 = 0; n2 < M; ++n2) x[n2] = home(s, n2)[tid];
+                __syncthreads(); // step s consumed
+                if (s == 0) {
+                    issue(g, 2, NE, M, false, p == 0);
+                    issue(g, 3, 0, NE, true, p == 0);
+                } else if (s == 1) {
+                    issue(g, 3, NE, M, false, p == 0);
+                } else if (s == 2) {
+                    if (has_next) issue(gn, 2, 0, NE, true, p == 1);
+                } else {
+                    if (has_next) issue(gn, 0, 0, M, true, p == 1);
+                }
+                rf::FFTN<M, -1>::run(x);
+                if (h == 0) {
+#pragma unroll
+                    for (int m = 0; m < M; ++m) v[j][m] = cmul(x[m], tc[m]);
+                } else {
+#pragma unroll
+                    for (int m = 0; m < M; ++m) v[j][m] = cfma(x[m], tc[m], v[j][m]);
+                    cpx* dst = buf + S::swz(tid + j * T);
+#pragma unroll
+                    for (int m = 0; m < M; ++m) dst[m * RS] = v[j][m];
+                }
+                STAGE_MARK(20 + s) // step s
+            }
+            __syncthreads();
+            STAGE_MARK(16) // barrier after the row writes
+            // ---- stage B: K1-point forward FFT of every row
+            row_fft<S, -1>(buf, tw_s, tid);
+            STAGE_MARK(17) // row FFT
+            __syncthreads();
+            // ---- stage C': column k' of all rows = the M bins of subcarrier 2k'+p
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const cpx* src = buf + tid + j * T;
+#pragma unroll
+                for (int m = 0; m < M; ++m) v[j][m] = src[m * RS];
+            }
+            __syncthreads();
+            STAGE_MARK(18) // stage C' reads
+            // output: records of item j staged at buf[j*T*M ...] in [k'][m] order, then written with
+            // consecutive lanes on consecutive elements (records of the other parity lie in between)
+            cpx* of = out + (size_t)g * N;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                if (mode == 0) {
+                    rf::FFTN<M, +1>::run(v[j]);
+#pragma unroll
+                    for (int m = 0; m < M; ++m) v[j][m] = cscale(v[j][m], inv_m);
+                }
+                cpx* st = buf + j * T * M;
+#pragma unroll
+                for (int m = 0; m < M; ++m) st[tid * M + m] = v[j][m];
+                __syncthreads();
+                // item 0's staging has been copied out: the upper halves of the rows that lie inside it are free
+                if (j == 1 && has_next) issue(gn, 1, 0, N1A, true, p == 1);
+                cpx* ob = of + (2 * j * T + p) * M; // record 2*(j*T + r) + p starts at ob + 2*M*r
+#pragma unroll
+                for (int q = 0; q < M; ++q) {
+                    // i = tid + q*T = M*(r0 + (T/M)*q) + e0 + (T%M)*q
+                    constexpr int TQ = T / M, TR = T % M;
+                    int e = e0 + TR * q, r = r0 + TQ * q;
+#pragma unroll
+                    for (int c = 0; c < (M - 1 + TR * (M - 1)) / M; ++c)
+                        if (e >= M) { e -= M; ++r; }
+                    stg_stream(ob + 2 * M * r + e, st[tid + q * T]);
+                }
+            }
+            __syncthreads();
+            if (has_next) issue(gn, 1, N1A, M, false, p == 1);
+            STAGE_MARK(19) // M-IFFT + output staging + stores
+            phase ^= 1;
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------
+// host side
+struct TwoPass {
+    int M = 0, K = 0, L = 0;
+    bool tx = false;
+    cpx* d_table = nullptr;
+    cpx* d_tw = nullptr;
+    cpx* d_w2 = nullptr;
+    cpx* d_scratch = nullptr; // modulator: grid_cap x M*K1 even samples of pass 0 (L2 resident)
+    int grid_cap = 0;
+    size_t smem = 0;
+    std::string name;
+};
+
+typedef Shape<15, 32, 32, 512, 2, 1> S15x1024;
+
+bool twopass_supported(int M, int K) { return M == S15x1024::M && K == 2 * S15x1024::K; }
+
+static void twopass_free(TwoPass* t)
+{
+    if (!t) return;
+    if (t->d_table) cudaFree(t->d_table);
+    if (t->d_tw) cudaFree(t->d_tw);
+    if (t->d_w2) cudaFree(t->d_w2);
+    if (t->d_scratch) cudaFree(t->d_scratch);
+    delete t;
+}
+void twopass_destroy(TwoPass* t) { twopass_free(t); }
+
+TwoPass* twopass_create_tx(int M, int K, int L, const std::vector<std::complex<float>>& taps)
+{
+    if (!twopass_supported(M, K) || L < 1) return nullptr;
+    typedef S15x1024 S;
+    const int K1 = K / 2;
+    TwoPass* t = new TwoPass;
+    t->M = M; t->K = K; t->L = L; t->tx = true;
+    t->smem = S::SMEM_BYTES;
+    t->name = "fused_mod2_kernel<M=15,K=2x32x32,T=512>";
+    try {
+        t->grid_cap = fused_grid_cap((const void*)&fused_mod2_kernel<S>, S::T, S::SMEM_BYTES);
+        const std::vector<cpx> C = make_fold_table(M, K, L, taps, +1, true); // [m][n1]
+        std::vector<cpx> P((size_t)2 * M * K1);
+        for (int p = 0; p < 2; ++p)
+            for (int m = 0; m < M; ++m)
+                for (int n = 0; n < K1; ++n) P[((size_t)p * M + m) * K1 + n] = C[(size_t)m * K + 2 * n + p];
+        t->d_table = upload(P);
+        t->d_tw = upload(make_row_twiddles(S::R1, S::R2));
+        std::vector<cpx> w((size_t)K1);
+        for (int b = 0; b < K1; ++b) {
+            const double ph = 2.0 * M_PI * (double)b / (double)K;
+            w[b] = make_float2((float)std::cos(ph), (float)std::sin(ph));
+        }
+        t->d_w2 = upload(w);
+        GFDM_CUDA_CHECK(cudaMalloc(&t->d_scratch, sizeof(cpx) * (size_t)t->grid_cap * M * K1));
+    } catch (...) {
+        twopass_free(t);
+        throw;
+    }
+    return t;
+}
+
+TwoPass* twopass_create_rx(int M, int K, int L, const std::vector<std::complex<float>>& taps)
+{
+    if (!twopass_supported(M, K) || L < 2) return nullptr;
+    typedef S15x1024 S;
+    const int K1 = K / 2;
+    TwoPass* t = new TwoPass;
+    t->M = M; t->K = K; t->L = L; t->tx = false;
+    t->smem = S::SMEM_BYTES;
+    t->name = "fused_rx2_kernel<M=15,K=2x32x32,T=512>";
+    try {
+        t->grid_cap = fused_grid_cap((const void*)&fused_rx2_kernel<S>, S::T, S::SMEM_BYTES);
+        // C_rx in double so that the extra twiddle does not cost a rounding
+        const std::vector<std::complex<double>> C = make_fold_table_d(M, K, L, taps, -1, true);
+        std::vector<cpx> P((size_t)4 * M * K1);
+        for (int p = 0; p < 2; ++p)
+            for (int h = 0; h < 2; ++h)
+                for (int m = 0; m < M; ++m)
+                    for (int n = 0; n < K1; ++n) {
+                        const std::complex<double> w = std::polar(1.0, -2.0 * M_PI * (double)(p * n) / (double)K);
+                        std::complex<double> c = C[(size_t)m * K + n + h * K1] * w;
+                        if (h && p) c = -c;
+                        P[(((size_t)p * 2 + h) * M + m) * K1 + n] = make_float2((float)c.real(), (float)c.imag());
+                    }
+        t->d_table = upload(P);
+        t->d_tw = upload(make_row_twiddles(S::R1, S::R2));
+    } catch (...) {
+        twopass_free(t);
+        throw;
+    }
+    return t;
+}
+
+int twopass_modulate(TwoPass* t, cpx* out, const cpx* in, size_t frames, cudaStream_t s)
+{
+    typedef S15x1024 S;
+    int launches = 0;
+    const size_t N = (size_t)t->M * t->K, max_chunk = (size_t)1 << 20;
+    for (size_t f0 = 0; f0 < frames; f0 += max_chunk) {
+        const int nf = (int)std::min(max_chunk, frames - f0);
+        const int grid = nf < t->grid_cap ? nf : t->grid_cap;
+        fused_mod2_kernel<S><<<grid, S::T, S::SMEM_BYTES, s>>>(out + f0 * N, in + f0 * N, t->d_table, t->d_tw, t->d_w2, t->d_scratch, nf);
+        ++launches;
+    }
+    GFDM_CUDA_CHECK(cudaGetLastError());
+    return launches;
+}
+
+int twopass_demodulate(TwoPass* t, cpx* out, const cpx* in, int mode, size_t frames, cudaStream_t s)
+{
+    typedef S15x1024 S;
+    int launches = 0;
+    const size_t N = (size_t)t->M * t->K, max_chunk = (size_t)1 << 20;
+    for (size_t f0 = 0; f0 < frames; f0 += max_chunk) {
+        const int nf = (int)std::min(max_chunk, frames - f0);
+        const int grid = nf < t->grid_cap ? nf : t->grid_cap;
+        fused_rx2_kernel<S><<<grid, S::T, S::SMEM_BYTES, s>>>(out + f0 * N, in + f0 * N, t->d_table, t->d_tw, mode, nf);
+        ++launches;
+    }
+    GFDM_CUDA_CHECK(cudaGetLastError());
+    return launches;
+}
+
+const char* twopass_name(const TwoPass* t) { return t->name.c_str(); }
+
+#ifdef GFDM_PROFILE_STAGES
+extern "C" __attribute__((visibility("default"))) int gfdm_debug_stage_cycles2(unsigned long long* out32, int reset)
+{
+    if (out32 && cudaMemcpyFromSymbol(out32, g_stage_cycles, sizeof(g_stage_cycles)) != cudaSuccess) return 1;
+    if (reset) {
+        unsigned long long z[32] = { 0 };
+        if (cudaMemcpyToSymbol(g_stage_cycles, z, sizeof(z)) != cudaSuccess) return 1;
+    }
+    return 0;
+}
+#endif
+
+} // namespace gfdm

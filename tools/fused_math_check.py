@@ -137,3 +137,46 @@ for (M, K, L, R, single) in [(5, 16, 2, 16, True), (9, 64, 2, 8, False), (15, 25
     e2 = np.abs(v3_rx(d, rx_table(taps, M, K, L), M, K, R, single, td=False) - Rfd).max()
     e3 = np.abs(v3_rx(d, rx_table(taps, M, K, L), M, K, R, single, td=True) - np.fft.ifft(Rfd, axis=1)).max()
     print((M, K, L, R), 'mod err %.2e  rx fd err %.2e  rx td err %.2e' % (e1, e2, e3))
+
+
+# ---------------------------------------------------------------------------------------------
+# two-pass kernels (K = 2*K1, frame larger than shared memory): decimation in frequency over the
+# subcarrier index -- pass p computes the K1-point transform that yields the outputs of parity p.
+#   modulator: E^p_b' = (d_b' + (-1)^p d_{b'+K1}) W^{p b'} (raw symbols, W = e^{+j2pi/K})
+#              Z_m[2n'+p] = K1-IFFT_{b'->n'} FFT_M(E^p_b')[m];  x[(2n'+p) + K n2] = M-IFFT_m Ctx[m][2n'+p] Z_m[2n'+p]
+#   receiver : B^p_m[n'] = Tlo^p[m][n'] U_n'[m] + Thi^p[m][n'] U_{n'+K1}[m],
+#              Tlo^p = Crx[m][n'] W^{p n'}, Thi^p = (-1)^p Crx[m][n'+K1] W^{p n'}  (W = e^{-j2pi/K})
+#              R_{2k'+p}[m] = K1-FFT_{n'->k'} B^p_m[n']
+def twopass_mod(d, C, M, K):
+    K1 = K // 2
+    dd = d.reshape(K, M)
+    x = np.zeros(M * K, complex)
+    for p in range(2):
+        E = (dd[:K1] + (-1) ** p * dd[K1:]) * np.exp(2j * np.pi * p * np.arange(K1) / K)[:, None]
+        D = np.fft.fft(E, axis=1)                         # [b'][m]
+        Z = np.fft.ifft(D.T, axis=1) * K1                 # [m][n']
+        Z = Z * C[:, p::2]
+        xp = np.fft.ifft(Z, axis=0) * M                   # [n2][n']
+        for n2 in range(M): x[p + 2 * np.arange(K1) + K * n2] = xp[n2]
+    return x
+
+
+def twopass_rx(x, C, M, K):
+    K1 = K // 2
+    U = np.fft.fft(x.reshape(M, K), axis=0)               # [m][n1]
+    R = np.zeros((K, M), complex)
+    for p in range(2):
+        w = np.exp(-2j * np.pi * p * np.arange(K1) / K)
+        B = C[:, :K1] * w * U[:, :K1] + (-1) ** p * C[:, K1:] * w * U[:, K1:]
+        V = np.fft.fft(B, axis=1)                         # [m][k']
+        R[p::2] = V.T
+    return R
+
+
+print('two-pass (K = 2*K1, decimation in frequency over subcarriers):')
+for (M, K, L) in [(15, 2048, 2), (15, 64, 2), (9, 128, 3)]:
+    taps = rng.standard_normal(M * L) + 1j * rng.standard_normal(M * L)
+    d = rng.standard_normal(M * K) + 1j * rng.standard_normal(M * K)
+    e1 = np.abs(twopass_mod(d, tx_table(taps, M, K, L), M, K) - ref_mod(d, taps, M, K, L)).max()
+    e2 = np.abs(twopass_rx(d, rx_table(taps, M, K, L), M, K) - ref_rx_fd(d, taps, M, K, L)).max()
+    print((M, K, L), 'mod err %.2e  rx fd err %.2e' % (e1, e2))

@@ -17,7 +17,8 @@ import bench  # noqa: E402
 w = dict(bench.WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else 'c3'])
 frames = int(sys.argv[2]) if len(sys.argv) > 2 else w['frames']
 lib = capi.load(os.path.join(ROOT, 'gr-gfdm_b200', 'lib', 'libgfdm_b200_prof.so'))
-dbg = lib.dll.gfdm_debug_stage_cycles
+twopass = w['K'] == 2048
+dbg = lib.dll.gfdm_debug_stage_cycles2 if twopass else lib.dll.gfdm_debug_stage_cycles
 dbg.argtypes = [ctypes.c_void_p, ctypes.c_int]
 tx, rx = bench.make_taps(w)
 mod = capi.Modulator(w['M'], w['K'], w['L'], tx, lib=lib)
@@ -30,6 +31,13 @@ names = {0: 'mod: wait bulk load', 1: 'mod: A read staging', 2: 'mod: A fft+row 
          4: 'mod: barrier after rows', 5: 'mod: C read columns', 6: 'mod: C table+ifft+store',
          15: 'rx: loop top/store issue', 16: 'rx: wait bulk load', 17: "rx: A' read staging", 18: "rx: A' fft+table+wait store", 19: 'rx: row write',
          20: 'rx: row fft (warp0)', 21: 'rx: barrier after rows', 22: "rx: C' read columns", 23: "rx: C' ifft+staging"}
+
+
+if twopass:
+    names = {0: 'mod2: wait bulk loads', 1: 'mod2: step 0 (read, fft)', 2: 'mod2: step 1 + row writes', 3: 'mod2: row fft (warp0)',
+             4: 'mod2: barrier + C read columns', 5: 'mod2: C table+ifft+store',
+             16: "rx2: A' four steps + row writes", 17: 'rx2: row fft (warp0)', 18: "rx2: barrier + C' reads",
+             19: "rx2: C' ifft+staging+stores", 20: 'rx2: step 0', 21: 'rx2: step 1', 22: 'rx2: step 2', 23: 'rx2: step 3'}
 
 
 def run(label, fn, reps=5):
@@ -51,4 +59,5 @@ def run(label, fn, reps=5):
 
 run('modulator', lambda: mod.modulate_ptr(d_tx.data_ptr(), d_in.data_ptr(), frames))
 run('receiver', lambda: dem.demodulate_ptr(d_out.data_ptr(), d_tx.data_ptr(), 0, frames))
-run('receiver+eq', lambda: dem.demodulate_ptr(d_out.data_ptr(), d_tx.data_ptr(), eq.data_ptr(), frames))
+if not twopass:
+    run('receiver+eq', lambda: dem.demodulate_ptr(d_out.data_ptr(), d_tx.data_ptr(), eq.data_ptr(), frames))
