@@ -334,6 +334,17 @@ def main():
     peak_src = 'MEASURED_PEAKS.json hbm_gbs (measured copy)' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s (B200_PROFILING.md)'
     alg_bytes = 16.0 * N * frames  # per launch: read N + write N complex64 per frame
     dom, dom_ms = ('modulator', mod_ms) if mod_ms >= dem_ms else ('receiver', dem_ms)
+    dom_name = mod.last_kernel() if dom == 'modulator' else dem.last_kernel()
+    # measured DRAM bytes per launch of that kernel from the committed `ncu --set full` capture
+    # (tools/ncu_traffic.py -> profiles/ncu_traffic.json); only valid for the frame count it was captured at
+    traffic, traffic_src = None, None
+    try:
+        tdb = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')))
+        ent = tdb.get(dom_name)
+        if ent and int(ent['frames']) == int(frames):
+            traffic, traffic_src = float(ent['traffic_bytes_per_launch']), ent.get('capture')
+    except Exception:
+        pass
     achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
     chain_gbs = 2 * alg_bytes / ((mod_ms + dem_ms) * 1e-3) / 1e9
     line = {
@@ -345,9 +356,9 @@ def main():
                    'constellation': '16-QAM', 'tx_taps': 'RRC alpha=%g' % w['alpha'], 'rx_taps': 'ZF (Gabor dual, folded to L=2)',
                    'l2_policy': 'inputs larger than L2 (%.0f MB per buffer vs 126 MB L2)' % (frames * N * 8 / 1e6),
                    'kernels': {'modulator': mod.last_kernel(), 'receiver': dem.last_kernel()}},
-        'roofline': {'bound': 'hbm', 'kernel': dom + ':' + (mod.last_kernel() if dom == 'modulator' else dem.last_kernel()),
-                     'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
-                     'peak_source': peak_src, 'algorithmic_bytes_per_launch': alg_bytes,
+        'roofline': {'bound': 'hbm', 'kernel': dom + ':' + dom_name,
+                     'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
+                     'traffic_source': traffic_src, 'peak_source': peak_src, 'algorithmic_bytes_per_launch': alg_bytes,
                      'kernel_ms': {'modulator': mod_ms, 'receiver': dem_ms},
                      'chain_achieved_gbs': chain_gbs, 'chain_frac': chain_gbs / peak},
         'clocks': clocks, 'gpu_launches': int(launches),
