@@ -1233,6 +1233,7 @@ struct gfdm_transmitter : HandleBase {
     std::vector<int> shifts;
     int preamble_size = 0;
     cpx* d_preambles = nullptr; // [n_shifts][preamble_size]
+    bool force_staged = false;  // tests: run the chain as separate kernels (mapper, modulator, preamble, prefixer)
     DeviceBuf mapped, frame;
     int out_size() const { return pre.frame_size() + preamble_size; }
     int shift_index(int s) const
@@ -1338,6 +1339,12 @@ int gfdm_transmitter_cyclic_shifts(const gfdm_transmitter* h, int* o)
     return GFDM_OK;
 }
 
+int gfdm_transmitter_set_chain_fusion(gfdm_transmitter* h, int on)
+{
+    h->force_staged = on == 0;
+    return GFDM_OK;
+}
+
 enum TxOp { TX_WORK, TX_WORK_ALL, TX_MODULATE, TX_ADD_FRAME };
 static int transmitter_batch(gfdm_transmitter* h, TxOp op, gfdm_complex* out, const gfdm_complex* in, int nin,
                              int shift, int n, int mem)
@@ -1376,6 +1383,22 @@ static int transmitter_batch(gfdm_transmitter* h, TxOp op, gfdm_complex* out, co
             break;
         case TX_WORK:
         case TX_WORK_ALL: {
+            // one kernel for the whole chain when the shape has a shared-memory resident modulator
+            TxArgs ta;
+            ta.inv_map = h->map.d_inv; ta.front = h->pre.d_front; ta.back = h->pre.d_back; ta.preambles = h->d_preambles;
+            ta.A = h->map.A; ta.per_timeslot = h->map.per_timeslot ? 1 : 0; ta.n_in = (int)in_sz;
+            ta.cp = h->pre.cp_len; ta.cs = h->pre.cs_len; ta.ramp = h->pre.ramp_len; ta.P = h->preamble_size;
+            ta.n_ant = (int)n_ant;
+            ta.ant_stride = (mem == GFDM_MEM_DEVICE ? (size_t)n : nf) * os;
+            for (size_t a = 0; a < n_ant && a < (size_t)GFDM_TX_MAX_ANT; ++a) {
+                ta.shift[a] = h->shifts[a];
+                ta.pre_idx[a] = h->shift_index(h->shifts[a]);
+            }
+            if (!h->force_staged && h->fused.available() && h->fused.supports_tx_chain(ta) && aligned16(di)) {
+                h->launches += h->fused.transmit(mem == GFDM_MEM_DEVICE ? dout + f0 * os : dout, di, ta, nf, h->stream);
+                h->last_kernel = h->fused.tx_name();
+                break;
+            }
             h->frame.ensure(nf * N * sizeof(cpx));
             tx_modulate(h, h->frame.as<cpx>(), di, in_sz, nf);
             for (size_t a = 0; a < n_ant; ++a) {

@@ -10,6 +10,22 @@ namespace gfdm {
 
 struct FusedImpl;
 
+// transmitter chain fused into the modulator kernel (mapper gather in front, preamble + cyclic prefix/suffix +
+// window behind); all pointers are device pointers owned by the transmitter handle
+constexpr int GFDM_TX_MAX_ANT = 4;
+struct TxArgs {
+    const int* inv_map = nullptr;   // [K] position of subcarrier k in the sorted subcarrier map, -1 = unused
+    const cpx* front = nullptr;     // [ramp] leading window ramp
+    const cpx* back = nullptr;      // [ramp] trailing window ramp
+    const cpx* preambles = nullptr; // [n_shifts][P]
+    size_t ant_stride = 0;          // elements between the outputs of two antennas (cyclic shifts)
+    int A = 0, per_timeslot = 1, n_in = 0; // active subcarriers, symbol order, symbols per frame (<= A*M)
+    int cp = 0, cs = 0, ramp = 0, P = 0;
+    int n_ant = 1;
+    int shift[GFDM_TX_MAX_ANT] = { 0, 0, 0, 0 };
+    int pre_idx[GFDM_TX_MAX_ANT] = { 0, 0, 0, 0 };
+};
+
 // host helpers shared by fused_modem.cu and fused_twopass.cu
 int fused_grid_cap(const void* fn, int threads, size_t smem); // persistent grid = SMs x resident CTAs
 std::vector<cpx> make_row_twiddles(int R1, int R2);           // W_K^{n0*k1} as [k1][n0], K = R1*R2
@@ -40,6 +56,11 @@ public:
     bool supports_eq() const;
     // in/out: [frames][N] device pointers; returns the number of kernel launches
     int modulate(cpx* out, const cpx* in, size_t frames, cudaStream_t s);
+    // whole transmitter chain in one kernel (single-pass shapes, even n_in, <= GFDM_TX_MAX_ANT antennas):
+    // in [frames][n_in] compact symbols -> out [n_ant][...][P+cp+N+cs]
+    bool supports_tx_chain(const TxArgs& tx) const;
+    int transmit(cpx* out, const cpx* in, const TxArgs& tx, size_t frames, cudaStream_t s);
+    const char* tx_name() const;
     // out_td (soft symbols) and/or out_fd (fft_filter_downsample result) may be null; eq may be null
     int demodulate(cpx* out_td, cpx* out_fd, const cpx* in, const cpx* eq, size_t frames, cudaStream_t s);
     // advanced receiver: successive interference cancellation resident in the receiver kernel.

@@ -39,12 +39,20 @@ namespace gfdm {
 // Fused modulator.  in/out: [n_frames][N]; table: C_tx [M][K]; tw: W_K^{n0*k1} as [k1][n0].
 // Shared memory: R = row buffer (also holds the tail of the staged input), P = prefetch region
 // holding the head of the NEXT group's staged input, loaded by TMA while this group is processed.
-template <class S>
+//
+// TXF = true is the whole transmitter_kernel::generic_work chain (lib/transmitter_kernel.cc:78-107) in this one
+// kernel: the resource mapper (lib/resource_mapper_kernel_cc.cc:108-134) becomes the gather of stage A out of the
+// staged COMPACT symbol vectors (in: [n_frames][n_in]), and preamble insertion + cyclic prefix/suffix + window
+// (lib/add_cyclic_prefix_cc.cc:67-98) become the store pattern of stage C (out: [n_ant][n_frames][P+cp+N+cs]),
+// so a frame costs 8*(n_in + n_ant*(P+cp+N+cs)) bytes of HBM traffic instead of four kernels' worth.
+template <class S, bool TXF>
 __global__ void __launch_bounds__(S::T, S::MINB) fused_mod_kernel(cpx* __restrict__ out, const cpx* __restrict__ in,
                                                                   const cpx* __restrict__ table,
-                                                                  const cpx* __restrict__ tw, int n_frames)
+                                                                  const cpx* __restrict__ tw, int n_frames,
+                                                                  const __grid_constant__ TxArgs tx)
 {
     constexpr int M = S::M, K = S::K, N = S::N, T = S::T, IPT = S::IPT, F = S::F, RS = S::RS, PF = S::PF;
+    const int EL = TXF ? tx.n_in : N; // staged elements per frame
     extern __shared__ __align__(128) unsigned char smem_raw[];
     cpx* buf = reinterpret_cast<cpx*>(smem_raw);
     cpx* tw_s = buf + S::BUF_ELEMS;
@@ -66,17 +74,23 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_mod_kernel(cpx* __restric
 
     // issue the bulk loads of group gg: head -> P, tail -> R
     auto load_head = [&](int gg) {
-        const int el = min(F, n_frames - gg * F) * N;
+        const int el = min(F, n_frames - gg * F) * EL;
         const uint32_t bytes = (uint32_t)min(el, PF) * sizeof(cpx);
         mbar_expect_tx(bar_p, bytes);
-        bulk_load(pre, in + (size_t)gg * F * N, bytes, bar_p);
+        if (bytes) bulk_load(pre, in + (size_t)gg * F * EL, bytes, bar_p);
     };
     auto load_tail = [&](int gg) {
-        const int el = min(F, n_frames - gg * F) * N;
+        const int el = min(F, n_frames - gg * F) * EL;
         const uint32_t bytes = (uint32_t)max(el - PF, 0) * sizeof(cpx);
         mbar_expect_tx(bar_r, bytes);
-        if (bytes) bulk_load(buf, in + (size_t)gg * F * N + PF, bytes, bar_r);
+        if (bytes) bulk_load(buf, in + (size_t)gg * F * EL + PF, bytes, bar_r);
     };
+    // transmitter: position of this thread's subcarrier(s) in the sorted subcarrier map (-1: unused)
+    int slot[IPT];
+    if constexpr (TXF) {
+#pragma unroll
+        for (int j = 0; j < IPT; ++j) slot[j] = __ldg(tx.inv_map + (tid + j * T) % K);
+    }
 
     int g = blockIdx.x;
     if (tid == 0 && g < n_groups) {
@@ -95,12 +109,29 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_mod_kernel(cpx* __restric
 
         cpx v[IPT][M];
         // ---- stage A: subcarrier symbols from the staged [k][m] block -> registers
+        if constexpr (!TXF) {
 #pragma unroll
-        for (int j = 0; j < IPT; ++j) {
-            const int e = (tid + j * T) * M; // (f*K + k)*M
-            const cpx* src = (e < PF) ? pre + e : buf + (e - PF);
+            for (int j = 0; j < IPT; ++j) {
+                const int e = (tid + j * T) * M; // (f*K + k)*M
+                const cpx* src = (e < PF) ? pre + e : buf + (e - PF);
 #pragma unroll
-            for (int m = 0; m < M; ++m) v[j][m] = src[m];
+                for (int m = 0; m < M; ++m) v[j][m] = src[m];
+            }
+        } else {
+            // map_to_resources as a gather: symbol (slot a, timeslot m) sits at m*A + a (per timeslot) or
+            // a*M + m (per subcarrier) of the frame's compact vector; beyond n_in and on unused subcarriers: zero
+#pragma unroll
+            for (int j = 0; j < IPT; ++j) {
+                const int f = (tid + j * T) / K, a = slot[j];
+#pragma unroll
+                for (int m = 0; m < M; ++m) {
+                    const int src = tx.per_timeslot ? m * tx.A + a : a * M + m;
+                    const int e = f * tx.n_in + src;
+                    cpx val = cmake(0.f, 0.f);
+                    if (a >= 0 && src < tx.n_in) val = (e < PF) ? pre[e] : buf[e - PF];
+                    v[j][m] = val;
+                }
+            }
         }
         __syncthreads(); // staging fully consumed: P may be refilled, R may take the rows
         if (tid == 0 && gn < n_groups) {
@@ -164,10 +195,42 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_mod_kernel(cpx* __restric
                 }
             }
             rf::FFTN<M, +1>::run(v[j]);
-            if (f < fh) {
-                cpx* dst = out + ((size_t)g * F + f) * N + n1;
+            if constexpr (!TXF) {
+                if (f < fh) {
+                    cpx* dst = out + ((size_t)g * F + f) * N + n1;
 #pragma unroll
-                for (int n2 = 0; n2 < M; ++n2) stg_stream(dst + (size_t)n2 * K, v[j][n2]);
+                    for (int n2 = 0; n2 < M; ++n2) stg_stream(dst + (size_t)n2 * K, v[j][n2]);
+                }
+            } else if (f < fh) {
+                // add_cyclic_prefix: o[i] = x[(i + N - cp - s) mod N], i < W = N + cp + cs  <=>  sample n goes to
+                // i = (n + cp + s) mod N and again to i + N while that is < W; ramps on the first / last samples
+                const int W = N + tx.cp + tx.cs, os = tx.P + W;
+                for (int a = 0; a < tx.n_ant; ++a) {
+                    cpx* o = out + (size_t)a * tx.ant_stride + ((size_t)g * F + f) * os + tx.P;
+                    const int i0 = n1 + tx.cp + tx.shift[a];
+#pragma unroll
+                    for (int n2 = 0; n2 < M; ++n2) {
+                        int i = i0 + n2 * K;
+                        i = i >= N ? i - N : i;
+                        for (; i < W; i += N) {
+                            cpx val = v[j][n2];
+                            if (i < tx.ramp) val = cmul_rn(val, __ldg(tx.front + i));
+                            if (i >= W - tx.ramp) val = cmul_rn(val, __ldg(tx.back + (i - (W - tx.ramp))));
+                            stg_stream(o + i, val);
+                        }
+                    }
+                }
+            }
+        }
+        if constexpr (TXF) {
+            // insert_preamble (lib/transmitter_kernel.cc:86-90): the shift's preamble in front of every frame
+            const int os = tx.P + N + tx.cp + tx.cs;
+            for (int a = 0; a < tx.n_ant; ++a) {
+                const cpx* p = tx.preambles + (size_t)tx.pre_idx[a] * tx.P;
+                for (int idx = tid; idx < fh * tx.P; idx += T) {
+                    const int f = idx / tx.P, i = idx - f * tx.P;
+                    stg_stream(out + (size_t)a * tx.ant_stride + ((size_t)g * F + f) * os + i, ldg_nc(p + i));
+                }
             }
         }
         STAGE_MARK(6) // stage C compute + stores
@@ -476,6 +539,7 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_rx_kernel(cpx* __restrict
 // ----------------------------------------------------------------------------------------
 // host side
 typedef void (*mod_launch_t)(cpx*, const cpx*, const cpx*, const cpx*, int, int, cudaStream_t);
+typedef void (*tx_launch_t)(cpx*, const cpx*, const cpx*, const cpx*, int, int, const TxArgs&, cudaStream_t);
 typedef void (*rx_launch_t)(cpx*, const cpx*, const cpx*, const cpx*, const cpx*, const cpx*, int, int, int, int,
                             cudaStream_t);
 
@@ -483,7 +547,13 @@ template <class S>
 static void launch_mod(cpx* out, const cpx* in, const cpx* table, const cpx* tw, int n_frames, int grid,
                        cudaStream_t s)
 {
-    fused_mod_kernel<S><<<grid, S::T, S::SMEM_BYTES, s>>>(out, in, table, tw, n_frames);
+    fused_mod_kernel<S, false><<<grid, S::T, S::SMEM_BYTES, s>>>(out, in, table, tw, n_frames, TxArgs{});
+}
+template <class S>
+static void launch_tx(cpx* out, const cpx* in, const cpx* table, const cpx* tw, int n_frames, int grid,
+                      const TxArgs& tx, cudaStream_t s)
+{
+    fused_mod_kernel<S, true><<<grid, S::T, S::SMEM_BYTES, s>>>(out, in, table, tw, n_frames, tx);
 }
 typedef void (*sic_launch_t)(cpx*, const cpx*, const cpx*, const cpx*, const cpx*, const cpx*, int, int, int,
                              SicArgs, cudaStream_t);
@@ -507,6 +577,9 @@ struct ShapeEntry {
     size_t smem;
     const char* mod_name;
     const char* rx_name;
+    const char* tx_name;
+    tx_launch_t tx;
+    const void* tx_fn;
     mod_launch_t mod;
     rx_launch_t rx;
     sic_launch_t sic; // null when the shape keeps more than one subcarrier per thread
@@ -517,16 +590,19 @@ struct ShapeEntry {
 };
 
 template <class S>
-static ShapeEntry make_entry(const char* mn, const char* rn)
+static ShapeEntry make_entry(const char* mn, const char* rn, const char* tn)
 {
     ShapeEntry e;
     e.M = S::M; e.K = S::K; e.R1 = S::R1; e.R2 = S::R2; e.T = S::T; e.F = S::F;
     e.smem = S::SMEM_BYTES;
     e.mod_name = mn;
     e.rx_name = rn;
+    e.tx_name = tn;
+    e.tx = &launch_tx<S>;
+    e.tx_fn = (const void*)&fused_mod_kernel<S, true>;
     e.mod = &launch_mod<S>;
     e.rx = &launch_rx<S>;
-    e.mod_fn = (const void*)&fused_mod_kernel<S>;
+    e.mod_fn = (const void*)&fused_mod_kernel<S, false>;
     e.rx_fn = (const void*)&fused_rx_kernel<S, false>;
     e.sic = nullptr;
     e.sic_fn = nullptr;
@@ -540,7 +616,8 @@ static ShapeEntry make_entry(const char* mn, const char* rn)
 
 #define GFDM_SHAPE(M, R1, R2, T, IPT, MINB)                                                            \
     make_entry<Shape<M, R1, R2, T, IPT, MINB>>("fused_mod_kernel<M=" #M ",K=" #R1 "x" #R2 ",T=" #T ">", \
-                                                "fused_rx_kernel<M=" #M ",K=" #R1 "x" #R2 ",T=" #T ">")
+                                                "fused_rx_kernel<M=" #M ",K=" #R1 "x" #R2 ",T=" #T ">",   \
+                                                "fused_tx_chain_kernel<M=" #M ",K=" #R1 "x" #R2 ",T=" #T ">")
 
 static const std::vector<ShapeEntry>& shape_table()
 {
@@ -561,7 +638,7 @@ struct FusedImpl {
     cpx* d_table_eq = nullptr; // rx only: plain twiddle
     cpx* d_tw = nullptr;
     cpx* d_taps = nullptr;
-    int mod_grid_cap = 0, rx_grid_cap = 0, sic_grid_cap = 0;
+    int mod_grid_cap = 0, rx_grid_cap = 0, sic_grid_cap = 0, tx_grid_cap = 0;
     // interference cancellation (advanced receiver)
     cpx* d_ic = nullptr;
     cpx* d_points = nullptr;
@@ -716,6 +793,32 @@ int FusedModem::modulate(cpx* out, const cpx* in, size_t frames, cudaStream_t s)
     GFDM_CUDA_CHECK(cudaGetLastError());
     return launches;
 }
+
+bool FusedModem::supports_tx_chain(const TxArgs& tx) const
+{
+    // single-pass shapes only; the bulk copies of the compact symbol vectors need 16-byte granularity
+    return impl_ && impl_->e && tx.n_in > 0 && tx.n_in % 2 == 0 && tx.n_ant >= 1 && tx.n_ant <= GFDM_TX_MAX_ANT;
+}
+
+int FusedModem::transmit(cpx* out, const cpx* in, const TxArgs& tx, size_t frames, cudaStream_t s)
+{
+    const ShapeEntry* e = impl_->e;
+    if (!impl_->tx_grid_cap) impl_->tx_grid_cap = fused_grid_cap(e->tx_fn, e->T, e->smem);
+    int launches = 0;
+    const size_t os = (size_t)tx.P + (size_t)e->M * e->K + tx.cp + tx.cs;
+    const size_t max_chunk = (size_t)1 << 20; // keep frame counts in int range
+    for (size_t f0 = 0; f0 < frames; f0 += max_chunk) {
+        const int nf = (int)std::min(max_chunk, frames - f0);
+        const int groups = (nf + e->F - 1) / e->F;
+        const int grid = groups < impl_->tx_grid_cap ? groups : impl_->tx_grid_cap;
+        e->tx(out + f0 * os, in + f0 * (size_t)tx.n_in, impl_->d_table, impl_->d_tw, nf, grid, tx, s);
+        ++launches;
+    }
+    GFDM_CUDA_CHECK(cudaGetLastError());
+    return launches;
+}
+
+const char* FusedModem::tx_name() const { return impl_ && impl_->e ? impl_->e->tx_name : "none"; }
 
 int FusedModem::demodulate(cpx* out_td, cpx* out_fd, const cpx* in, const cpx* eq, size_t frames, cudaStream_t s)
 {

@@ -144,6 +144,7 @@ class Library(object):
         'gfdm_transmitter_add_frame': (c_int, [c_void_p, c_void_p, c_void_p, c_int]),
         'gfdm_transmitter_work_batch': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int]),
         'gfdm_transmitter_work_all_batch': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int]),
+        'gfdm_transmitter_set_chain_fusion': (c_int, [c_void_p, c_int]),
     }
 
     def __init__(self, path):
@@ -790,6 +791,10 @@ class Transmitter(_Handle):
             _ptr(smap), smap.size, int(bool(per_timeslot)), overlap, _ptr(t), t.size, _ptr(w), w.size,
             _ptr(shifts), shifts.size, ptrs, _ptr(sizes), len(pre)))
         self._block = timeslots * subcarriers
+
+    def set_chain_fusion(self, on):
+        """CUDA library: run the chain as one kernel (default) or as four separate kernels."""
+        self._ck(self._dll.gfdm_transmitter_set_chain_fusion(self._h, int(bool(on))))
 
     def input_vector_size(self):
         return self._dll.gfdm_transmitter_input_vector_size(self._h)

@@ -307,6 +307,10 @@ GFDM_B200_API int gfdm_transmitter_work_batch(gfdm_transmitter* h, gfdm_complex*
 GFDM_B200_API int gfdm_transmitter_work_all_batch(gfdm_transmitter* h, gfdm_complex* out,
                                                   const gfdm_complex* in, int ninput_size,
                                                   int n_frames, int mem);
+/* The CUDA library runs mapper + modulator + preamble + prefixer as ONE kernel where the shape allows
+ * (8*(n_in + P+cp+N+cs) bytes of HBM traffic per frame and antenna); on = 0 forces the four separate
+ * kernels (used by the parity tests: both forms must agree bit for bit).  No-op on the CPU oracles. */
+GFDM_B200_API int gfdm_transmitter_set_chain_fusion(gfdm_transmitter* h, int on);
 
 #ifdef __cplusplus
 }

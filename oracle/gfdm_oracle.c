@@ -1114,6 +1114,7 @@ int gfdm_transmitter_work_batch(gfdm_transmitter* h, cf* out, const cf* in, int 
     }
     return GFDM_OK;
 }
+int gfdm_transmitter_set_chain_fusion(gfdm_transmitter* h, int on) { (void)h; (void)on; return GFDM_OK; }
 /* the per-frame loop of lib/transmitter_cc_impl.cc:165-177 */
 int gfdm_transmitter_work_all_batch(gfdm_transmitter* h, cf* out, const cf* in, int nin, int n, int mem)
 {

@@ -612,6 +612,7 @@ int gfdm_transmitter_work_batch(gfdm_transmitter* h, gfdm_complex* out, const gf
     for (int i = 0; i < n; ++i) h->k->generic_work(C(out) + i * os, C(in) + (size_t)i * nin, nin);
     REF_CATCH
 }
+int gfdm_transmitter_set_chain_fusion(gfdm_transmitter*, int) { return GFDM_OK; }
 int gfdm_transmitter_work_all_batch(gfdm_transmitter* h, gfdm_complex* out, const gfdm_complex* in,
                                     int nin, int n, int mem)
 {
