@@ -111,6 +111,78 @@ __device__ __forceinline__ void stg_stream(cpx* p, cpx v)
 }
 
 // ----------------------------------------------------------------------------------------
+// Tensor memory (TMEM, 256 KB per SM: 128 lanes x 512 columns x 32 bit) as a per-thread constant store.
+// The fused kernels have no MMA, so TMEM is idle; the 32x32b access shape gives every thread of a warp its own
+// lane (lane = 32*(warp%4) + laneid) and N consecutive columns -- a software-managed extension of the register
+// file with ~12 cycles of latency on a datapath that is neither the LSU nor L2.  Used for the loop-invariant
+// folded filter/twiddle table column(s) of each thread when the table does not fit in shared memory.
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot, uint32_t ncols) // one converged warp; ncols = 2^n >= 32
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) // the warp that allocated
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld_x2(float* r, uint32_t a)
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=f"(r[0]), "=f"(r[1]) : "r"(a) : "memory");
+}
+__device__ __forceinline__ void tmem_st_x2(uint32_t a, const float* r)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(a), "f"(r[0]), "f"(r[1]) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_x4(float* r, uint32_t a)
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]) : "r"(a) : "memory");
+}
+__device__ __forceinline__ void tmem_st_x4(uint32_t a, const float* r)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(r[0]), "f"(r[1]), "f"(r[2]), "f"(r[3]) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_x8(float* r, uint32_t a)
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];" : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]) : "r"(a) : "memory");
+}
+__device__ __forceinline__ void tmem_st_x8(uint32_t a, const float* r)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(a), "f"(r[0]), "f"(r[1]), "f"(r[2]), "f"(r[3]), "f"(r[4]), "f"(r[5]), "f"(r[6]), "f"(r[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_x16(float* r, uint32_t a)
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];" : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]), "=f"(r[8]), "=f"(r[9]), "=f"(r[10]), "=f"(r[11]), "=f"(r[12]), "=f"(r[13]), "=f"(r[14]), "=f"(r[15]) : "r"(a) : "memory");
+}
+__device__ __forceinline__ void tmem_st_x16(uint32_t a, const float* r)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(a), "f"(r[0]), "f"(r[1]), "f"(r[2]), "f"(r[3]), "f"(r[4]), "f"(r[5]), "f"(r[6]), "f"(r[7]), "f"(r[8]), "f"(r[9]), "f"(r[10]), "f"(r[11]), "f"(r[12]), "f"(r[13]), "f"(r[14]), "f"(r[15]) : "memory");
+}
+// N (even) consecutive 32-bit columns <-> registers, as power-of-two pieces (whole warp, converged)
+template <int N>
+__device__ __forceinline__ void tmem_ld(float* r, uint32_t a)
+{
+    static_assert(N % 2 == 0 && N >= 0, "column count must be even");
+    if constexpr (N >= 16) { tmem_ld_x16(r, a); tmem_ld<N - 16>(r + 16, a + 16); }
+    else if constexpr (N >= 8) { tmem_ld_x8(r, a); tmem_ld<N - 8>(r + 8, a + 8); }
+    else if constexpr (N >= 4) { tmem_ld_x4(r, a); tmem_ld<N - 4>(r + 4, a + 4); }
+    else if constexpr (N >= 2) { tmem_ld_x2(r, a); tmem_ld<N - 2>(r + 2, a + 2); }
+}
+template <int N>
+__device__ __forceinline__ void tmem_st(uint32_t a, const float* r)
+{
+    static_assert(N % 2 == 0 && N >= 0, "column count must be even");
+    if constexpr (N >= 16) { tmem_st_x16(a, r); tmem_st<N - 16>(a + 16, r + 16); }
+    else if constexpr (N >= 8) { tmem_st_x8(a, r); tmem_st<N - 8>(a + 8, r + 8); }
+    else if constexpr (N >= 4) { tmem_st_x4(a, r); tmem_st<N - 4>(a + 4, r + 4); }
+    else if constexpr (N >= 2) { tmem_st_x2(a, r); tmem_st<N - 2>(a + 2, r + 2); }
+}
+
+// ----------------------------------------------------------------------------------------
 // optional per-stage cycle counters (build with -DGFDM_PROFILE_STAGES; tools/stage_profile.py)
 #ifdef GFDM_PROFILE_STAGES
 static __device__ unsigned long long g_stage_cycles[32];
@@ -128,7 +200,7 @@ static __device__ unsigned long long g_stage_cycles[32];
 
 // ----------------------------------------------------------------------------------------
 // compile-time shape of one fused kernel
-template <int M_, int R1_, int R2_, int T_, int IPT_, int MINB_>
+template <int M_, int R1_, int R2_, int T_, int IPT_, int MINB_, bool TMEM_ = true>
 struct Shape {
     static constexpr int M = M_, R1 = R1_, R2 = R2_, T = T_, IPT = IPT_, MINB = MINB_;
     static constexpr int K = R1 * R2;
@@ -148,17 +220,23 @@ struct Shape {
     static constexpr int ROW_ELEMS = ROWS * RS;
     static constexpr int STAGE_ELEMS = F * N;
     static constexpr int BUF_ELEMS = ROW_ELEMS > STAGE_ELEMS ? ROW_ELEMS : STAGE_ELEMS;
-    static constexpr int TW_ELEMS = TWO_PASS ? K : 0;
     // per-CTA shared memory budget in complex elements (228 KB per SM, 1 KB per CTA reserved)
     // small constants of the receiver: [0,64) receive taps of the equalising path (L*M <= 64),
     // [64,96) interference-cancellation taps, [96,160) constellation points, [160,192) reduction scratch
     static constexpr int TAPS_ELEMS = 192;
     static constexpr int IC_OFF = 64, PTS_OFF = 96, RED_OFF = 160, MAX_POINTS = 64;
     static constexpr int BUDGET_ELEMS = ((233472 / MINB) - 1024) / 8 - 8 - TAPS_ELEMS;
+    // the folded filter/twiddle table stays resident in shared memory when the whole next group fits beside it
+    // (and beside the row-FFT twiddles) ...
+    static constexpr bool TBL_SMEM = BUDGET_ELEMS - BUF_ELEMS - (TWO_PASS ? K : 0) >= F * N + N;
+    // ... otherwise every thread parks its own loop-invariant constants in tensor memory: its IPT table columns
+    // (2M 32-bit columns each) and, for two-pass rows, its R1 pass-1 twiddles W_K^{n0*k1}, n0 = tid % R2.
+    // Warp w owns lanes 32*(w%4).., the warps sharing a lane quarter take consecutive column blocks.
+    static constexpr bool TBL_TMEM = !TBL_SMEM && TMEM_; // the two-pass kernels (fused_twopass.cu) opt out
+    static constexpr bool TW_TMEM = TBL_TMEM && TWO_PASS && T % R2 == 0;
+    static constexpr int TW_ELEMS = (TWO_PASS && !TW_TMEM) ? K : 0;
     static constexpr int P_MAX = BUDGET_ELEMS - BUF_ELEMS - TW_ELEMS;
     static_assert(P_MAX >= 0, "frame group does not fit in shared memory");
-    // the folded filter/twiddle table stays resident when the whole next group fits beside it
-    static constexpr bool TBL_SMEM = P_MAX >= F * N + N;
     static constexpr int TBL_ELEMS = TBL_SMEM ? N : 0;
     static constexpr int P_AVAIL = P_MAX - TBL_ELEMS;
     // prefetch region P: modulator -> the first PF staged elements of the next group,
@@ -166,13 +244,59 @@ struct Shape {
     static constexpr int PF = (F * N) < (P_AVAIL / (2 * M)) * 2 * M ? (F * N) : (P_AVAIL / (2 * M)) * 2 * M;
     static constexpr int PR = M < P_AVAIL / (F * K) ? M : P_AVAIL / (F * K);
     static constexpr int P_ELEMS = PF > F * PR * K ? PF : F * PR * K;
+    static constexpr int TMEM_TBL_COLS = IPT * 2 * M;             // per thread
+    static constexpr int TMEM_TW_COLS = TW_TMEM ? 2 * R1 : 0;     // per thread
+    static constexpr int TMEM_PER_THREAD = TMEM_TBL_COLS + TMEM_TW_COLS;
+    static constexpr int TMEM_USED = ((T / 32 + 3) / 4) * TMEM_PER_THREAD;
+    static constexpr int TMEM_COLS = TMEM_USED <= 32 ? 32 : TMEM_USED <= 64 ? 64 : TMEM_USED <= 128 ? 128 : TMEM_USED <= 256 ? 256 : 512;
+    static_assert(!TBL_TMEM || (TMEM_USED <= 512 && TMEM_COLS * MINB <= 512), "constants do not fit in tensor memory");
     static constexpr size_t SMEM_BYTES = sizeof(cpx) * (size_t)(BUF_ELEMS + TW_ELEMS + TBL_ELEMS + P_ELEMS + TAPS_ELEMS) + 64;
     __host__ __device__ static constexpr int swz(int n) { return TWO_PASS ? n + n / R2 : n; } // row-FFT input slot
 };
 
+// Tensor-memory setup of a fused kernel: allocate, then every thread stores its own table columns (and pass-1
+// twiddles).  Returns the allocation base (for the dealloc) and this thread's first column.
+template <class S>
+__device__ __forceinline__ void tmem_setup(uint32_t* slot, const cpx* __restrict__ table, const cpx* __restrict__ tw, int tid,
+                                           uint32_t& base, uint32_t& mine)
+{
+    constexpr int M = S::M, K = S::K, T = S::T;
+    if (tid < 32) tmem_alloc(slot, S::TMEM_COLS);
+    tmem_fence_before_sync();
+    __syncthreads();
+    tmem_fence_after_sync();
+    base = *slot;
+    mine = base + ((uint32_t)(((tid >> 5) & 3) * 32) << 16) + (uint32_t)(tid >> 7) * S::TMEM_PER_THREAD;
+#pragma unroll
+    for (int j = 0; j < S::IPT; ++j) {
+        const int n1 = (tid + j * T) % K;
+        float tf[2 * M];
+#pragma unroll
+        for (int m = 0; m < M; ++m) {
+            const cpx c = ldg_nc(table + m * K + n1);
+            tf[2 * m] = c.x;
+            tf[2 * m + 1] = c.y;
+        }
+        tmem_st<2 * M>(mine + j * 2 * M, tf);
+    }
+    if constexpr (S::TW_TMEM) {
+        static_assert(S::R1 % 8 == 0, "pass-1 twiddles are fetched in groups of eight");
+        const int n0 = tid % S::R2;
+        float wf[2 * S::R1];
+#pragma unroll
+        for (int k1 = 0; k1 < S::R1; ++k1) {
+            const cpx c = ldg_nc(tw + k1 * S::R2 + n0);
+            wf[2 * k1] = c.x;
+            wf[2 * k1 + 1] = c.y;
+        }
+        tmem_st<2 * S::R1>(mine + S::TMEM_TBL_COLS, wf);
+    }
+    tmem_wait_st();
+}
+
 // Row FFTs over the K-long rows held in shared memory (in place; input at swz(), output natural).
 template <class S, int DIR>
-__device__ __forceinline__ void row_fft(cpx* __restrict__ buf, const cpx* __restrict__ tw_s, int tid)
+__device__ __forceinline__ void row_fft(cpx* __restrict__ buf, const cpx* __restrict__ tw_s, int tid, uint32_t tmem_tw = 0)
 {
     constexpr int R1 = S::R1, R2 = S::R2, RS = S::RS, T = S::T;
     if constexpr (!S::TWO_PASS) {
@@ -201,9 +325,17 @@ __device__ __forceinline__ void row_fft(cpx* __restrict__ buf, const cpx* __rest
 #pragma unroll
             for (int c = 0; c < R1; c += 8) {
                 cpx w[8];
+                if constexpr (S::TW_TMEM) {
+                    float wf[16]; // this thread's twiddles k1 = c .. c+7 out of tensor memory
+                    tmem_ld_x16(wf, tmem_tw + 2 * c);
+                    tmem_wait_ld();
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    if (c + i > 0 && c + i < R1) w[i] = tw_s[(c + i) * R2 + n0];
+                    for (int i = 0; i < 8; ++i) w[i] = cmake(wf[2 * i], wf[2 * i + 1]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        if (c + i > 0 && c + i < R1) w[i] = tw_s[(c + i) * R2 + n0];
+                }
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
                     if (c + i > 0 && c + i < R1) {

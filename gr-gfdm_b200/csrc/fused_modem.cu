@@ -70,6 +70,12 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_mod_kernel(cpx* __restric
         mbar_init(bar_p, 1);
         mbar_init(bar_r, 1);
     }
+    // table columns of this thread -> tensor memory (once per CTA)
+    uint32_t tmem_base = 0, tmem_mine = 0;
+    if constexpr (S::TBL_TMEM) {
+        uint32_t* slot = reinterpret_cast<uint32_t*>(bars + 2);
+        tmem_setup<S>(slot, table, tw, tid, tmem_base, tmem_mine);
+    }
     __syncthreads();
 
     // issue the bulk loads of group gg: head -> P, tail -> R
@@ -151,18 +157,12 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_mod_kernel(cpx* __restric
         __syncthreads();
         STAGE_MARK(2) // stage A FFT + row writes
         // ---- stage B: K-point inverse FFT of every row (over the subcarrier index)
-        row_fft<S, +1>(buf, tw_s, tid);
+        row_fft<S, +1>(buf, tw_s, tid, tmem_mine + S::TMEM_TBL_COLS);
         STAGE_MARK(3) // row FFT (warp 0's own time)
         __syncthreads();
         STAGE_MARK(4) // barrier after row FFT
         // table column of the first item (unless resident): issued after the barrier so that the
         // compiler cannot hoist it into the register-hungry radix-32 passes; the column reads hide it
-        cpx tc[M];
-        if constexpr (!S::TBL_SMEM) {
-            const int n1 = tid % K;
-#pragma unroll
-            for (int m = 0; m < M; ++m) tc[m] = ldg_nc(table + m * K + n1);
-        }
         // ---- stage C: column n1 of all rows -> registers
 #pragma unroll
         for (int j = 0; j < IPT; ++j) {
@@ -186,13 +186,11 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_mod_kernel(cpx* __restric
 #pragma unroll
                 for (int m = 0; m < M; ++m) v[j][m] = cmul(v[j][m], tbl_s[m * K + n1]);
             } else {
+                float tf[2 * M]; // this item's table column out of tensor memory
+                tmem_ld<2 * M>(tf, tmem_mine + j * 2 * M);
+                tmem_wait_ld();
 #pragma unroll
-                for (int m = 0; m < M; ++m) v[j][m] = cmul(v[j][m], tc[m]);
-                if (j + 1 < IPT) { // next item's column: in flight while this item's IFFT and stores run
-                    const int n1n = (tid + (j + 1) * T) % K;
-#pragma unroll
-                    for (int m = 0; m < M; ++m) tc[m] = ldg_nc(table + m * K + n1n);
-                }
+                for (int m = 0; m < M; ++m) v[j][m] = cmul(v[j][m], cmake(tf[2 * m], tf[2 * m + 1]));
             }
             rf::FFTN<M, +1>::run(v[j]);
             if constexpr (!TXF) {
@@ -234,6 +232,11 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_mod_kernel(cpx* __restric
             }
         }
         STAGE_MARK(6) // stage C compute + stores
+    }
+    if constexpr (S::TBL_TMEM) {
+        tmem_fence_before_sync();
+        __syncthreads();
+        if (tid < 32) tmem_dealloc(tmem_base, S::TMEM_COLS);
     }
 }
 
@@ -282,6 +285,12 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_rx_kernel(cpx* __restrict
         for (int i = tid; i < sic.n_points && i < S::MAX_POINTS; i += T) taps_s[S::PTS_OFF + i] = sic.points[i];
     }
     if (tid == 0) mbar_init(bar_p, 1);
+    // table columns of this thread -> tensor memory (once per CTA)
+    uint32_t tmem_base = 0, tmem_mine = 0;
+    if constexpr (S::TBL_TMEM) {
+        uint32_t* slot = reinterpret_cast<uint32_t*>(bar_p + 1);
+        tmem_setup<S>(slot, table, tw, tid, tmem_base, tmem_mine);
+    }
     __syncthreads();
 
     // sample rows n2 < PR of every frame of group gg -> P (one bulk copy per frame, or one per group)
@@ -345,12 +354,6 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_rx_kernel(cpx* __restrict
             load_head(gn);
         }
         STAGE_MARK(17) // stage A' reads
-        cpx tc[M];
-        if constexpr (!S::TBL_SMEM) { // table column of the first item: in flight during its M-point FFT
-            const int n1 = tid % K;
-#pragma unroll
-            for (int m = 0; m < M; ++m) tc[m] = ldg_nc(table + m * K + n1);
-        }
 #pragma unroll
         for (int j = 0; j < IPT; ++j) {
             const int it = tid + j * T;
@@ -360,13 +363,11 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_rx_kernel(cpx* __restrict
 #pragma unroll
                 for (int m = 0; m < M; ++m) v[j][m] = cmul(v[j][m], tbl_s[m * K + n1]);
             } else {
+                float tf[2 * M]; // this item's table column out of tensor memory
+                tmem_ld<2 * M>(tf, tmem_mine + j * 2 * M);
+                tmem_wait_ld();
 #pragma unroll
-                for (int m = 0; m < M; ++m) v[j][m] = cmul(v[j][m], tc[m]);
-                if (j + 1 < IPT) {
-                    const int n1n = (tid + (j + 1) * T) % K;
-#pragma unroll
-                    for (int m = 0; m < M; ++m) tc[m] = ldg_nc(table + m * K + n1n);
-                }
+                for (int m = 0; m < M; ++m) v[j][m] = cmul(v[j][m], cmake(tf[2 * m], tf[2 * m + 1]));
             }
         }
         // the previous group's bulk store must have finished reading R
@@ -384,7 +385,7 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_rx_kernel(cpx* __restrict
         __syncthreads();
         STAGE_MARK(19) // row writes
         // ---- stage B: K-point forward FFT of every row (over n1)
-        row_fft<S, -1>(buf, tw_s, tid);
+        row_fft<S, -1>(buf, tw_s, tid, tmem_mine + S::TMEM_TBL_COLS);
         STAGE_MARK(20) // row FFT
         if (gn < n_groups) load_rest(gn); // tail rows of the next group: in flight during stage C'
         __syncthreads();
@@ -534,6 +535,11 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_rx_kernel(cpx* __restrict
         STAGE_MARK(23) // M-IFFT + output staging + store issue
     }
     if (tid == 0) bulk_wait_all();
+    if constexpr (S::TBL_TMEM) {
+        tmem_fence_before_sync();
+        __syncthreads();
+        if (tid < 32) tmem_dealloc(tmem_base, S::TMEM_COLS);
+    }
 }
 
 // ----------------------------------------------------------------------------------------

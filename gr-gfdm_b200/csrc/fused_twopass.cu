@@ -402,7 +402,7 @@ struct TwoPass {
     std::string name;
 };
 
-typedef Shape<15, 32, 32, 512, 2, 1> S15x1024;
+typedef Shape<15, 32, 32, 512, 2, 1, false> S15x1024;
 
 bool twopass_supported(int M, int K) { return M == S15x1024::M && K == 2 * S15x1024::K; }
 
