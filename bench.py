@@ -199,6 +199,30 @@ def run_reference(args, w):
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_numa_node(torch, local_rank):
+    """Pin this rank to the CPUs next to its GPU (sysfs local_cpulist) BEFORE the pinned host buffers are
+    allocated, so that first-touch places them on the GPU's NUMA node and the HOST-buffer legs of N ranks do not
+    share one memory controller.  Returns (previous affinity, description); a no-op when sysfs has no answer."""
+    try:
+        prev = os.sched_getaffinity(0)
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = '%04x:%02x:%02x.0' % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        txt = open('/sys/bus/pci/devices/%s/local_cpulist' % bdf).read().strip()
+        cpus = set()
+        for part in txt.split(','):
+            if not part:
+                continue
+            lo, _, hi = part.partition('-')
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= prev
+        if cpus and cpus != prev:
+            os.sched_setaffinity(0, cpus)
+            return prev, '%s: %d of %d cpus' % (bdf, len(cpus), len(prev))
+        return prev, '%s: all %d cpus local' % (bdf, len(prev))
+    except Exception as e:  # noqa: BLE001 -- containers without sysfs, odd topologies
+        return None, 'unavailable (%s)' % type(e).__name__
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -241,6 +265,7 @@ def main():
     mod.set_stream(stream.cuda_stream)
     dem.set_stream(stream.cuda_stream)
 
+    prev_affinity, affinity_desc = bind_to_gpu_numa_node(torch, local_rank)
     host_in = torch.from_numpy(make_symbols(w, frames, rank)).pin_memory()
     d_in = host_in.to(dev, non_blocking=False)
     d_tx = torch.empty_like(d_in)
@@ -320,6 +345,63 @@ def main():
                'steps': args.e2e_steps, 'ms_per_step': float(dt.item()) * 1e3,
                'path': 'gfdm_modulator_work_batch + gfdm_receiver_work_batch, GFDM_MEM_HOST, pinned host buffers'}
 
+    # ---- the same chain through the byte-wide entries: chunks -> samples -> hard decisions.
+    # Reported beside the headline, never instead of it: the symbol side crosses HBM / PCIe as 1 byte per symbol.
+    chunk_chain = None
+    if not args.no_e2e and N % 16 == 0:
+        from gfdm_b200 import design
+        sm = capi.Symbol_mapper((design.qam16_points(), capi.DECISION_NEAREST), lib=lib)
+        g = torch.Generator(device=dev).manual_seed(w['seed'] + rank)
+        d_ch = torch.randint(0, 16, (frames, N), dtype=torch.uint8, device=dev, generator=g)
+        d_dec = torch.empty_like(d_ch)
+        host_ch = d_ch.cpu().pin_memory()
+        host_dec = torch.empty_like(host_ch).pin_memory()
+        cev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+
+        def chunk_step(record=False):
+            if record:
+                cev[0].record(stream)
+            mod.modulate_chunks_ptr(sm, d_tx.data_ptr(), d_ch.data_ptr(), frames)
+            if record:
+                cev[1].record(stream)
+            dem.demodulate_decide_ptr(sm, d_dec.data_ptr(), d_tx.data_ptr(), 0, frames)
+            if record:
+                cev[2].record(stream)
+
+        with torch.cuda.stream(stream):
+            for _ in range(3):
+                chunk_step()
+            chunk_step(True)
+        barrier()
+        cm, cd = cev[0].elapsed_time(cev[1]), cev[1].elapsed_time(cev[2])
+        errors = int((d_dec != d_ch).sum().item())
+
+        def chunk_e2e():
+            mod.modulate_chunks_batch_host_ptr(sm, host_tx.data_ptr(), host_ch.data_ptr(), frames)
+            dem.demodulate_decide_batch_host_ptr(sm, host_dec.data_ptr(), host_tx.data_ptr(), 0, frames)
+
+        chunk_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            chunk_e2e()
+        barrier()
+        dtc = torch.tensor([(time.perf_counter() - t0) / args.e2e_steps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dtc, op=dist.ReduceOp.MAX)
+        chunk_chain = {'value': frames / ((cm + cd) * 1e-3), 'unit': 'frames/s per GPU (device resident)',
+                       'kernel_ms': {'modulator': cm, 'receiver': cd},
+                       'kernels': {'modulator': mod.last_kernel(), 'receiver': dem.last_kernel()},
+                       'algorithmic_bytes_per_frame': 2 * (8 * N + N),
+                       'achieved_gbs': 2 * 9.0 * N * frames / ((cm + cd) * 1e-3) / 1e9,
+                       'symbol_errors_noiseless': errors,
+                       'e2e': {'value': world * frames / float(dtc.item()), 'unit': 'frames/s',
+                               'h2d_bytes_per_step': frames * 9 * N, 'd2h_bytes_per_step': frames * 9 * N,
+                               'ms_per_step': float(dtc.item()) * 1e3,
+                               'path': 'gfdm_modulator_work_chunks_batch + gfdm_receiver_work_decide_batch, GFDM_MEM_HOST'}}
+    if prev_affinity is not None:
+        os.sched_setaffinity(0, prev_affinity)  # the CPU baseline leg uses every host core
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -365,6 +447,9 @@ def main():
     }
     if e2e is not None:
         line['e2e'] = e2e
+        line['config']['host_affinity'] = affinity_desc
+    if chunk_chain is not None:
+        line['chunk_chain'] = chunk_chain
     if not args.no_cpu:
         ref = cpu_reference_run(w, seconds_budget=args.cpu_seconds / 2.0)
         ref['run']()  # warm

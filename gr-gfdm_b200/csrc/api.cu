@@ -168,13 +168,16 @@ static size_t chunk_frames(size_t bytes_per_frame, size_t n)
 // i-1 (stream s_d2h) run concurrently, so both PCIe directions stay busy.  run(dout, d0, d1, f0, nf)
 // enqueues the kernels of one chunk on h->stream.  Synchronous for the caller, like generic_work.
 // seed_out: the staged output starts as the caller's data (kernels that leave elements untouched).
+// Sizes are BYTES per frame (the symbol side of a frame may be one byte per symbol, see the chunk entries).
 template <class Run>
-static void host_pipeline(HandleBase* h, size_t n, size_t chunk, const gfdm_complex* in0, size_t in0_sz,
-                          const gfdm_complex* in1, size_t in1_sz, gfdm_complex* out, size_t out_sz, bool seed_out,
-                          Run run)
+static void host_pipeline_bytes(HandleBase* h, size_t n, size_t chunk, const void* in0v, size_t in0_sz, const void* in1v,
+                                size_t in1_sz, void* outv, size_t out_sz, bool seed_out, Run run)
 {
     if (!n) return;
     if (chunk < 1) chunk = 1;
+    const unsigned char* in0 = static_cast<const unsigned char*>(in0v);
+    const unsigned char* in1 = static_cast<const unsigned char*>(in1v);
+    unsigned char* out = static_cast<unsigned char*>(outv);
     if (!h->s_h2d) {
         GFDM_CUDA_CHECK(cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
         GFDM_CUDA_CHECK(cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));
@@ -186,9 +189,9 @@ static void host_pipeline(HandleBase* h, size_t n, size_t chunk, const gfdm_comp
     }
     const size_t c0 = std::min(chunk, n);
     for (int i = 0; i < 2; ++i) {
-        if (in0 && in0_sz) h->slot_in0[i].ensure(c0 * in0_sz * sizeof(cpx));
-        if (in1 && in1_sz) h->slot_in1[i].ensure(c0 * in1_sz * sizeof(cpx));
-        h->slot_out[i].ensure(std::max<size_t>(c0 * out_sz, 1) * sizeof(cpx));
+        if (in0 && in0_sz) h->slot_in0[i].ensure(c0 * in0_sz);
+        if (in1 && in1_sz) h->slot_in1[i].ensure(c0 * in1_sz);
+        h->slot_out[i].ensure(std::max<size_t>(c0 * out_sz, 16));
     }
     // work queued earlier on the handle's stream may still use the slots (a DEVICE call followed by a HOST call)
     GFDM_CUDA_CHECK(cudaEventRecord(h->ev_run[0], h->stream));
@@ -197,23 +200,23 @@ static void host_pipeline(HandleBase* h, size_t n, size_t chunk, const gfdm_comp
     for (size_t f0 = 0; f0 < n; f0 += chunk, ++idx) {
         const size_t nf = std::min(chunk, n - f0);
         const int sl = (int)(idx & 1);
-        cpx* d0 = nullptr;
-        cpx* d1 = nullptr;
-        cpx* dout = h->slot_out[sl].as<cpx>();
+        void* d0 = nullptr;
+        void* d1 = nullptr;
+        void* dout = h->slot_out[sl].p;
         // inputs of this slot are free once the kernels of chunk idx-2 have run
         if (idx >= 2) GFDM_CUDA_CHECK(cudaStreamWaitEvent(h->s_h2d, h->ev_run[sl], 0));
         if (in0 && in0_sz) {
-            d0 = h->slot_in0[sl].as<cpx>();
-            GFDM_CUDA_CHECK(cudaMemcpyAsync(d0, in0 + f0 * in0_sz, nf * in0_sz * sizeof(cpx), cudaMemcpyHostToDevice, h->s_h2d));
+            d0 = h->slot_in0[sl].p;
+            GFDM_CUDA_CHECK(cudaMemcpyAsync(d0, in0 + f0 * in0_sz, nf * in0_sz, cudaMemcpyHostToDevice, h->s_h2d));
         }
         if (in1 && in1_sz) {
-            d1 = h->slot_in1[sl].as<cpx>();
-            GFDM_CUDA_CHECK(cudaMemcpyAsync(d1, in1 + f0 * in1_sz, nf * in1_sz * sizeof(cpx), cudaMemcpyHostToDevice, h->s_h2d));
+            d1 = h->slot_in1[sl].p;
+            GFDM_CUDA_CHECK(cudaMemcpyAsync(d1, in1 + f0 * in1_sz, nf * in1_sz, cudaMemcpyHostToDevice, h->s_h2d));
         }
         if (seed_out) {
             // the output slot is free once chunk idx-2 has been copied back
             if (idx >= 2) GFDM_CUDA_CHECK(cudaStreamWaitEvent(h->s_h2d, h->ev_out[sl], 0));
-            GFDM_CUDA_CHECK(cudaMemcpyAsync(dout, out + f0 * out_sz, nf * out_sz * sizeof(cpx), cudaMemcpyHostToDevice, h->s_h2d));
+            GFDM_CUDA_CHECK(cudaMemcpyAsync(dout, out + f0 * out_sz, nf * out_sz, cudaMemcpyHostToDevice, h->s_h2d));
         }
         GFDM_CUDA_CHECK(cudaEventRecord(h->ev_in[sl], h->s_h2d));
         GFDM_CUDA_CHECK(cudaStreamWaitEvent(h->stream, h->ev_in[sl], 0));
@@ -222,11 +225,22 @@ static void host_pipeline(HandleBase* h, size_t n, size_t chunk, const gfdm_comp
         GFDM_CUDA_CHECK(cudaEventRecord(h->ev_run[sl], h->stream));
         GFDM_CUDA_CHECK(cudaStreamWaitEvent(h->s_d2h, h->ev_run[sl], 0));
         if (out_sz)
-            GFDM_CUDA_CHECK(cudaMemcpyAsync(out + f0 * out_sz, dout, nf * out_sz * sizeof(cpx), cudaMemcpyDeviceToHost, h->s_d2h));
+            GFDM_CUDA_CHECK(cudaMemcpyAsync(out + f0 * out_sz, dout, nf * out_sz, cudaMemcpyDeviceToHost, h->s_d2h));
         GFDM_CUDA_CHECK(cudaEventRecord(h->ev_out[sl], h->s_d2h));
     }
     GFDM_CUDA_CHECK(cudaStreamSynchronize(h->s_d2h));
     GFDM_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+}
+// the same with every array complex64 and sizes in elements per frame
+template <class Run>
+static void host_pipeline(HandleBase* h, size_t n, size_t chunk, const gfdm_complex* in0, size_t in0_sz,
+                          const gfdm_complex* in1, size_t in1_sz, gfdm_complex* out, size_t out_sz, bool seed_out,
+                          Run run)
+{
+    host_pipeline_bytes(h, n, chunk, in0, in0_sz * sizeof(cpx), in1, in1_sz * sizeof(cpx), out, out_sz * sizeof(cpx), seed_out,
+                        [&](void* dout, const void* d0, const void* d1, size_t f0, size_t nf) {
+                            run(static_cast<cpx*>(dout), static_cast<const cpx*>(d0), static_cast<const cpx*>(d1), f0, nf);
+                        });
 }
 
 // frames per pipeline chunk: 32 MB of host traffic per chunk keeps fill/drain below a millisecond
@@ -1438,6 +1452,417 @@ int gfdm_transmitter_work_all_batch(gfdm_transmitter* h, gfdm_complex* out, cons
                                     int mem)
 {
     return transmitter_batch(h, TX_WORK_ALL, out, in, nin, 0, n, mem);
+}
+
+/* ======================================================================== */
+/* rows either side of the hot path     */
+
+/* ---- remove_prefix_cc: lib/remove_prefix_cc_impl.cc:84-115 ---------------- */
+struct gfdm_remove_prefix : HandleBase {
+    int frame_len = 0, block_len = 0, offset = 0;
+};
+int gfdm_remove_prefix_create(gfdm_remove_prefix** out, int frame_len, int block_len, int offset)
+{
+    API_TRY
+    // the block does not validate (:44-61) and would read past the frame; the ABI rejects it
+    if (frame_len < 1 || block_len < 1 || offset < 0 || offset + block_len > frame_len)
+        throw std::invalid_argument("remove_prefix: offset + block_len MUST NOT exceed frame_len!");
+    std::unique_ptr<gfdm_remove_prefix> h(new gfdm_remove_prefix);
+    h->frame_len = frame_len; h->block_len = block_len; h->offset = offset;
+    h->open();
+    *out = h.release();
+    API_CATCH
+}
+void gfdm_remove_prefix_destroy(gfdm_remove_prefix* h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    h->close();
+    delete h;
+}
+int gfdm_remove_prefix_work_batch(gfdm_remove_prefix* h, gfdm_complex* out, const gfdm_complex* in, int n, int mem)
+{
+    API_TRY
+    h->use();
+    if (n < 0) throw std::invalid_argument("n_frames MUST NOT be negative");
+    Staging st(h, mem);
+    // the strided copy of remove_cyclic_prefix with cp = offset, cs = whatever follows the block
+    const int cs = h->frame_len - h->block_len - h->offset;
+    auto run = [&](cpx* dout, const cpx* d0, const cpx*, size_t, size_t nf) {
+        launch_remove_cp(dout, d0, h->block_len, h->offset, cs, nf, h->stream);
+        h->launches += 1;
+        h->last_kernel = "remove_cp_kernel";
+    };
+    if (mem == GFDM_MEM_DEVICE)
+        run(reinterpret_cast<cpx*>(out), reinterpret_cast<const cpx*>(in), nullptr, 0, (size_t)n);
+    else
+        host_pipeline(h, (size_t)n, pipe_chunk(sizeof(cpx) * ((size_t)h->frame_len + h->block_len), (size_t)n), in,
+                      (size_t)h->frame_len, nullptr, 0, out, (size_t)h->block_len, false, run);
+    API_CATCH
+}
+
+/* ---- extract_burst_cc: lib/extract_burst_cc_impl.cc:43-242 ----------------- */
+struct gfdm_extract_burst : HandleBase {
+    int burst_len = 0, tag_backoff = 0;
+    bool cfo = false;
+    DeviceBuf d_desc;
+};
+int gfdm_extract_burst_create(gfdm_extract_burst** out, int burst_len, int tag_backoff, int activate_cfo_correction)
+{
+    API_TRY
+    if (burst_len < 1) throw std::invalid_argument("extract_burst: burst_len MUST be positive!");
+    std::unique_ptr<gfdm_extract_burst> h(new gfdm_extract_burst);
+    h->burst_len = burst_len; h->tag_backoff = tag_backoff; h->cfo = activate_cfo_correction != 0;
+    h->open();
+    *out = h.release();
+    API_CATCH
+}
+void gfdm_extract_burst_destroy(gfdm_extract_burst* h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    h->d_desc.release();
+    h->close();
+    delete h;
+}
+int gfdm_extract_burst_activate_cfo_compensation(gfdm_extract_burst* h, int on)
+{
+    h->cfo = on != 0;
+    return GFDM_OK;
+}
+int gfdm_extract_burst_work(gfdm_extract_burst* h, gfdm_complex* out, int max_bursts, const gfdm_complex* in,
+                            long long n_in, const long long* burst_starts, const float* scale_factors,
+                            const gfdm_complex* phase_rotations, int n_tags, int* n_produced, long long* n_consumed,
+                            int mem)
+{
+    API_TRY
+    h->use();
+    if (max_bursts < 0 || n_in < 0 || n_tags < 0) throw std::invalid_argument("sizes MUST NOT be negative");
+    for (int i = 1; i < n_tags; ++i)
+        if (burst_starts[i] < burst_starts[i - 1]) throw std::invalid_argument("extract_burst: burst_starts MUST be sorted!");
+    Staging st(h, mem);
+    // the control flow of general_work (:117-242) runs on the host over the tag arrays and yields one
+    // descriptor per produced burst; the samples are touched by the kernel only
+    const long long BL = h->burst_len, noutput_items = (long long)max_bursts * BL, avail_items = n_in;
+    long long consumed_items = avail_items, produced_items = 0;
+    std::vector<BurstDesc> desc;
+    for (int t = 0; t < n_tags; ++t) {
+        const long long burst_start = burst_starts[t];
+        if (avail_items - burst_start >= BL && produced_items + BL <= noutput_items) {
+            BurstDesc d{};
+            d.start = burst_start - h->tag_backoff;
+            d.scale = scale_factors ? scale_factors[t] : 1.0f;
+            // get_phase_rotation (:88-96): inc = conj(pr)/|pr| rounded to complex<float>; the kernel rotates by its angle
+            const cf pr = phase_rotations ? cf(phase_rotations[t].re, phase_rotations[t].im) : cf(1.0f, 0.0f);
+            const double scale = 1.0 / std::abs(pr);
+            const cf inc((float)(scale * pr.real()), (float)(-1.0f * scale * pr.imag()));
+            d.angle = std::atan2((double)inc.imag(), (double)inc.real());
+            d.inc_re = std::cos(d.angle);
+            d.inc_im = std::sin(d.angle);
+            desc.push_back(d);
+            produced_items += BL;
+            consumed_items = burst_start + BL;
+        } else {
+            consumed_items = burst_start > 0 ? burst_start : 0;
+            break;
+        }
+    }
+    const int nb = (int)desc.size();
+    if (nb > 0) {
+        h->d_desc.ensure(sizeof(BurstDesc) * desc.size());
+        GFDM_CUDA_CHECK(cudaMemcpyAsync(h->d_desc.p, desc.data(), sizeof(BurstDesc) * desc.size(), cudaMemcpyHostToDevice, h->stream));
+        GFDM_CUDA_CHECK(cudaStreamSynchronize(h->stream)); // `desc` is pageable and dies with this call
+        const cpx* di = st.in(in, (size_t)n_in, h->stage_in);
+        cpx* dout = st.out(out, (size_t)nb * BL, h->stage_out);
+        launch_extract_burst(dout, di, h->d_desc.as<BurstDesc>(), h->burst_len, h->cfo, nb, h->stream);
+        h->launches += 1;
+        h->last_kernel = "extract_burst_kernel";
+        st.finish(out, (size_t)nb * BL, h->stage_out);
+    }
+    if (n_produced) *n_produced = nb;
+    if (n_consumed) *n_consumed = consumed_items;
+    API_CATCH
+}
+
+/* ---- symbol mapping: python/pygfdm/symbolmapping.py:27-47, utils.py:47-51 -- */
+struct gfdm_symbol_mapper : HandleBase {
+    std::vector<cf> points;
+    int rule = 0, bits = 0;
+    cpx* d_points = nullptr;
+};
+int gfdm_symbol_mapper_create(gfdm_symbol_mapper** out, const gfdm_constellation* c)
+{
+    API_TRY
+    if (!c || !c->points || c->n_points < 1 || c->n_points > 256)
+        throw std::invalid_argument("constellation MUST have between 1 and 256 points!");
+    if (c->decision_rule == GFDM_DECISION_QPSK_SIGN && c->n_points != 4)
+        throw std::invalid_argument("the QPSK sign rule needs exactly 4 constellation points!");
+    std::unique_ptr<gfdm_symbol_mapper> h(new gfdm_symbol_mapper);
+    h->points = vec(c->points, c->n_points);
+    h->rule = c->decision_rule;
+    for (int b = 0; b <= 8; ++b)
+        if ((1 << b) == c->n_points) h->bits = b;
+    h->open();
+    h->d_points = dev_upload(h->points);
+    *out = h.release();
+    API_CATCH
+}
+void gfdm_symbol_mapper_destroy(gfdm_symbol_mapper* h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->d_points) cudaFree(h->d_points);
+    h->close();
+    delete h;
+}
+int gfdm_symbol_mapper_n_points(const gfdm_symbol_mapper* h) { return (int)h->points.size(); }
+int gfdm_symbol_mapper_bits_per_symbol(const gfdm_symbol_mapper* h) { return h->bits; }
+int gfdm_symbol_mapper_points(const gfdm_symbol_mapper* h, gfdm_complex* o)
+{
+    memcpy(o, h->points.data(), sizeof(cf) * h->points.size());
+    return GFDM_OK;
+}
+int gfdm_symbol_mapper_decision_rule(const gfdm_symbol_mapper* h) { return h->rule; }
+
+extern "C++" {
+// run(dout, din, n) on device pointers; HOST arrays are staged in chunks of <= 64 Mi symbols
+template <class Run>
+static void symbol_batch(gfdm_symbol_mapper* h, void* out, size_t out_b, const void* in, size_t in_b, size_t n, int mem,
+                         Run run)
+{
+    Staging st(h, mem);
+    if (mem == GFDM_MEM_DEVICE) {
+        run(out, in, n);
+        return;
+    }
+    const size_t c = std::min<size_t>(n, (size_t)64 << 20);
+    for (size_t i0 = 0; i0 < n; i0 += c) {
+        const size_t ni = std::min(c, n - i0);
+        h->stage_in.ensure(ni * in_b);
+        h->stage_out.ensure(ni * out_b);
+        GFDM_CUDA_CHECK(cudaMemcpyAsync(h->stage_in.p, static_cast<const unsigned char*>(in) + i0 * in_b, ni * in_b,
+                                        cudaMemcpyHostToDevice, h->stream));
+        run(h->stage_out.p, h->stage_in.p, ni);
+        GFDM_CUDA_CHECK(cudaMemcpyAsync(static_cast<unsigned char*>(out) + i0 * out_b, h->stage_out.p, ni * out_b,
+                                        cudaMemcpyDeviceToHost, h->stream));
+        h->sync();
+    }
+}
+} // extern "C++"
+int gfdm_symbol_mapper_map_chunks_batch(gfdm_symbol_mapper* h, gfdm_complex* out, const unsigned char* chunks, size_t n,
+                                        int mem)
+{
+    API_TRY
+    h->use();
+    symbol_batch(h, out, sizeof(cpx), chunks, 1, n, mem, [&](void* o, const void* i, size_t ni) {
+        launch_map_chunks(static_cast<cpx*>(o), static_cast<const unsigned char*>(i), h->d_points, (int)h->points.size(), ni,
+                          h->stream);
+        h->launches += ni ? 1 : 0;
+        h->last_kernel = "map_chunks_kernel";
+    });
+    API_CATCH
+}
+int gfdm_symbol_mapper_decide_batch(gfdm_symbol_mapper* h, unsigned char* chunks, const gfdm_complex* in, size_t n, int mem)
+{
+    API_TRY
+    h->use();
+    symbol_batch(h, chunks, 1, in, sizeof(cpx), n, mem, [&](void* o, const void* i, size_t ni) {
+        launch_decide_chunks(static_cast<unsigned char*>(o), static_cast<const cpx*>(i), h->d_points, (int)h->points.size(),
+                             h->rule, ni, h->stream);
+        h->launches += ni ? 1 : 0;
+        h->last_kernel = "decide_chunks_kernel";
+    });
+    API_CATCH
+}
+int gfdm_symbol_mapper_bits2symbols_batch(gfdm_symbol_mapper* h, gfdm_complex* out, const unsigned char* bits, size_t n,
+                                          int mem)
+{
+    API_TRY
+    h->use();
+    if (h->bits < 1) throw std::invalid_argument("bits2symbols: the constellation size MUST be a power of two >= 2!");
+    symbol_batch(h, out, sizeof(cpx), bits, (size_t)h->bits, n, mem, [&](void* o, const void* i, size_t ni) {
+        launch_bits2symbols(static_cast<cpx*>(o), static_cast<const unsigned char*>(i), h->d_points, (int)h->points.size(),
+                            h->bits, ni, h->stream);
+        h->launches += ni ? 1 : 0;
+        h->last_kernel = "bits2symbols_kernel";
+    });
+    API_CATCH
+}
+int gfdm_symbol_mapper_symbols2bits_batch(gfdm_symbol_mapper* h, unsigned char* bits, const gfdm_complex* in, size_t n,
+                                          int mem)
+{
+    API_TRY
+    h->use();
+    if (h->bits < 1) throw std::invalid_argument("symbols2bits: the constellation size MUST be a power of two >= 2!");
+    symbol_batch(h, bits, (size_t)h->bits, in, sizeof(cpx), n, mem, [&](void* o, const void* i, size_t ni) {
+        launch_symbols2bits(static_cast<unsigned char*>(o), static_cast<const cpx*>(i), h->d_points, (int)h->points.size(),
+                            h->rule, h->bits, ni, h->stream);
+        h->launches += ni ? 1 : 0;
+        h->last_kernel = "symbols2bits_kernel";
+    });
+    API_CATCH
+}
+
+/* ---- chunk entries of the path kernels -------------------------------------- */
+// The constellation lives on the symbol mapper's device; handles of one chain share a device.
+static void check_same_device(const HandleBase* a, const gfdm_symbol_mapper* sm)
+{
+    if (!sm || sm->magic != HANDLE_MAGIC) throw std::invalid_argument("symbol mapper MUST NOT be NULL");
+    if (a->device != sm->device) throw std::invalid_argument("the symbol mapper lives on another device");
+}
+
+static void modulator_run_chunks(gfdm_modulator* h, const gfdm_symbol_mapper* sm, cpx* out, const unsigned char* chunks,
+                                 size_t frames)
+{
+    if (!frames) return;
+    const int np = (int)sm->points.size();
+    if (h->fused.available() && h->fused.supports_chunks(np) && aligned16(chunks) && aligned16(out)) {
+        h->launches += h->fused.modulate_chunks(out, chunks, sm->d_points, np, frames, h->stream);
+        h->last_kernel = h->fused.modc_name();
+        return;
+    }
+    // shapes without a byte-input kernel: lookup kernel into scratch, then the symbol path
+    const size_t el = frames * (size_t)h->N;
+    h->work_c.ensure(el * sizeof(cpx));
+    launch_map_chunks(h->work_c.as<cpx>(), chunks, sm->d_points, np, el, h->stream);
+    h->launches += 1;
+    modulator_run(h, out, h->work_c.as<cpx>(), frames);
+}
+int gfdm_modulator_work_chunks_batch(gfdm_modulator* h, const gfdm_symbol_mapper* sm, gfdm_complex* out,
+                                     const unsigned char* chunks, int n, int mem)
+{
+    API_TRY
+    h->use();
+    if (n < 0) throw std::invalid_argument("n_frames MUST NOT be negative");
+    check_same_device(h, sm);
+    Staging st(h, mem);
+    if (mem == GFDM_MEM_DEVICE) {
+        modulator_run_chunks(h, sm, reinterpret_cast<cpx*>(out), chunks, (size_t)n);
+    } else {
+        host_pipeline_bytes(h, (size_t)n, pipe_chunk((sizeof(cpx) + 1) * h->N, (size_t)n), chunks, (size_t)h->N, nullptr, 0, out,
+                            sizeof(cpx) * h->N, false, [&](void* dout, const void* d0, const void*, size_t, size_t nf) {
+                                modulator_run_chunks(h, sm, static_cast<cpx*>(dout), static_cast<const unsigned char*>(d0), nf);
+                            });
+    }
+    API_CATCH
+}
+
+static void receiver_run_decide(gfdm_receiver* h, const gfdm_symbol_mapper* sm, unsigned char* chunks_out, const cpx* in,
+                                const cpx* eq, size_t frames)
+{
+    if (!frames) return;
+    const int np = (int)sm->points.size();
+    if (h->fused.available() && (!eq || h->fused.supports_eq()) && h->fused.supports_chunks(np) && aligned16(in) &&
+        aligned16(chunks_out) && (!eq || aligned16(eq))) {
+        h->launches += h->fused.demodulate_decide(chunks_out, in, eq, sm->d_points, np, sm->rule, frames, h->stream);
+        h->last_kernel = h->fused.rxd_name();
+        return;
+    }
+    const size_t el = frames * (size_t)h->N;
+    h->work_c.ensure(el * sizeof(cpx));
+    receiver_run(h, h->work_c.as<cpx>(), in, eq, frames);
+    launch_decide_chunks(chunks_out, h->work_c.as<cpx>(), sm->d_points, np, sm->rule, el, h->stream);
+    h->launches += 1;
+}
+int gfdm_receiver_work_decide_batch(gfdm_receiver* h, const gfdm_symbol_mapper* sm, unsigned char* chunks_out,
+                                    const gfdm_complex* in, const gfdm_complex* eq, int n, int mem)
+{
+    API_TRY
+    h->use();
+    if (n < 0) throw std::invalid_argument("n_frames MUST NOT be negative");
+    check_same_device(h, sm);
+    Staging st(h, mem);
+    const size_t N = h->N;
+    if (mem == GFDM_MEM_DEVICE) {
+        receiver_run_decide(h, sm, chunks_out, reinterpret_cast<const cpx*>(in), reinterpret_cast<const cpx*>(eq), (size_t)n);
+    } else {
+        host_pipeline_bytes(h, (size_t)n, pipe_chunk(((eq ? 2 : 1) * sizeof(cpx) + 1) * N, (size_t)n), in, sizeof(cpx) * N, eq,
+                            sizeof(cpx) * N, chunks_out, N, false,
+                            [&](void* dout, const void* d0, const void* d1, size_t, size_t nf) {
+                                receiver_run_decide(h, sm, static_cast<unsigned char*>(dout), static_cast<const cpx*>(d0),
+                                                    static_cast<const cpx*>(d1), nf);
+                            });
+    }
+    API_CATCH
+}
+
+int gfdm_transmitter_work_chunks_batch(gfdm_transmitter* h, const gfdm_symbol_mapper* sm, gfdm_complex* out,
+                                       const unsigned char* chunks, int nin, int n, int mem)
+{
+    API_TRY
+    h->use();
+    if (n < 0) throw std::invalid_argument("n_frames MUST NOT be negative");
+    if (nin < 0) throw std::invalid_argument("ninput_size MUST NOT be negative");
+    h->map.check_map_size((size_t)nin);
+    check_same_device(h, sm);
+    for (int s : h->shifts) h->pre.check_shift(s);
+    Staging st(h, mem);
+    const size_t os = h->out_size(), N = h->N;
+    const int np = (int)sm->points.size();
+    auto run = [&](cpx* dout, const unsigned char* dch, size_t nf) {
+        TxArgs ta;
+        ta.inv_map = h->map.d_inv; ta.front = h->pre.d_front; ta.back = h->pre.d_back; ta.preambles = h->d_preambles;
+        ta.A = h->map.A; ta.per_timeslot = h->map.per_timeslot ? 1 : 0; ta.n_in = nin;
+        ta.cp = h->pre.cp_len; ta.cs = h->pre.cs_len; ta.ramp = h->pre.ramp_len; ta.P = h->preamble_size;
+        ta.n_ant = 1;
+        ta.ant_stride = nf * os;
+        ta.shift[0] = h->shifts[0];
+        ta.pre_idx[0] = h->shift_index(h->shifts[0]);
+        ta.points = sm->d_points;
+        ta.n_points = np;
+        if (!h->force_staged && h->fused.available() && h->fused.supports_tx_chain_chunks(ta) && aligned16(dch)) {
+            h->launches += h->fused.transmit_chunks(dout, dch, ta, nf, h->stream);
+            h->last_kernel = h->fused.txc_name();
+            return;
+        }
+        // lookup kernel, then the symbol chain (fused or staged, as gfdm_transmitter_work_batch would run it)
+        const size_t el = nf * (size_t)nin;
+        h->work_c.ensure(std::max<size_t>(el, 1) * sizeof(cpx));
+        launch_map_chunks(h->work_c.as<cpx>(), dch, sm->d_points, np, el, h->stream);
+        h->launches += 1;
+        const cpx* di = h->work_c.as<cpx>();
+        if (!h->force_staged && h->fused.available() && h->fused.supports_tx_chain(ta)) {
+            h->launches += h->fused.transmit(dout, di, ta, nf, h->stream);
+            h->last_kernel = h->fused.tx_name();
+            return;
+        }
+        h->frame.ensure(nf * N * sizeof(cpx));
+        tx_modulate(h, h->frame.as<cpx>(), di, (size_t)nin, nf);
+        tx_add_frame(h, dout, h->frame.as<cpx>(), h->shifts[0], nf);
+        h->last_kernel = h->fused.available() ? "map_chunks+map+fused_mod+copy_rows+add_cp" : "generic:transmitter";
+    };
+    if (mem == GFDM_MEM_DEVICE) {
+        run(reinterpret_cast<cpx*>(out), chunks, (size_t)n);
+    } else {
+        host_pipeline_bytes(h, (size_t)n, pipe_chunk(sizeof(cpx) * os + (size_t)nin, (size_t)n), chunks, (size_t)nin, nullptr, 0,
+                            out, sizeof(cpx) * os, false, [&](void* dout, const void* d0, const void*, size_t, size_t nf) {
+                                run(static_cast<cpx*>(dout), static_cast<const unsigned char*>(d0), nf);
+                            });
+    }
+    API_CATCH
+}
+
+int gfdm_resource_mapper_demap_chunks_batch(gfdm_resource_mapper* h, unsigned char* out, const unsigned char* in, size_t sz,
+                                            int n, int mem)
+{
+    API_TRY
+    h->use();
+    h->c.check_demap_size(sz);
+    if (n < 0) throw std::invalid_argument("n_frames MUST NOT be negative");
+    if (sz == 0) return GFDM_OK;
+    Staging st(h, mem);
+    const size_t fs = h->c.frame_size;
+    auto run = [&](void* dout, const void* d0, const void*, size_t, size_t nf) {
+        launch_demap_chunks(static_cast<unsigned char*>(dout), static_cast<const unsigned char*>(d0), h->c.d_smap, h->c.M,
+                            h->c.K, h->c.A, h->c.per_timeslot, sz, nf, h->stream);
+        h->launches += 1;
+        h->last_kernel = "demap_chunks_kernel";
+    };
+    if (mem == GFDM_MEM_DEVICE)
+        run(out, in, nullptr, 0, (size_t)n);
+    else
+        host_pipeline_bytes(h, (size_t)n, pipe_chunk(fs + sz, (size_t)n), in, fs, nullptr, 0, out, sz, false, run);
+    API_CATCH
 }
 
 } // extern "C"

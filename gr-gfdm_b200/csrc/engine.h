@@ -47,4 +47,26 @@ void launch_est_snr(float* snr, float* cnrs, const cpx* F2, int K, int A, int dc
 void launch_zf_prepare(cpx* out, const cpx* in, size_t n, cudaStream_t s);
 void launch_energy(float* out, const cpx* in, size_t n, cudaStream_t s);
 
+// ---------------------------------------------------------------- next_kernels.cu
+// extract_burst_cc (lib/extract_burst_cc_impl.cc:117-242): one descriptor per produced burst
+struct BurstDesc {
+    long long start;       // index of the burst's first sample in the stream window (negative: zeros in front)
+    double angle;          // CFO rotation per sample (radians), = arg(inc)
+    double inc_re, inc_im; // cos/sin(angle)
+    float scale;           // power normalisation factor
+    int pad;
+};
+void launch_extract_burst(cpx* out, const cpx* in, const BurstDesc* desc, int burst_len, bool cfo, int n_bursts,
+                          cudaStream_t s);
+// symbol mapping (python/pygfdm/symbolmapping.py:27-47): chunk = constellation point index, one byte per symbol
+void launch_map_chunks(cpx* out, const unsigned char* chunks, const cpx* points, int n_points, size_t n, cudaStream_t s);
+void launch_decide_chunks(unsigned char* chunks, const cpx* in, const cpx* points, int n_points, int rule, size_t n,
+                          cudaStream_t s);
+void launch_bits2symbols(cpx* out, const unsigned char* bits, const cpx* points, int n_points, int bps, size_t n,
+                         cudaStream_t s);
+void launch_symbols2bits(unsigned char* bits, const cpx* in, const cpx* points, int n_points, int rule, int bps, size_t n,
+                         cudaStream_t s);
+void launch_demap_chunks(unsigned char* out, const unsigned char* in, const int* smap, int M, int K, int A, bool per_timeslot,
+                         size_t n_out, size_t frames, cudaStream_t s);
+
 } // namespace gfdm

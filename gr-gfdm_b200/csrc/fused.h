@@ -24,7 +24,11 @@ struct TxArgs {
     int n_ant = 1;
     int shift[GFDM_TX_MAX_ANT] = { 0, 0, 0, 0 };
     int pre_idx[GFDM_TX_MAX_ANT] = { 0, 0, 0, 0 };
+    // chunk input (one byte per symbol): constellation points, device pointer
+    const cpx* points = nullptr;
+    int n_points = 0;
 };
+constexpr int GFDM_FUSED_MAX_POINTS = 64; // constellation size the fused kernels keep in shared memory
 
 // host helpers shared by fused_modem.cu and fused_twopass.cu
 int fused_grid_cap(const void* fn, int threads, size_t smem); // persistent grid = SMs x resident CTAs
@@ -61,6 +65,19 @@ public:
     bool supports_tx_chain(const TxArgs& tx) const;
     int transmit(cpx* out, const cpx* in, const TxArgs& tx, size_t frames, cudaStream_t s);
     const char* tx_name() const;
+    // chunk entries: the symbol side of a frame is one byte per symbol.
+    // modulate_chunks: chunks [frames][N] -> out [frames][N]; transmit_chunks: chunks [frames][tx.n_in];
+    // demodulate_decide: in [frames][N] samples -> chunks_out [frames][N] hard decisions (full grid).
+    bool supports_chunks(int n_points) const;
+    int modulate_chunks(cpx* out, const unsigned char* chunks, const cpx* d_points, int n_points, size_t frames,
+                        cudaStream_t s);
+    bool supports_tx_chain_chunks(const TxArgs& tx) const;
+    int transmit_chunks(cpx* out, const unsigned char* chunks, const TxArgs& tx, size_t frames, cudaStream_t s);
+    int demodulate_decide(unsigned char* chunks_out, const cpx* in, const cpx* eq, const cpx* d_points, int n_points,
+                          int rule, size_t frames, cudaStream_t s);
+    const char* modc_name() const;
+    const char* txc_name() const;
+    const char* rxd_name() const;
     // out_td (soft symbols) and/or out_fd (fft_filter_downsample result) may be null; eq may be null
     int demodulate(cpx* out_td, cpx* out_fd, const cpx* in, const cpx* eq, size_t frames, cudaStream_t s);
     // advanced receiver: successive interference cancellation resident in the receiver kernel.

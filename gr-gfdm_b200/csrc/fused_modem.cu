@@ -45,7 +45,12 @@ namespace gfdm {
 // staged COMPACT symbol vectors (in: [n_frames][n_in]), and preamble insertion + cyclic prefix/suffix + window
 // (lib/add_cyclic_prefix_cc.cc:67-98) become the store pattern of stage C (out: [n_ant][n_frames][P+cp+N+cs]),
 // so a frame costs 8*(n_in + n_ant*(P+cp+N+cs)) bytes of HBM traffic instead of four kernels' worth.
-template <class S, bool TXF>
+//
+// CHK = true: the symbol side arrives as CHUNKS, one byte per symbol = index of a constellation point
+// (python/pygfdm/symbolmapping.py:34-38 / gr-digital chunks_to_symbols); `in` then points to bytes, the whole
+// group is staged in P (F*EL bytes) and stage A looks the points up in shared memory, so the symbols cross HBM
+// as EL instead of 8*EL bytes per frame.
+template <class S, bool TXF, bool CHK = false>
 __global__ void __launch_bounds__(S::T, S::MINB) fused_mod_kernel(cpx* __restrict__ out, const cpx* __restrict__ in,
                                                                   const cpx* __restrict__ table,
                                                                   const cpx* __restrict__ tw, int n_frames,
@@ -63,6 +68,16 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_mod_kernel(cpx* __restric
     uint64_t* bar_r = bars + 1; // tail of the staged input (region R)
     const int tid = threadIdx.x;
     const int n_groups = (n_frames + F - 1) / F;
+    // chunk input: staged bytes in P, constellation in the (otherwise unused) small-constant region
+    const unsigned char* in_b = reinterpret_cast<const unsigned char*>(in);
+    const unsigned char* pre_b = reinterpret_cast<const unsigned char*>(pre);
+    cpx* pts_s = pre + S::P_ELEMS + S::PTS_OFF;
+    if constexpr (CHK) {
+        static_assert((size_t)F * N <= (size_t)S::P_ELEMS * sizeof(cpx), "a group of chunks must fit in region P");
+        for (int i = tid; i < S::MAX_POINTS; i += T) pts_s[i] = i < tx.n_points ? tx.points[i] : cmake(0.f, 0.f);
+    }
+    const int n_pts = CHK ? tx.n_points : 0;
+    auto lookup = [&](unsigned char c) { return (int)c < n_pts ? pts_s[c] : cmake(0.f, 0.f); }; // chunk >= n_points: 0+0j
 
     for (int i = tid; i < S::TW_ELEMS; i += T) tw_s[i] = tw[i];
     for (int i = tid; i < S::TBL_ELEMS; i += T) tbl_s[i] = table[i];
@@ -81,11 +96,17 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_mod_kernel(cpx* __restric
     // issue the bulk loads of group gg: head -> P, tail -> R
     auto load_head = [&](int gg) {
         const int el = min(F, n_frames - gg * F) * EL;
+        if constexpr (CHK) {
+            mbar_expect_tx(bar_p, (uint32_t)el);
+            if (el) bulk_load(pre, in_b + (size_t)gg * F * EL, (uint32_t)el, bar_p);
+            return;
+        }
         const uint32_t bytes = (uint32_t)min(el, PF) * sizeof(cpx);
         mbar_expect_tx(bar_p, bytes);
         if (bytes) bulk_load(pre, in + (size_t)gg * F * EL, bytes, bar_p);
     };
     auto load_tail = [&](int gg) {
+        if constexpr (CHK) return;
         const int el = min(F, n_frames - gg * F) * EL;
         const uint32_t bytes = (uint32_t)max(el - PF, 0) * sizeof(cpx);
         mbar_expect_tx(bar_r, bytes);
@@ -109,13 +130,20 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_mod_kernel(cpx* __restric
         const int fh = min(F, n_frames - g * F);
         const int gn = g + gridDim.x;
         mbar_wait(bar_p, phase);
-        if (PF < F * N) mbar_wait(bar_r, phase);
+        if (!CHK && PF < F * N) mbar_wait(bar_r, phase);
         phase ^= 1;
         STAGE_MARK(0) // wait for the bulk loads
 
         cpx v[IPT][M];
         // ---- stage A: subcarrier symbols from the staged [k][m] block -> registers
-        if constexpr (!TXF) {
+        if constexpr (!TXF && CHK) {
+#pragma unroll
+            for (int j = 0; j < IPT; ++j) {
+                const unsigned char* src = pre_b + (tid + j * T) * M;
+#pragma unroll
+                for (int m = 0; m < M; ++m) v[j][m] = lookup(src[m]);
+            }
+        } else if constexpr (!TXF) {
 #pragma unroll
             for (int j = 0; j < IPT; ++j) {
                 const int e = (tid + j * T) * M; // (f*K + k)*M
@@ -134,7 +162,11 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_mod_kernel(cpx* __restric
                     const int src = tx.per_timeslot ? m * tx.A + a : a * M + m;
                     const int e = f * tx.n_in + src;
                     cpx val = cmake(0.f, 0.f);
-                    if (a >= 0 && src < tx.n_in) val = (e < PF) ? pre[e] : buf[e - PF];
+                    if constexpr (CHK) {
+                        if (a >= 0 && src < tx.n_in) val = lookup(pre_b[e]);
+                    } else {
+                        if (a >= 0 && src < tx.n_in) val = (e < PF) ? pre[e] : buf[e - PF];
+                    }
                     v[j][m] = val;
                 }
             }
@@ -255,7 +287,8 @@ struct SicArgs {
     float inv_map_total;         // 1 / (map.size() * M)
 };
 
-template <class S, bool SIC>
+// DEC = true: the output is the hard decision of every soft symbol, one byte per symbol (chunks) -- see the epilogue.
+template <class S, bool SIC, bool DEC = false>
 __global__ void __launch_bounds__(S::T, S::MINB) fused_rx_kernel(cpx* __restrict__ out, const cpx* __restrict__ in,
                                                                  const cpx* __restrict__ eq,
                                                                  const cpx* __restrict__ table,
@@ -282,8 +315,10 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_rx_kernel(cpx* __restrict
     if constexpr (SIC) {
         static_assert(IPT == 1, "the cancellation loop keeps one subcarrier per thread in registers");
         for (int i = tid; i < M && i < 32; i += T) taps_s[S::IC_OFF + i] = sic.ic_taps[i];
-        for (int i = tid; i < sic.n_points && i < S::MAX_POINTS; i += T) taps_s[S::PTS_OFF + i] = sic.points[i];
     }
+    // constellation: interference cancellation and the hard-decision output (mode 2)
+    if constexpr (SIC || DEC)
+        for (int i = tid; i < sic.n_points && i < S::MAX_POINTS; i += T) taps_s[S::PTS_OFF + i] = sic.points[i];
     if (tid == 0) mbar_init(bar_p, 1);
     // table columns of this thread -> tensor memory (once per CTA)
     uint32_t tmem_base = 0, tmem_mine = 0;
@@ -517,19 +552,34 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_rx_kernel(cpx* __restrict
         // slice drains to HBM while the next item's M-point IFFT runs
 #pragma unroll
         for (int j = 0; j < IPT; ++j) {
-            if (!SIC && mode == 0) {
+            if (!SIC && mode != 1) {
                 rf::FFTN<M, +1>::run(v[j]);
 #pragma unroll
                 for (int m = 0; m < M; ++m) v[j][m] = cscale(v[j][m], inv_m);
             }
-            cpx* dst = buf + (size_t)(tid + j * T) * M;
+            if constexpr (DEC) {
+                // hard decisions (symbols2bits' argmin / the constellation's decision rule): the soft symbols never
+                // leave the SM, the frame goes out as one byte per symbol in the same [k][m] order
+                unsigned char* dst = reinterpret_cast<unsigned char*>(buf) + (size_t)(tid + j * T) * M;
+                const cpx* pts_s = taps_s + S::PTS_OFF;
 #pragma unroll
-            for (int m = 0; m < M; ++m) dst[m] = v[j][m];
+                for (int m = 0; m < M; ++m) dst[m] = (unsigned char)decide_symbol(v[j][m], pts_s, sic.n_points, sic.rule);
+            } else {
+                cpx* dst = buf + (size_t)(tid + j * T) * M;
+#pragma unroll
+                for (int m = 0; m < M; ++m) dst[m] = v[j][m];
+            }
             fence_proxy_async();
             __syncthreads();
             if (tid == 0) {
                 const int e0 = j * T * M, e1 = min((j + 1) * T * M, fh * N);
-                if (e1 > e0) bulk_store(out + (size_t)g * F * N + e0, buf + e0, (uint32_t)(e1 - e0) * sizeof(cpx));
+                if (e1 > e0) {
+                    if constexpr (DEC)
+                        bulk_store(reinterpret_cast<unsigned char*>(out) + (size_t)g * F * N + e0,
+                                   reinterpret_cast<unsigned char*>(buf) + e0, (uint32_t)(e1 - e0));
+                    else
+                        bulk_store(out + (size_t)g * F * N + e0, buf + e0, (uint32_t)(e1 - e0) * sizeof(cpx));
+                }
             }
         }
         STAGE_MARK(23) // M-IFFT + output staging + store issue
@@ -561,8 +611,27 @@ static void launch_tx(cpx* out, const cpx* in, const cpx* table, const cpx* tw, 
 {
     fused_mod_kernel<S, true><<<grid, S::T, S::SMEM_BYTES, s>>>(out, in, table, tw, n_frames, tx);
 }
+template <class S>
+static void launch_modc(cpx* out, const cpx* in, const cpx* table, const cpx* tw, int n_frames, int grid,
+                        const TxArgs& tx, cudaStream_t s)
+{
+    fused_mod_kernel<S, false, true><<<grid, S::T, S::SMEM_BYTES, s>>>(out, in, table, tw, n_frames, tx);
+}
+template <class S>
+static void launch_txc(cpx* out, const cpx* in, const cpx* table, const cpx* tw, int n_frames, int grid,
+                       const TxArgs& tx, cudaStream_t s)
+{
+    fused_mod_kernel<S, true, true><<<grid, S::T, S::SMEM_BYTES, s>>>(out, in, table, tw, n_frames, tx);
+}
 typedef void (*sic_launch_t)(cpx*, const cpx*, const cpx*, const cpx*, const cpx*, const cpx*, int, int, int,
                              SicArgs, cudaStream_t);
+// receiver with the hard-decision output (DEC): the constellation travels in SicArgs
+template <class S>
+static void launch_rxd(cpx* out, const cpx* in, const cpx* eq, const cpx* table, const cpx* tw, const cpx* taps, int L,
+                       int n_frames, int grid, SicArgs sic, cudaStream_t s)
+{
+    fused_rx_kernel<S, false, true><<<grid, S::T, S::SMEM_BYTES, s>>>(out, in, eq, table, tw, taps, L, 0, n_frames, sic);
+}
 template <class S>
 static void launch_rx(cpx* out, const cpx* in, const cpx* eq, const cpx* table, const cpx* tw, const cpx* taps, int L,
                       int mode, int n_frames, int grid, cudaStream_t s)
@@ -593,6 +662,13 @@ struct ShapeEntry {
     const void* rx_fn;
     const void* sic_fn;
     const char* sic_name;
+    // chunk entries: modulator / transmitter chain with byte input, receiver with hard-decision output
+    tx_launch_t modc, txc;
+    sic_launch_t rxd;
+    const void* modc_fn;
+    const void* txc_fn;
+    const void* rxd_fn;
+    std::string modc_name, txc_name, rxd_name;
 };
 
 template <class S>
@@ -613,6 +689,15 @@ static ShapeEntry make_entry(const char* mn, const char* rn, const char* tn)
     e.sic = nullptr;
     e.sic_fn = nullptr;
     e.sic_name = "none";
+    e.modc = &launch_modc<S>;
+    e.txc = &launch_txc<S>;
+    e.rxd = &launch_rxd<S>;
+    e.modc_fn = (const void*)&fused_mod_kernel<S, false, true>;
+    e.txc_fn = (const void*)&fused_mod_kernel<S, true, true>;
+    e.rxd_fn = (const void*)&fused_rx_kernel<S, false, true>;
+    e.modc_name = std::string(mn) + "+chunks";
+    e.txc_name = std::string(tn) + "+chunks";
+    e.rxd_name = std::string(rn) + "+decide";
     if constexpr (S::IPT == 1) {
         e.sic = &launch_sic<S>;
         e.sic_fn = (const void*)&fused_rx_kernel<S, true>;
@@ -644,7 +729,7 @@ struct FusedImpl {
     cpx* d_table_eq = nullptr; // rx only: plain twiddle
     cpx* d_tw = nullptr;
     cpx* d_taps = nullptr;
-    int mod_grid_cap = 0, rx_grid_cap = 0, sic_grid_cap = 0, tx_grid_cap = 0;
+    int mod_grid_cap = 0, rx_grid_cap = 0, sic_grid_cap = 0, tx_grid_cap = 0, modc_grid_cap = 0, txc_grid_cap = 0, rxd_grid_cap = 0;
     // interference cancellation (advanced receiver)
     cpx* d_ic = nullptr;
     cpx* d_points = nullptr;
@@ -825,6 +910,90 @@ int FusedModem::transmit(cpx* out, const cpx* in, const TxArgs& tx, size_t frame
 }
 
 const char* FusedModem::tx_name() const { return impl_ && impl_->e ? impl_->e->tx_name : "none"; }
+
+// ---- chunk entries ---------------------------------------------------------------------------
+// The bulk copies move whole 16-byte units: a frame of chunks (N bytes) and a store slice (T*M bytes) must be
+// multiples of 16, which holds for every shape in the table; the constellation must fit the shared-memory slot.
+bool FusedModem::supports_chunks(int n_points) const
+{
+    if (!impl_ || !impl_->e) return false;
+    const ShapeEntry* e = impl_->e;
+    return n_points >= 1 && n_points <= GFDM_FUSED_MAX_POINTS && (e->M * e->K) % 16 == 0 && (e->T * e->M) % 16 == 0;
+}
+
+int FusedModem::modulate_chunks(cpx* out, const unsigned char* chunks, const cpx* d_points, int n_points, size_t frames,
+                                cudaStream_t s)
+{
+    const ShapeEntry* e = impl_->e;
+    if (!impl_->modc_grid_cap) impl_->modc_grid_cap = fused_grid_cap(e->modc_fn, e->T, e->smem);
+    TxArgs tx;
+    tx.points = d_points;
+    tx.n_points = n_points;
+    int launches = 0;
+    const size_t N = (size_t)e->M * e->K, max_chunk = (size_t)1 << 20;
+    for (size_t f0 = 0; f0 < frames; f0 += max_chunk) {
+        const int nf = (int)std::min(max_chunk, frames - f0);
+        const int groups = (nf + e->F - 1) / e->F;
+        const int grid = groups < impl_->modc_grid_cap ? groups : impl_->modc_grid_cap;
+        e->modc(out + f0 * N, reinterpret_cast<const cpx*>(chunks + f0 * N), impl_->d_table, impl_->d_tw, nf, grid, tx, s);
+        ++launches;
+    }
+    GFDM_CUDA_CHECK(cudaGetLastError());
+    return launches;
+}
+
+bool FusedModem::supports_tx_chain_chunks(const TxArgs& tx) const
+{
+    return impl_ && impl_->e && tx.n_in > 0 && tx.n_in % 16 == 0 && tx.n_ant >= 1 && tx.n_ant <= GFDM_TX_MAX_ANT &&
+           tx.n_points >= 1 && tx.n_points <= GFDM_FUSED_MAX_POINTS &&
+           (size_t)impl_->e->F * tx.n_in <= (size_t)impl_->e->F * impl_->e->M * impl_->e->K;
+}
+
+int FusedModem::transmit_chunks(cpx* out, const unsigned char* chunks, const TxArgs& tx, size_t frames, cudaStream_t s)
+{
+    const ShapeEntry* e = impl_->e;
+    if (!impl_->txc_grid_cap) impl_->txc_grid_cap = fused_grid_cap(e->txc_fn, e->T, e->smem);
+    int launches = 0;
+    const size_t os = (size_t)tx.P + (size_t)e->M * e->K + tx.cp + tx.cs;
+    const size_t max_chunk = (size_t)1 << 20;
+    for (size_t f0 = 0; f0 < frames; f0 += max_chunk) {
+        const int nf = (int)std::min(max_chunk, frames - f0);
+        const int groups = (nf + e->F - 1) / e->F;
+        const int grid = groups < impl_->txc_grid_cap ? groups : impl_->txc_grid_cap;
+        e->txc(out + f0 * os, reinterpret_cast<const cpx*>(chunks + f0 * (size_t)tx.n_in), impl_->d_table, impl_->d_tw, nf,
+               grid, tx, s);
+        ++launches;
+    }
+    GFDM_CUDA_CHECK(cudaGetLastError());
+    return launches;
+}
+
+int FusedModem::demodulate_decide(unsigned char* chunks_out, const cpx* in, const cpx* eq, const cpx* d_points, int n_points,
+                                  int rule, size_t frames, cudaStream_t s)
+{
+    const ShapeEntry* e = impl_->e;
+    if (!impl_->rxd_grid_cap) impl_->rxd_grid_cap = fused_grid_cap(e->rxd_fn, e->T, e->smem);
+    int launches = 0;
+    const size_t N = (size_t)e->M * e->K, max_chunk = (size_t)1 << 20;
+    SicArgs a{};
+    a.points = d_points;
+    a.n_points = n_points;
+    a.rule = rule;
+    for (size_t f0 = 0; f0 < frames; f0 += max_chunk) {
+        const int nf = (int)std::min(max_chunk, frames - f0);
+        const int groups = (nf + e->F - 1) / e->F;
+        const int grid = groups < impl_->rxd_grid_cap ? groups : impl_->rxd_grid_cap;
+        e->rxd(reinterpret_cast<cpx*>(chunks_out + f0 * N), in + f0 * N, eq ? eq + f0 * N : nullptr,
+               eq ? impl_->d_table_eq : impl_->d_table, impl_->d_tw, impl_->d_taps, impl_->L, nf, grid, a, s);
+        ++launches;
+    }
+    GFDM_CUDA_CHECK(cudaGetLastError());
+    return launches;
+}
+
+const char* FusedModem::modc_name() const { return impl_ && impl_->e ? impl_->e->modc_name.c_str() : "none"; }
+const char* FusedModem::txc_name() const { return impl_ && impl_->e ? impl_->e->txc_name.c_str() : "none"; }
+const char* FusedModem::rxd_name() const { return impl_ && impl_->e ? impl_->e->rxd_name.c_str() : "none"; }
 
 int FusedModem::demodulate(cpx* out_td, cpx* out_fd, const cpx* in, const cpx* eq, size_t frames, cudaStream_t s)
 {

@@ -1,0 +1,200 @@
+// next_kernels.cu -- the rows either side of the hot path as coalesced
+// gather kernels: burst extraction (lib/extract_burst_cc_impl.cc:117-242) fed by a descriptor array instead of
+// stream tags, and the byte-wide symbol mapping (python/pygfdm/symbolmapping.py:27-47, gr-digital's
+// chunks_to_symbols / constellation decoder).  remove_prefix_cc (lib/remove_prefix_cc_impl.cc:84-115) is the
+// strided copy of remove_cp_kernel (stage_kernels.cu) with cp = offset.
+// All of them are HBM-bound: one thread per (group of) output element(s), 128-bit accesses where the layout
+// allows, grid-stride loops sized to the SM count.
+#include "engine.h"
+
+namespace gfdm {
+
+static constexpr unsigned TH = 256;
+
+static unsigned grid_for(size_t items, unsigned threads)
+{
+    // enough CTAs to fill the device (148 SMs x 8 resident CTAs of 256 threads), grid-stride beyond that
+    const size_t want = (items + threads - 1) / threads;
+    const size_t cap = (size_t)148 * 8;
+    return (unsigned)(want < cap ? (want ? want : 1) : cap);
+}
+
+// ---------------------------------------------------------------------------------------------
+// extract_burst_cc: burst b, sample i:  out[b][i] = scale_b * in[start_b + i] * inc_b^i   (zeros where start_b + i < 0)
+// The rotation inc^i is evaluated directly (angle in double, one sincos per 4 samples, three complex products in
+// double), not by VOLK's recursive fp32 rotator: no drift, any sample can be computed independently.
+__global__ void __launch_bounds__(TH) extract_burst_kernel(cpx* __restrict__ out, const cpx* __restrict__ in,
+                                                           const BurstDesc* __restrict__ desc, int burst_len, int cfo,
+                                                           int n_bursts)
+{
+    const int quads = (burst_len + 3) / 4;
+    const size_t total = (size_t)n_bursts * quads;
+    for (size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x; gid < total; gid += (size_t)gridDim.x * blockDim.x) {
+        const int b = (int)(gid / quads);
+        const int i0 = (int)(gid - (size_t)b * quads) * 4;
+        const BurstDesc d = desc[b];
+        double pr = 1.0, pi = 0.0;
+        if (cfo) sincos(d.angle * (double)i0, &pi, &pr);
+        cpx* o = out + (size_t)b * burst_len;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int i = i0 + j;
+            if (i < burst_len) {
+                const long long src = d.start + i;
+                cpx v = cmake(0.f, 0.f);
+                if (src >= 0) {
+                    const cpx x = in[src];
+                    v = cmake(__fmul_rn(x.x, d.scale), __fmul_rn(x.y, d.scale)); // volk_32f_s32f_multiply_32f
+                    if (cfo) {
+                        const double re = (double)v.x * pr - (double)v.y * pi;
+                        const double im = (double)v.x * pi + (double)v.y * pr;
+                        v = cmake((float)re, (float)im);
+                    }
+                }
+                o[i] = v;
+            }
+            if (cfo) {
+                const double nr = pr * d.inc_re - pi * d.inc_im;
+                pi = pr * d.inc_im + pi * d.inc_re;
+                pr = nr;
+            }
+        }
+    }
+}
+void launch_extract_burst(cpx* out, const cpx* in, const BurstDesc* desc, int burst_len, bool cfo, int n_bursts,
+                          cudaStream_t s)
+{
+    if (n_bursts <= 0) return;
+    const size_t total = (size_t)n_bursts * ((burst_len + 3) / 4);
+    extract_burst_kernel<<<grid_for(total, TH), TH, 0, s>>>(out, in, desc, burst_len, cfo ? 1 : 0, n_bursts);
+    GFDM_CUDA_CHECK(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------------------------
+// symbol mapping.  The constellation (<= 256 points) sits in shared memory.
+__global__ void __launch_bounds__(TH) map_chunks_kernel(cpx* __restrict__ out, const unsigned char* __restrict__ chunks,
+                                                        const cpx* __restrict__ points, int n_points, size_t n)
+{
+    __shared__ cpx pts[256];
+    for (int i = threadIdx.x; i < 256; i += TH) pts[i] = i < n_points ? points[i] : cmake(0.f, 0.f);
+    __syncthreads();
+    // 4 symbols per thread where the chunk address allows a 32-bit load; the tail and unaligned heads go one by one
+    const size_t head = ((4 - (reinterpret_cast<uintptr_t>(chunks) & 3)) & 3);
+    const size_t h = head < n ? head : n;
+    const size_t quads = (n - h) / 4;
+    const size_t stride = (size_t)gridDim.x * blockDim.x, tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (size_t q = tid; q < quads; q += stride) {
+        const uint32_t w = *reinterpret_cast<const uint32_t*>(chunks + h + 4 * q);
+        cpx* o = out + h + 4 * q;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = pts[(w >> (8 * j)) & 255u];
+    }
+    for (size_t i = tid; i < h; i += stride) out[i] = pts[chunks[i]];
+    for (size_t i = h + 4 * quads + tid; i < n; i += stride) out[i] = pts[chunks[i]];
+}
+void launch_map_chunks(cpx* out, const unsigned char* chunks, const cpx* points, int n_points, size_t n, cudaStream_t s)
+{
+    if (!n) return;
+    map_chunks_kernel<<<grid_for((n + 3) / 4, TH), TH, 0, s>>>(out, chunks, points, n_points, n);
+    GFDM_CUDA_CHECK(cudaGetLastError());
+}
+
+__global__ void __launch_bounds__(TH) decide_chunks_kernel(unsigned char* __restrict__ chunks, const cpx* __restrict__ in,
+                                                           const cpx* __restrict__ points, int n_points, int rule, size_t n)
+{
+    __shared__ cpx pts[256];
+    for (int i = threadIdx.x; i < 256; i += TH) pts[i] = i < n_points ? points[i] : cmake(0.f, 0.f);
+    __syncthreads();
+    const size_t head = ((4 - (reinterpret_cast<uintptr_t>(chunks) & 3)) & 3);
+    const size_t h = head < n ? head : n;
+    const size_t quads = (n - h) / 4;
+    const size_t stride = (size_t)gridDim.x * blockDim.x, tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (size_t q = tid; q < quads; q += stride) {
+        const cpx* x = in + h + 4 * q;
+        uint32_t w = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) w |= (uint32_t)decide_symbol(x[j], pts, n_points, rule) << (8 * j);
+        *reinterpret_cast<uint32_t*>(chunks + h + 4 * q) = w;
+    }
+    for (size_t i = tid; i < h; i += stride) chunks[i] = (unsigned char)decide_symbol(in[i], pts, n_points, rule);
+    for (size_t i = h + 4 * quads + tid; i < n; i += stride) chunks[i] = (unsigned char)decide_symbol(in[i], pts, n_points, rule);
+}
+void launch_decide_chunks(unsigned char* chunks, const cpx* in, const cpx* points, int n_points, int rule, size_t n,
+                          cudaStream_t s)
+{
+    if (!n) return;
+    decide_chunks_kernel<<<grid_for((n + 3) / 4, TH), TH, 0, s>>>(chunks, in, points, n_points, rule, n);
+    GFDM_CUDA_CHECK(cudaGetLastError());
+}
+
+// pack_bits (MSB first) + constellation lookup: one thread per symbol
+__global__ void __launch_bounds__(TH) bits2symbols_kernel(cpx* __restrict__ out, const unsigned char* __restrict__ bits,
+                                                          const cpx* __restrict__ points, int n_points, int bps, size_t n)
+{
+    __shared__ cpx pts[256];
+    for (int i = threadIdx.x; i < 256; i += TH) pts[i] = i < n_points ? points[i] : cmake(0.f, 0.f);
+    __syncthreads();
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        int v = 0;
+        for (int b = 0; b < bps; ++b) v = (v << 1) | (bits[i * bps + b] & 1);
+        out[i] = pts[v];
+    }
+}
+void launch_bits2symbols(cpx* out, const unsigned char* bits, const cpx* points, int n_points, int bps, size_t n,
+                         cudaStream_t s)
+{
+    if (!n) return;
+    bits2symbols_kernel<<<grid_for(n, TH), TH, 0, s>>>(out, bits, points, n_points, bps, n);
+    GFDM_CUDA_CHECK(cudaGetLastError());
+}
+
+// decision + unpackbits (MSB first): one thread per symbol
+__global__ void __launch_bounds__(TH) symbols2bits_kernel(unsigned char* __restrict__ bits, const cpx* __restrict__ in,
+                                                          const cpx* __restrict__ points, int n_points, int rule, int bps,
+                                                          size_t n)
+{
+    __shared__ cpx pts[256];
+    for (int i = threadIdx.x; i < 256; i += TH) pts[i] = i < n_points ? points[i] : cmake(0.f, 0.f);
+    __syncthreads();
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int v = decide_symbol(in[i], pts, n_points, rule);
+        for (int b = 0; b < bps; ++b) bits[i * bps + b] = (unsigned char)((v >> (bps - 1 - b)) & 1);
+    }
+}
+void launch_symbols2bits(unsigned char* bits, const cpx* in, const cpx* points, int n_points, int rule, int bps, size_t n,
+                         cudaStream_t s)
+{
+    if (!n) return;
+    symbols2bits_kernel<<<grid_for(n, TH), TH, 0, s>>>(bits, in, points, n_points, rule, bps, n);
+    GFDM_CUDA_CHECK(cudaGetLastError());
+}
+
+// demap_from_resources (lib/resource_mapper_kernel_cc.cc:136-162) on a grid of chunks
+__global__ void __launch_bounds__(TH) demap_chunks_kernel(unsigned char* __restrict__ out, const unsigned char* __restrict__ in,
+                                                          const int* __restrict__ smap, int M, int K, int A, int per_timeslot,
+                                                          size_t n_out, size_t total)
+{
+    for (size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x; gid < total; gid += (size_t)gridDim.x * blockDim.x) {
+        const size_t f = gid / n_out;
+        const size_t i = gid - f * n_out;
+        int a, t;
+        if (per_timeslot) {
+            t = (int)(i / A);
+            a = (int)(i - (size_t)t * A);
+        } else {
+            a = (int)(i / M);
+            t = (int)(i - (size_t)a * M);
+        }
+        out[gid] = in[f * (size_t)M * K + (size_t)M * smap[a] + t];
+    }
+}
+void launch_demap_chunks(unsigned char* out, const unsigned char* in, const int* smap, int M, int K, int A, bool per_timeslot,
+                         size_t n_out, size_t frames, cudaStream_t s)
+{
+    const size_t total = frames * n_out;
+    if (!total) return;
+    demap_chunks_kernel<<<grid_for(total, TH), TH, 0, s>>>(out, in, smap, M, K, A, per_timeslot ? 1 : 0, n_out, total);
+    GFDM_CUDA_CHECK(cudaGetLastError());
+}
+
+} // namespace gfdm

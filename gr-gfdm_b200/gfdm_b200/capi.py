@@ -39,6 +39,10 @@ def _c64(a):
     return np.ascontiguousarray(a, dtype=np.complex64)
 
 
+def _u8(a):
+    return np.ascontiguousarray(a, dtype=np.uint8)
+
+
 def _ptr(a):
     return a.ctypes.data_as(c_void_p)
 
@@ -145,6 +149,29 @@ class Library(object):
         'gfdm_transmitter_work_batch': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int]),
         'gfdm_transmitter_work_all_batch': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int]),
         'gfdm_transmitter_set_chain_fusion': (c_int, [c_void_p, c_int]),
+        # rows either side of the path
+        'gfdm_remove_prefix_create': (c_int, [POINTER(c_void_p), c_int, c_int, c_int]),
+        'gfdm_remove_prefix_destroy': (None, [c_void_p]),
+        'gfdm_remove_prefix_work_batch': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int]),
+        'gfdm_extract_burst_create': (c_int, [POINTER(c_void_p), c_int, c_int, c_int]),
+        'gfdm_extract_burst_destroy': (None, [c_void_p]),
+        'gfdm_extract_burst_activate_cfo_compensation': (c_int, [c_void_p, c_int]),
+        'gfdm_extract_burst_work': (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_longlong, c_void_p, c_void_p,
+                                            c_void_p, c_int, POINTER(c_int), POINTER(c_longlong), c_int]),
+        'gfdm_symbol_mapper_create': (c_int, [POINTER(c_void_p), POINTER(_Constellation)]),
+        'gfdm_symbol_mapper_destroy': (None, [c_void_p]),
+        'gfdm_symbol_mapper_n_points': (c_int, [c_void_p]),
+        'gfdm_symbol_mapper_bits_per_symbol': (c_int, [c_void_p]),
+        'gfdm_symbol_mapper_points': (c_int, [c_void_p, c_void_p]),
+        'gfdm_symbol_mapper_decision_rule': (c_int, [c_void_p]),
+        'gfdm_symbol_mapper_map_chunks_batch': (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_int]),
+        'gfdm_symbol_mapper_decide_batch': (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_int]),
+        'gfdm_symbol_mapper_bits2symbols_batch': (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_int]),
+        'gfdm_symbol_mapper_symbols2bits_batch': (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_int]),
+        'gfdm_modulator_work_chunks_batch': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int]),
+        'gfdm_transmitter_work_chunks_batch': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int]),
+        'gfdm_receiver_work_decide_batch': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int]),
+        'gfdm_resource_mapper_demap_chunks_batch': (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int]),
     }
 
     def __init__(self, path):
@@ -315,6 +342,23 @@ class Modulator(_Handle):
         self._ck(self._dll.gfdm_modulator_work_batch(self._h, c_void_p(out_ptr), c_void_p(in_ptr),
                                                      n_frames, MEM_DEVICE))
 
+    def modulate_chunks_batch(self, symbol_mapper, chunks):
+        """chunks[n_frames, block_size] uint8 (constellation point indices) -> time samples."""
+        c = _u8(chunks)
+        self._two_dim(c, self.block_size())
+        out = np.empty(c.shape, np.complex64)
+        self._ck(self._dll.gfdm_modulator_work_chunks_batch(self._h, symbol_mapper._h, _ptr(out), _ptr(c),
+                                                            c.shape[0], MEM_HOST))
+        return out
+
+    def modulate_chunks_batch_host_ptr(self, symbol_mapper, out_ptr, chunks_ptr, n_frames):
+        self._ck(self._dll.gfdm_modulator_work_chunks_batch(self._h, symbol_mapper._h, c_void_p(out_ptr),
+                                                            c_void_p(chunks_ptr), n_frames, MEM_HOST))
+
+    def modulate_chunks_ptr(self, symbol_mapper, out_ptr, chunks_ptr, n_frames):
+        self._ck(self._dll.gfdm_modulator_work_chunks_batch(self._h, symbol_mapper._h, c_void_p(out_ptr),
+                                                            c_void_p(chunks_ptr), n_frames, MEM_DEVICE))
+
 
 class Demodulator(_Handle):
     """receiver_kernel_cc / gfdm_python.Demodulator (python/bindings/demodulator_python.cc:35-205)."""
@@ -431,6 +475,30 @@ class Demodulator(_Handle):
         self._ck(self._dll.gfdm_receiver_work_batch(self._h, c_void_p(out_ptr), c_void_p(in_ptr),
                                                     c_void_p(eq_ptr) if eq_ptr else None,
                                                     n_frames, MEM_HOST))
+
+    def demodulate_decide_batch(self, symbol_mapper, array, eq_arr=None):
+        """time samples [n_frames, block_size] -> hard decisions (uint8 point indices) on the full grid."""
+        a = _c64(array)
+        self._two_dim(a, self.block_size())
+        eq = None
+        if eq_arr is not None:
+            eq = _c64(eq_arr)
+            self._two_dim(eq, self.block_size())
+        out = np.empty(a.shape, np.uint8)
+        self._ck(self._dll.gfdm_receiver_work_decide_batch(self._h, symbol_mapper._h, _ptr(out), _ptr(a),
+                                                           _ptr(eq) if eq is not None else None,
+                                                           a.shape[0], MEM_HOST))
+        return out
+
+    def demodulate_decide_batch_host_ptr(self, symbol_mapper, out_ptr, in_ptr, eq_ptr, n_frames):
+        self._ck(self._dll.gfdm_receiver_work_decide_batch(self._h, symbol_mapper._h, c_void_p(out_ptr),
+                                                           c_void_p(in_ptr), c_void_p(eq_ptr) if eq_ptr else None,
+                                                           n_frames, MEM_HOST))
+
+    def demodulate_decide_ptr(self, symbol_mapper, out_ptr, in_ptr, eq_ptr, n_frames):
+        self._ck(self._dll.gfdm_receiver_work_decide_batch(self._h, symbol_mapper._h, c_void_p(out_ptr),
+                                                           c_void_p(in_ptr), c_void_p(eq_ptr) if eq_ptr else None,
+                                                           n_frames, MEM_DEVICE))
 
     def demodulate_ptr(self, out_ptr, in_ptr, eq_ptr, n_frames):
         self._ck(self._dll.gfdm_receiver_work_batch(self._h, c_void_p(out_ptr), c_void_p(in_ptr),
@@ -582,6 +650,20 @@ class Resource_mapper(_Handle):
         self._ck(self._dll.gfdm_resource_mapper_demap_from_resources_batch(
             self._h, _ptr(out), _ptr(a), n, a.shape[0], MEM_HOST))
         return out
+
+    def demap_chunks_batch(self, chunks, size_per_frame=None):
+        """demap_from_resources on a grid of uint8 chunks [n_frames, frame_size]."""
+        c = _u8(chunks)
+        self._two_dim(c, self.frame_size())
+        n = self.block_size() if size_per_frame is None else size_per_frame
+        out = np.empty((c.shape[0], n), np.uint8)
+        self._ck(self._dll.gfdm_resource_mapper_demap_chunks_batch(self._h, _ptr(out), _ptr(c), n, c.shape[0],
+                                                                   MEM_HOST))
+        return out
+
+    def demap_chunks_ptr(self, out_ptr, in_ptr, size_per_frame, n_frames):
+        self._ck(self._dll.gfdm_resource_mapper_demap_chunks_batch(
+            self._h, c_void_p(out_ptr), c_void_p(in_ptr), size_per_frame, n_frames, MEM_DEVICE))
 
     def map_ptr(self, out_ptr, in_ptr, size_per_frame, n_frames):
         self._ck(self._dll.gfdm_resource_mapper_map_to_resources_batch(
@@ -848,6 +930,148 @@ class Transmitter(_Handle):
                                                            a.shape[0], MEM_HOST))
         return out
 
+    def work_chunks_batch(self, symbol_mapper, chunks):
+        """chunks[n_frames, ninput_size] uint8 -> frames of cyclic_shifts[0]."""
+        c = _u8(chunks)
+        if c.ndim != 2:
+            raise RuntimeError('batch arrays MUST be two-dimensional')
+        out = np.empty((c.shape[0], self.output_vector_size()), np.complex64)
+        self._ck(self._dll.gfdm_transmitter_work_chunks_batch(self._h, symbol_mapper._h, _ptr(out), _ptr(c),
+                                                              c.shape[1], c.shape[0], MEM_HOST))
+        return out
+
+    def work_chunks_ptr(self, symbol_mapper, out_ptr, chunks_ptr, ninput_size, n_frames):
+        self._ck(self._dll.gfdm_transmitter_work_chunks_batch(self._h, symbol_mapper._h, c_void_p(out_ptr),
+                                                              c_void_p(chunks_ptr), ninput_size, n_frames, MEM_DEVICE))
+
     def work_ptr(self, out_ptr, in_ptr, ninput_size, n_frames, all_antennas=False):
         fn = self._dll.gfdm_transmitter_work_all_batch if all_antennas else self._dll.gfdm_transmitter_work_batch
         self._ck(fn(self._h, c_void_p(out_ptr), c_void_p(in_ptr), ninput_size, n_frames, MEM_DEVICE))
+
+
+class Remove_prefix(_Handle):
+    """remove_prefix_cc (lib/remove_prefix_cc_impl.cc:84-115) as a batched gather."""
+    _destroy = 'gfdm_remove_prefix_destroy'
+
+    def __init__(self, frame_len, block_len, offset, lib=None):
+        _Handle.__init__(self, lib)
+        self.frame_len, self.block_len, self.offset = frame_len, block_len, offset
+        self._ck(self._dll.gfdm_remove_prefix_create(byref(self._h), frame_len, block_len, offset))
+
+    def work_batch(self, array):
+        a = _c64(array)
+        self._two_dim(a, self.frame_len)
+        out = np.empty((a.shape[0], self.block_len), np.complex64)
+        self._ck(self._dll.gfdm_remove_prefix_work_batch(self._h, _ptr(out), _ptr(a), a.shape[0], MEM_HOST))
+        return out
+
+    def work_ptr(self, out_ptr, in_ptr, n_frames):
+        self._ck(self._dll.gfdm_remove_prefix_work_batch(self._h, c_void_p(out_ptr), c_void_p(in_ptr), n_frames,
+                                                         MEM_DEVICE))
+
+
+class Extract_burst(_Handle):
+    """extract_burst_cc (lib/extract_burst_cc_impl.cc:117-242): one general_work() call per ``work``."""
+    _destroy = 'gfdm_extract_burst_destroy'
+
+    def __init__(self, burst_len, tag_backoff, activate_cfo_correction=False, lib=None):
+        _Handle.__init__(self, lib)
+        self.burst_len = burst_len
+        self._ck(self._dll.gfdm_extract_burst_create(byref(self._h), burst_len, tag_backoff,
+                                                     int(bool(activate_cfo_correction))))
+
+    def activate_cfo_compensation(self, on):
+        self._ck(self._dll.gfdm_extract_burst_activate_cfo_compensation(self._h, int(bool(on))))
+
+    def _tags(self, burst_starts, scale_factors, phase_rotations):
+        st = np.ascontiguousarray(burst_starts, dtype=np.int64)
+        sc = None if scale_factors is None else np.ascontiguousarray(scale_factors, dtype=np.float32)
+        pr = None if phase_rotations is None else _c64(phase_rotations)
+        for x in (sc, pr):
+            if x is not None and x.size != st.size:
+                raise RuntimeError('tag arrays MUST have the same length')
+        return st, sc, pr
+
+    def work(self, stream, burst_starts, scale_factors=None, phase_rotations=None, max_bursts=None):
+        """Returns (bursts[n_produced, burst_len], n_consumed)."""
+        x = _c64(stream).ravel()
+        st, sc, pr = self._tags(burst_starts, scale_factors, phase_rotations)
+        mb = st.size if max_bursts is None else max_bursts
+        out = np.empty((max(mb, 1), self.burst_len), np.complex64)
+        n_prod, n_cons = c_int(), c_longlong()
+        self._ck(self._dll.gfdm_extract_burst_work(
+            self._h, _ptr(out), mb, _ptr(x), x.size, _ptr(st), _ptr(sc) if sc is not None else None,
+            _ptr(pr) if pr is not None else None, st.size, byref(n_prod), byref(n_cons), MEM_HOST))
+        return out[:n_prod.value].copy(), n_cons.value
+
+    def work_ptr(self, out_ptr, max_bursts, in_ptr, n_in, burst_starts, scale_factors=None, phase_rotations=None):
+        st, sc, pr = self._tags(burst_starts, scale_factors, phase_rotations)
+        n_prod, n_cons = c_int(), c_longlong()
+        self._ck(self._dll.gfdm_extract_burst_work(
+            self._h, c_void_p(out_ptr), max_bursts, c_void_p(in_ptr), n_in, _ptr(st),
+            _ptr(sc) if sc is not None else None, _ptr(pr) if pr is not None else None, st.size,
+            byref(n_prod), byref(n_cons), MEM_DEVICE))
+        return n_prod.value, n_cons.value
+
+
+class Symbol_mapper(_Handle):
+    """Symbol mapping either side of the path: pygfdm bits2symbols / symbols2bits
+    (python/pygfdm/symbolmapping.py:27-47) and the chunk <-> point mapping of gr-digital's
+    chunks_to_symbols / constellation decoder.  ``constellation`` is ``(points, decision_rule)``."""
+    _destroy = 'gfdm_symbol_mapper_destroy'
+
+    def __init__(self, constellation=None, lib=None):
+        _Handle.__init__(self, lib)
+        pts, rule = constellation if constellation is not None else qpsk_constellation()
+        pts = _c64(pts)
+        c = _Constellation(pts.ctypes.data, pts.size, int(rule))
+        self._ck(self._dll.gfdm_symbol_mapper_create(byref(self._h), byref(c)))
+
+    def n_points(self):
+        return self._dll.gfdm_symbol_mapper_n_points(self._h)
+
+    def bits_per_symbol(self):
+        return self._dll.gfdm_symbol_mapper_bits_per_symbol(self._h)
+
+    def decision_rule(self):
+        return self._dll.gfdm_symbol_mapper_decision_rule(self._h)
+
+    def points(self):
+        out = np.empty(self.n_points(), np.complex64)
+        self._ck(self._dll.gfdm_symbol_mapper_points(self._h, _ptr(out)))
+        return out
+
+    def map_chunks(self, chunks):
+        c = _u8(chunks)
+        out = np.empty(c.shape, np.complex64)
+        self._ck(self._dll.gfdm_symbol_mapper_map_chunks_batch(self._h, _ptr(out), _ptr(c), c.size, MEM_HOST))
+        return out
+
+    def decide(self, symbols):
+        a = _c64(symbols)
+        out = np.empty(a.shape, np.uint8)
+        self._ck(self._dll.gfdm_symbol_mapper_decide_batch(self._h, _ptr(out), _ptr(a), a.size, MEM_HOST))
+        return out
+
+    def bits2symbols(self, bits):
+        b = _u8(bits).ravel()
+        bps = max(self.bits_per_symbol(), 1)
+        if b.size % bps:
+            raise RuntimeError('number of bits MUST be a multiple of bits_per_symbol(%d)' % bps)
+        out = np.empty(b.size // bps, np.complex64)
+        self._ck(self._dll.gfdm_symbol_mapper_bits2symbols_batch(self._h, _ptr(out), _ptr(b), out.size, MEM_HOST))
+        return out
+
+    def symbols2bits(self, symbols):
+        a = _c64(symbols).ravel()
+        out = np.empty(a.size * max(self.bits_per_symbol(), 1), np.uint8)
+        self._ck(self._dll.gfdm_symbol_mapper_symbols2bits_batch(self._h, _ptr(out), _ptr(a), a.size, MEM_HOST))
+        return out
+
+    def map_chunks_ptr(self, out_ptr, chunks_ptr, n):
+        self._ck(self._dll.gfdm_symbol_mapper_map_chunks_batch(self._h, c_void_p(out_ptr), c_void_p(chunks_ptr), n,
+                                                               MEM_DEVICE))
+
+    def decide_ptr(self, out_ptr, in_ptr, n):
+        self._ck(self._dll.gfdm_symbol_mapper_decide_batch(self._h, c_void_p(out_ptr), c_void_p(in_ptr), n,
+                                                           MEM_DEVICE))

@@ -312,6 +312,87 @@ GFDM_B200_API int gfdm_transmitter_work_all_batch(gfdm_transmitter* h, gfdm_comp
  * kernels (used by the parity tests: both forms must agree bit for bit).  No-op on the CPU oracles. */
 GFDM_B200_API int gfdm_transmitter_set_chain_fusion(gfdm_transmitter* h, int on);
 
+/* ======================================================================== */
+/* The rows either side of the hot path.  The reference implements
+ * them as GNU Radio blocks / stock gr-digital blocks / pygfdm helpers; here they are batched kernels fed by
+ * plain arrays instead of stream tags.                                                                  */
+
+/* ---- remove_prefix_cc -- lib/remove_prefix_cc_impl.cc:84-115 ------------
+ * out[f][0:block_len] = in[f][offset : offset+block_len], frames of frame_len samples
+ * (constructor: include/gfdm/remove_prefix_cc.h, make(frame_len, block_len, offset, ...)). */
+typedef struct gfdm_remove_prefix gfdm_remove_prefix;
+GFDM_B200_API int gfdm_remove_prefix_create(gfdm_remove_prefix** out, int frame_len, int block_len,
+                                            int offset);
+GFDM_B200_API void gfdm_remove_prefix_destroy(gfdm_remove_prefix* h);
+GFDM_B200_API int gfdm_remove_prefix_work_batch(gfdm_remove_prefix* h, gfdm_complex* out,
+                                                const gfdm_complex* in, int n_frames, int mem);
+
+/* ---- extract_burst_cc -- lib/extract_burst_cc_impl.cc:43-242 ------------
+ * One general_work() call (:117-242) over a window of `n_in` stream samples.  The stream tags become
+ * parallel HOST arrays sorted by offset (the reference sorts them, :131): burst_starts[i] = tag offset
+ * relative to in[0]; scale_factors[i] = the tag's "scale_factor" (NULL: 1.0, :78-86);
+ * phase_rotations[i] = the tag's "phase_rotation" (NULL: 1+0j, :88-96).  For every tag, in order:
+ *   actual_start = burst_start - tag_backoff;
+ *   if (n_in - burst_start >= burst_len && produced + burst_len <= max_bursts*burst_len)
+ *        out burst = scale * in[actual_start : actual_start+burst_len]   (negative start: zeros in front
+ *        and the burst is cut short, :196-205); with CFO correction on, sample i of the burst is rotated
+ *        by inc^i, inc = conj(phase_rotation)/|phase_rotation| (:88-96,107-115);
+ *        consumed = burst_start + burst_len;
+ *   else consumed = max(0, burst_start) and the loop stops (:224-238).
+ * n_produced = bursts written to out[n_produced][burst_len]; n_consumed = items the block would consume
+ * (n_in when every tag was served).  `mem` applies to in/out only.                                     */
+typedef struct gfdm_extract_burst gfdm_extract_burst;
+GFDM_B200_API int gfdm_extract_burst_create(gfdm_extract_burst** out, int burst_len, int tag_backoff,
+                                            int activate_cfo_correction);
+GFDM_B200_API void gfdm_extract_burst_destroy(gfdm_extract_burst* h);
+GFDM_B200_API int gfdm_extract_burst_activate_cfo_compensation(gfdm_extract_burst* h, int on); /* :98-105 */
+GFDM_B200_API int gfdm_extract_burst_work(gfdm_extract_burst* h, gfdm_complex* out, int max_bursts,
+                                          const gfdm_complex* in, long long n_in,
+                                          const long long* burst_starts, const float* scale_factors,
+                                          const gfdm_complex* phase_rotations, int n_tags,
+                                          int* n_produced, long long* n_consumed, int mem);
+
+/* ---- symbol mapping -- python/pygfdm/symbolmapping.py:27-47, python/pygfdm/utils.py:47-51,
+ *      gr::digital chunks_to_symbols_bc / constellation decoder as used by
+ *      python/qa_advanced_receiver_sb_cc.py:97-99 ---------------------------------------------------
+ * chunk = index of a constellation point (one unsigned char per symbol); bits = one unsigned char (0/1)
+ * per bit, MSB first, log2(n_points) bits per symbol (pack_bits :27-31, unpackbits :44).
+ * map: out = points[chunk] (chunk >= n_points gives 0+0j); decide: the constellation's decision rule. */
+typedef struct gfdm_symbol_mapper gfdm_symbol_mapper;
+GFDM_B200_API int gfdm_symbol_mapper_create(gfdm_symbol_mapper** out, const gfdm_constellation* constellation);
+GFDM_B200_API void gfdm_symbol_mapper_destroy(gfdm_symbol_mapper* h);
+GFDM_B200_API int gfdm_symbol_mapper_n_points(const gfdm_symbol_mapper* h);
+GFDM_B200_API int gfdm_symbol_mapper_bits_per_symbol(const gfdm_symbol_mapper* h); /* 0 unless n_points = 2^b */
+GFDM_B200_API int gfdm_symbol_mapper_points(const gfdm_symbol_mapper* h, gfdm_complex* points_out);
+GFDM_B200_API int gfdm_symbol_mapper_decision_rule(const gfdm_symbol_mapper* h);
+GFDM_B200_API int gfdm_symbol_mapper_map_chunks_batch(gfdm_symbol_mapper* h, gfdm_complex* out,
+                                                      const unsigned char* chunks, size_t n_symbols, int mem);
+GFDM_B200_API int gfdm_symbol_mapper_decide_batch(gfdm_symbol_mapper* h, unsigned char* chunks_out,
+                                                  const gfdm_complex* in, size_t n_symbols, int mem);
+GFDM_B200_API int gfdm_symbol_mapper_bits2symbols_batch(gfdm_symbol_mapper* h, gfdm_complex* out,
+                                                        const unsigned char* bits, size_t n_symbols, int mem);
+GFDM_B200_API int gfdm_symbol_mapper_symbols2bits_batch(gfdm_symbol_mapper* h, unsigned char* bits_out,
+                                                        const gfdm_complex* in, size_t n_symbols, int mem);
+
+/* The same mapping fused into the kernels of the path, so that the symbol side of a frame crosses HBM
+ * (and PCIe) as one byte per symbol instead of eight:
+ *   modulator   <- chunks[n_frames][block_size]                       (8N+N instead of 16N bytes per frame)
+ *   transmitter <- chunks[n_frames][ninput_size] (compact, as map_to_resources takes them)
+ *   receiver    -> chunks[n_frames][block_size]  = decide(generic_work[_equalize] output), full grid
+ *   demapper    on chunk grids (demap_from_resources on bytes) completes the receive chain.        */
+GFDM_B200_API int gfdm_modulator_work_chunks_batch(gfdm_modulator* h, const gfdm_symbol_mapper* sm,
+                                                   gfdm_complex* out, const unsigned char* chunks,
+                                                   int n_frames, int mem);
+GFDM_B200_API int gfdm_transmitter_work_chunks_batch(gfdm_transmitter* h, const gfdm_symbol_mapper* sm,
+                                                     gfdm_complex* out, const unsigned char* chunks,
+                                                     int ninput_size, int n_frames, int mem);
+GFDM_B200_API int gfdm_receiver_work_decide_batch(gfdm_receiver* h, const gfdm_symbol_mapper* sm,
+                                                  unsigned char* chunks_out, const gfdm_complex* in,
+                                                  const gfdm_complex* f_eq_in, int n_frames, int mem);
+GFDM_B200_API int gfdm_resource_mapper_demap_chunks_batch(gfdm_resource_mapper* h, unsigned char* out,
+                                                          const unsigned char* in, size_t size_per_frame,
+                                                          int n_frames, int mem);
+
 #ifdef __cplusplus
 }
 #endif

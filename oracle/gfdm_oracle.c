@@ -137,6 +137,8 @@ static void normalize_taps(cf* dst, const cf* src, int n, int n_timeslots)
 
 /* ======================================================================== */
 const char* gfdm_last_error(void) { return g_err; }
+/* used by gfdm_oracle_next.c (linked into this library) */
+void gfdm_oracle_set_error(const char* msg) { snprintf(g_err, sizeof(g_err), "%s", msg); }
 const char* gfdm_backend(void) { return "oracle-port"; }
 int gfdm_device_count(void) { return 0; }
 int gfdm_set_device(int device) { (void)device; return GFDM_OK; }

@@ -81,6 +81,8 @@ struct gfdm_fft {
 extern "C" {
 
 const char* gfdm_last_error(void) { return g_err.c_str(); }
+/* used by gfdm_oracle_next.c (linked into this library) */
+void gfdm_oracle_set_error(const char* msg) { g_err = msg; }
 const char* gfdm_backend(void) { return "oracle-ref"; }
 int gfdm_device_count(void) { return 0; }
 int gfdm_set_device(int) { return GFDM_OK; }
