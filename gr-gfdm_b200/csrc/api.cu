@@ -1589,6 +1589,7 @@ struct gfdm_symbol_mapper : HandleBase {
     std::vector<cf> points;
     int rule = 0, bits = 0;
     cpx* d_points = nullptr;
+    DecideGrid grid; // O(1) decisions when the constellation is a uniform rectangular grid
 };
 int gfdm_symbol_mapper_create(gfdm_symbol_mapper** out, const gfdm_constellation* c)
 {
@@ -1602,6 +1603,11 @@ int gfdm_symbol_mapper_create(gfdm_symbol_mapper** out, const gfdm_constellation
     h->rule = c->decision_rule;
     for (int b = 0; b <= 8; ++b)
         if ((1 << b) == c->n_points) h->bits = b;
+    {
+        std::vector<cpx> p(h->points.size());
+        for (size_t i = 0; i < p.size(); ++i) p[i] = make_float2(h->points[i].real(), h->points[i].imag());
+        h->grid = make_decide_grid(p);
+    }
     h->open();
     h->d_points = dev_upload(h->points);
     *out = h.release();
@@ -1668,7 +1674,7 @@ int gfdm_symbol_mapper_decide_batch(gfdm_symbol_mapper* h, unsigned char* chunks
     h->use();
     symbol_batch(h, chunks, 1, in, sizeof(cpx), n, mem, [&](void* o, const void* i, size_t ni) {
         launch_decide_chunks(static_cast<unsigned char*>(o), static_cast<const cpx*>(i), h->d_points, (int)h->points.size(),
-                             h->rule, ni, h->stream);
+                             h->rule, h->grid, ni, h->stream);
         h->launches += ni ? 1 : 0;
         h->last_kernel = "decide_chunks_kernel";
     });
@@ -1696,7 +1702,7 @@ int gfdm_symbol_mapper_symbols2bits_batch(gfdm_symbol_mapper* h, unsigned char* 
     if (h->bits < 1) throw std::invalid_argument("symbols2bits: the constellation size MUST be a power of two >= 2!");
     symbol_batch(h, bits, (size_t)h->bits, in, sizeof(cpx), n, mem, [&](void* o, const void* i, size_t ni) {
         launch_symbols2bits(static_cast<unsigned char*>(o), static_cast<const cpx*>(i), h->d_points, (int)h->points.size(),
-                            h->rule, h->bits, ni, h->stream);
+                            h->rule, h->bits, h->grid, ni, h->stream);
         h->launches += ni ? 1 : 0;
         h->last_kernel = "symbols2bits_kernel";
     });
@@ -1754,14 +1760,14 @@ static void receiver_run_decide(gfdm_receiver* h, const gfdm_symbol_mapper* sm, 
     const int np = (int)sm->points.size();
     if (h->fused.available() && (!eq || h->fused.supports_eq()) && h->fused.supports_chunks(np) && aligned16(in) &&
         aligned16(chunks_out) && (!eq || aligned16(eq))) {
-        h->launches += h->fused.demodulate_decide(chunks_out, in, eq, sm->d_points, np, sm->rule, frames, h->stream);
+        h->launches += h->fused.demodulate_decide(chunks_out, in, eq, sm->d_points, np, sm->rule, sm->grid, frames, h->stream);
         h->last_kernel = h->fused.rxd_name();
         return;
     }
     const size_t el = frames * (size_t)h->N;
     h->work_c.ensure(el * sizeof(cpx));
     receiver_run(h, h->work_c.as<cpx>(), in, eq, frames);
-    launch_decide_chunks(chunks_out, h->work_c.as<cpx>(), sm->d_points, np, sm->rule, el, h->stream);
+    launch_decide_chunks(chunks_out, h->work_c.as<cpx>(), sm->d_points, np, sm->rule, sm->grid, el, h->stream);
     h->launches += 1;
 }
 int gfdm_receiver_work_decide_batch(gfdm_receiver* h, const gfdm_symbol_mapper* sm, unsigned char* chunks_out,

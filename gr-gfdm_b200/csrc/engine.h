@@ -60,12 +60,12 @@ void launch_extract_burst(cpx* out, const cpx* in, const BurstDesc* desc, int bu
                           cudaStream_t s);
 // symbol mapping (python/pygfdm/symbolmapping.py:27-47): chunk = constellation point index, one byte per symbol
 void launch_map_chunks(cpx* out, const unsigned char* chunks, const cpx* points, int n_points, size_t n, cudaStream_t s);
-void launch_decide_chunks(unsigned char* chunks, const cpx* in, const cpx* points, int n_points, int rule, size_t n,
-                          cudaStream_t s);
+void launch_decide_chunks(unsigned char* chunks, const cpx* in, const cpx* points, int n_points, int rule,
+                          const DecideGrid& grid, size_t n, cudaStream_t s);
 void launch_bits2symbols(cpx* out, const unsigned char* bits, const cpx* points, int n_points, int bps, size_t n,
                          cudaStream_t s);
-void launch_symbols2bits(unsigned char* bits, const cpx* in, const cpx* points, int n_points, int rule, int bps, size_t n,
-                         cudaStream_t s);
+void launch_symbols2bits(unsigned char* bits, const cpx* in, const cpx* points, int n_points, int rule, int bps,
+                         const DecideGrid& grid, size_t n, cudaStream_t s);
 void launch_demap_chunks(unsigned char* out, const unsigned char* in, const int* smap, int M, int K, int A, bool per_timeslot,
                          size_t n_out, size_t frames, cudaStream_t s);
 

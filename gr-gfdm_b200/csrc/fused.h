@@ -74,7 +74,7 @@ public:
     bool supports_tx_chain_chunks(const TxArgs& tx) const;
     int transmit_chunks(cpx* out, const unsigned char* chunks, const TxArgs& tx, size_t frames, cudaStream_t s);
     int demodulate_decide(unsigned char* chunks_out, const cpx* in, const cpx* eq, const cpx* d_points, int n_points,
-                          int rule, size_t frames, cudaStream_t s);
+                          int rule, const DecideGrid& grid, size_t frames, cudaStream_t s);
     const char* modc_name() const;
     const char* txc_name() const;
     const char* rxd_name() const;

@@ -285,6 +285,7 @@ struct SicArgs {
     const unsigned char* count;  // [K] multiplicity of subcarrier k in the subcarrier map (0 = inactive)
     int n_points, rule, ic_iter, phase_comp;
     float inv_map_total;         // 1 / (map.size() * M)
+    DecideGrid grid;             // hard-decision output (DEC): O(1) decisions on grid constellations
 };
 
 // DEC = true: the output is the hard decision of every soft symbol, one byte per symbol (chunks) -- see the epilogue.
@@ -319,6 +320,9 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_rx_kernel(cpx* __restrict
     // constellation: interference cancellation and the hard-decision output (mode 2)
     if constexpr (SIC || DEC)
         for (int i = tid; i < sic.n_points && i < S::MAX_POINTS; i += T) taps_s[S::PTS_OFF + i] = sic.points[i];
+    unsigned char* lut_s = reinterpret_cast<unsigned char*>(taps_s + S::RED_OFF); // DEC only (no phase reduction there)
+    if constexpr (DEC)
+        if (tid < 64) lut_s[tid] = sic.grid.lut[tid];
     if (tid == 0) mbar_init(bar_p, 1);
     // table columns of this thread -> tensor memory (once per CTA)
     uint32_t tmem_base = 0, tmem_mine = 0;
@@ -562,8 +566,7 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_rx_kernel(cpx* __restrict
                 // leave the SM, the frame goes out as one byte per symbol in the same [k][m] order
                 unsigned char* dst = reinterpret_cast<unsigned char*>(buf) + (size_t)(tid + j * T) * M;
                 const cpx* pts_s = taps_s + S::PTS_OFF;
-#pragma unroll
-                for (int m = 0; m < M; ++m) dst[m] = (unsigned char)decide_symbol(v[j][m], pts_s, sic.n_points, sic.rule);
+                decide_block<M>(v[j], dst, pts_s, sic.n_points, sic.rule, sic.grid, lut_s);
             } else {
                 cpx* dst = buf + (size_t)(tid + j * T) * M;
 #pragma unroll
@@ -969,7 +972,7 @@ int FusedModem::transmit_chunks(cpx* out, const unsigned char* chunks, const TxA
 }
 
 int FusedModem::demodulate_decide(unsigned char* chunks_out, const cpx* in, const cpx* eq, const cpx* d_points, int n_points,
-                                  int rule, size_t frames, cudaStream_t s)
+                                  int rule, const DecideGrid& dgrid, size_t frames, cudaStream_t s)
 {
     const ShapeEntry* e = impl_->e;
     if (!impl_->rxd_grid_cap) impl_->rxd_grid_cap = fused_grid_cap(e->rxd_fn, e->T, e->smem);
@@ -979,6 +982,7 @@ int FusedModem::demodulate_decide(unsigned char* chunks_out, const cpx* in, cons
     a.points = d_points;
     a.n_points = n_points;
     a.rule = rule;
+    a.grid = dgrid;
     for (size_t f0 = 0; f0 < frames; f0 += max_chunk) {
         const int nf = (int)std::min(max_chunk, frames - f0);
         const int groups = (nf + e->F - 1) / e->F;

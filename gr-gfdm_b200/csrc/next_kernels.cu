@@ -100,10 +100,13 @@ void launch_map_chunks(cpx* out, const unsigned char* chunks, const cpx* points,
 }
 
 __global__ void __launch_bounds__(TH) decide_chunks_kernel(unsigned char* __restrict__ chunks, const cpx* __restrict__ in,
-                                                           const cpx* __restrict__ points, int n_points, int rule, size_t n)
+                                                           const cpx* __restrict__ points, int n_points, int rule,
+                                                           const __grid_constant__ DecideGrid grid, size_t n)
 {
     __shared__ cpx pts[256];
+    __shared__ unsigned char lut[64];
     for (int i = threadIdx.x; i < 256; i += TH) pts[i] = i < n_points ? points[i] : cmake(0.f, 0.f);
+    if (threadIdx.x < 64) lut[threadIdx.x] = grid.lut[threadIdx.x];
     __syncthreads();
     const size_t head = ((4 - (reinterpret_cast<uintptr_t>(chunks) & 3)) & 3);
     const size_t h = head < n ? head : n;
@@ -113,17 +116,17 @@ __global__ void __launch_bounds__(TH) decide_chunks_kernel(unsigned char* __rest
         const cpx* x = in + h + 4 * q;
         uint32_t w = 0;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) w |= (uint32_t)decide_symbol(x[j], pts, n_points, rule) << (8 * j);
+        for (int j = 0; j < 4; ++j) w |= (uint32_t)decide_symbol_grid(x[j], pts, n_points, rule, grid, lut) << (8 * j);
         *reinterpret_cast<uint32_t*>(chunks + h + 4 * q) = w;
     }
-    for (size_t i = tid; i < h; i += stride) chunks[i] = (unsigned char)decide_symbol(in[i], pts, n_points, rule);
-    for (size_t i = h + 4 * quads + tid; i < n; i += stride) chunks[i] = (unsigned char)decide_symbol(in[i], pts, n_points, rule);
+    for (size_t i = tid; i < h; i += stride) chunks[i] = (unsigned char)decide_symbol_grid(in[i], pts, n_points, rule, grid, lut);
+    for (size_t i = h + 4 * quads + tid; i < n; i += stride) chunks[i] = (unsigned char)decide_symbol_grid(in[i], pts, n_points, rule, grid, lut);
 }
-void launch_decide_chunks(unsigned char* chunks, const cpx* in, const cpx* points, int n_points, int rule, size_t n,
-                          cudaStream_t s)
+void launch_decide_chunks(unsigned char* chunks, const cpx* in, const cpx* points, int n_points, int rule,
+                          const DecideGrid& grid, size_t n, cudaStream_t s)
 {
     if (!n) return;
-    decide_chunks_kernel<<<grid_for((n + 3) / 4, TH), TH, 0, s>>>(chunks, in, points, n_points, rule, n);
+    decide_chunks_kernel<<<grid_for((n + 3) / 4, TH), TH, 0, s>>>(chunks, in, points, n_points, rule, grid, n);
     GFDM_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -151,21 +154,23 @@ void launch_bits2symbols(cpx* out, const unsigned char* bits, const cpx* points,
 // decision + unpackbits (MSB first): one thread per symbol
 __global__ void __launch_bounds__(TH) symbols2bits_kernel(unsigned char* __restrict__ bits, const cpx* __restrict__ in,
                                                           const cpx* __restrict__ points, int n_points, int rule, int bps,
-                                                          size_t n)
+                                                          const __grid_constant__ DecideGrid grid, size_t n)
 {
     __shared__ cpx pts[256];
+    __shared__ unsigned char lut[64];
     for (int i = threadIdx.x; i < 256; i += TH) pts[i] = i < n_points ? points[i] : cmake(0.f, 0.f);
+    if (threadIdx.x < 64) lut[threadIdx.x] = grid.lut[threadIdx.x];
     __syncthreads();
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const int v = decide_symbol(in[i], pts, n_points, rule);
+        const int v = decide_symbol_grid(in[i], pts, n_points, rule, grid, lut);
         for (int b = 0; b < bps; ++b) bits[i * bps + b] = (unsigned char)((v >> (bps - 1 - b)) & 1);
     }
 }
-void launch_symbols2bits(unsigned char* bits, const cpx* in, const cpx* points, int n_points, int rule, int bps, size_t n,
-                         cudaStream_t s)
+void launch_symbols2bits(unsigned char* bits, const cpx* in, const cpx* points, int n_points, int rule, int bps,
+                         const DecideGrid& grid, size_t n, cudaStream_t s)
 {
     if (!n) return;
-    symbols2bits_kernel<<<grid_for(n, TH), TH, 0, s>>>(bits, in, points, n_points, rule, bps, n);
+    symbols2bits_kernel<<<grid_for(n, TH), TH, 0, s>>>(bits, in, points, n_points, rule, bps, grid, n);
     GFDM_CUDA_CHECK(cudaGetLastError());
 }
 

@@ -108,6 +108,31 @@ def get_zero_forcing_taps(filtertype, alpha, M, K, L=2):
     return G / np.sqrt(np.sum(np.abs(G) ** 2) / M)
 
 
+def get_mmse_taps(filtertype, alpha, M, K, L=2, snr_db=20.0):
+    """MMSE receive taps for the sparse receiver: gfdmlib's MMSE receiver pulse
+    (python/gfdmlib/gfdm/detail/gfdmutil.py:115-131, Zak transforms of gabor.py:11-21) restated for NumPy/Py3 --
+    Z(g_mmse) = 1 / conj(Z(g) + sigma^2 Z(g_zf) / K), zeros of Z(g) masked (|Z| < 1e-6), sigma^2 = 10^(-snr/10) --
+    then folded onto the L*M sparse taps exactly like get_zero_forcing_taps.  snr -> inf gives the ZF taps,
+    snr -> -inf the matched filter.  Design parity: unpinned (gfdmlib is Python 2 and is not exercised by the
+    reference's kernels); the kernels' arithmetic with given taps is pinned.
+    """
+    if K % L:
+        raise ValueError('subcarriers MUST be a multiple of overlap')
+    N = M * K
+    sigma2 = 10.0 ** (-snr_db / 10.0)
+    g = np.roll(gfdm_filter_taps(filtertype, alpha, M, K, 1), N // 2)  # pulse peak at index 0
+    Zg = np.fft.fft(g.reshape(M, K), axis=0)                            # sqrt(K) * zak(g, K), as [m, k]
+    small = np.abs(Zg) < 1e-6
+    Zg2 = np.where(small, 1.0, Zg)
+    Zgd = 1.0 / np.conjugate(Zg2)
+    Zgm = 1.0 / np.conjugate(Zg + sigma2 * Zgd / K)
+    Zgm[small] = 0.0
+    gmm = np.fft.ifft(Zgm, axis=0).reshape(N)
+    gmm = gmm / np.sum(gmm * g)
+    G = np.conjugate(np.fft.fft(gmm[::K // L]))
+    return G / np.sqrt(np.sum(np.abs(G) ** 2) / M)
+
+
 # --------------------------------------------------------------------------
 # windows
 def get_window_len(cp_len, n_timeslots, n_subcarriers, cs_len=0):
