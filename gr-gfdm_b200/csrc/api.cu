@@ -1116,6 +1116,12 @@ static void est_preamble_channel(gfdm_channel_estimator* h, cpx* H, const cpx* r
 static void est_frame(gfdm_channel_estimator* h, cpx* fe, const cpx* rx, size_t frames)
 {
     if (!frames) return;
+    if (est_fused_supported(h->K, h->A, h->dc_free)) {
+        launch_est_fused(fe, rx, h->fft_k.d_tw, h->d_inv0, h->d_inv1, h->d_g, h->M, h->K, h->A, h->dc_free, frames, h->stream);
+        h->launches += 1;
+        h->last_kernel = "est_fused_kernel";
+        return;
+    }
     h->hbuf.ensure(frames * (size_t)h->K * sizeof(cpx));
     h->filt.ensure(frames * (size_t)h->n_est() * sizeof(cpx));
     est_preamble_channel(h, h->hbuf.as<cpx>(), rx, frames);
@@ -1557,8 +1563,8 @@ int gfdm_extract_burst_work(gfdm_extract_burst* h, gfdm_complex* out, int max_bu
             const double scale = 1.0 / std::abs(pr);
             const cf inc((float)(scale * pr.real()), (float)(-1.0f * scale * pr.imag()));
             d.angle = std::atan2((double)inc.imag(), (double)inc.real());
-            d.inc_re = std::cos(d.angle);
-            d.inc_im = std::sin(d.angle);
+            d.inc32_re = std::cos(32.0 * d.angle);
+            d.inc32_im = std::sin(32.0 * d.angle);
             desc.push_back(d);
             produced_items += BL;
             consumed_items = burst_start + BL;

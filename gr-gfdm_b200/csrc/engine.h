@@ -43,6 +43,10 @@ void launch_copy_rows(cpx* out, const cpx* row, int len, size_t out_stride, size
 void launch_est_combine(cpx* H, const cpx* F, const cpx* inv0, const cpx* inv1, int K, size_t frames, cudaStream_t s);
 void launch_est_filter(cpx* filt, const cpx* H, const float* g, int K, int A, int dc_free, size_t frames, cudaStream_t s);
 void launch_est_interp(cpx* frame, const cpx* filt, int M, int K, int A, int dc_free, size_t frames, cudaStream_t s);
+// estimate_frame as one kernel (power-of-two fft_len); tw = FftPlan(K).d_tw
+bool est_fused_supported(int K, int A, int dc_free);
+void launch_est_fused(cpx* frame, const cpx* rx, const cpx* tw, const cpx* inv0, const cpx* inv1, const float* g, int M,
+                      int K, int A, int dc_free, size_t frames, cudaStream_t s);
 void launch_est_snr(float* snr, float* cnrs, const cpx* F2, int K, int A, int dc_free, size_t frames, cudaStream_t s);
 void launch_zf_prepare(cpx* out, const cpx* in, size_t n, cudaStream_t s);
 void launch_energy(float* out, const cpx* in, size_t n, cudaStream_t s);
@@ -51,8 +55,8 @@ void launch_energy(float* out, const cpx* in, size_t n, cudaStream_t s);
 // extract_burst_cc (lib/extract_burst_cc_impl.cc:117-242): one descriptor per produced burst
 struct BurstDesc {
     long long start;       // index of the burst's first sample in the stream window (negative: zeros in front)
-    double angle;          // CFO rotation per sample (radians), = arg(inc)
-    double inc_re, inc_im; // cos/sin(angle)
+    double angle;              // CFO rotation per sample (radians), = arg(inc)
+    double inc32_re, inc32_im; // cos/sin(32*angle): one warp step
     float scale;           // power normalisation factor
     int pad;
 };

@@ -11,6 +11,13 @@ namespace gfdm {
 
 static constexpr unsigned TH = 256;
 
+__device__ __forceinline__ cpx ldg_stream_cpx(const cpx* p)
+{
+    float2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
+}
+
 static unsigned grid_for(size_t items, unsigned threads)
 {
     // enough CTAs to fill the device (148 SMs x 8 resident CTAs of 256 threads), grid-stride beyond that
@@ -21,43 +28,44 @@ static unsigned grid_for(size_t items, unsigned threads)
 
 // ---------------------------------------------------------------------------------------------
 // extract_burst_cc: burst b, sample i:  out[b][i] = scale_b * in[start_b + i] * inc_b^i   (zeros where start_b + i < 0)
-// The rotation inc^i is evaluated directly (angle in double, one sincos per 4 samples, three complex products in
-// double), not by VOLK's recursive fp32 rotator: no drift, any sample can be computed independently.
+// The rotation inc^i is evaluated directly, not by VOLK's recursive fp32 rotator (no drift, any sample can be computed
+// independently): a warp owns 128 consecutive samples of a burst, lane l takes samples l, l+32, l+64, l+96 (every
+// access is a full 256-byte line), computes one sincos in double at its first sample and steps by inc^32 in double.
 __global__ void __launch_bounds__(TH) extract_burst_kernel(cpx* __restrict__ out, const cpx* __restrict__ in,
                                                            const BurstDesc* __restrict__ desc, int burst_len, int cfo,
                                                            int n_bursts)
 {
-    const int quads = (burst_len + 3) / 4;
-    const size_t total = (size_t)n_bursts * quads;
-    for (size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x; gid < total; gid += (size_t)gridDim.x * blockDim.x) {
-        const int b = (int)(gid / quads);
-        const int i0 = (int)(gid - (size_t)b * quads) * 4;
+    const int tiles = (burst_len + 127) / 128; // warp tiles per burst
+    const size_t total = (size_t)n_bursts * tiles;
+    const int lane = threadIdx.x & 31;
+    const size_t warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t w = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < total; w += warps) {
+        const int b = (int)(w / tiles);
+        const int i0 = (int)(w - (size_t)b * tiles) * 128 + lane;
         const BurstDesc d = desc[b];
         double pr = 1.0, pi = 0.0;
         if (cfo) sincos(d.angle * (double)i0, &pi, &pr);
         cpx* o = out + (size_t)b * burst_len;
+        cpx x[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int i = i0 + j;
-            if (i < burst_len) {
-                const long long src = d.start + i;
-                cpx v = cmake(0.f, 0.f);
-                if (src >= 0) {
-                    const cpx x = in[src];
-                    v = cmake(__fmul_rn(x.x, d.scale), __fmul_rn(x.y, d.scale)); // volk_32f_s32f_multiply_32f
-                    if (cfo) {
-                        const double re = (double)v.x * pr - (double)v.y * pi;
-                        const double im = (double)v.x * pi + (double)v.y * pr;
-                        v = cmake((float)re, (float)im);
-                    }
-                }
-                o[i] = v;
-            }
+            const int i = i0 + 32 * j;
+            const long long src = d.start + i;
+            x[j] = (i < burst_len && src >= 0) ? ldg_stream_cpx(in + src) : cmake(0.f, 0.f);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int i = i0 + 32 * j;
+            cpx v = cmake(__fmul_rn(x[j].x, d.scale), __fmul_rn(x[j].y, d.scale)); // volk_32f_s32f_multiply_32f
             if (cfo) {
-                const double nr = pr * d.inc_re - pi * d.inc_im;
-                pi = pr * d.inc_im + pi * d.inc_re;
+                const double re = (double)v.x * pr - (double)v.y * pi;
+                const double im = (double)v.x * pi + (double)v.y * pr;
+                v = cmake((float)re, (float)im);
+                const double nr = pr * d.inc32_re - pi * d.inc32_im;
+                pi = pr * d.inc32_im + pi * d.inc32_re;
                 pr = nr;
             }
+            if (i < burst_len) o[i] = v;
         }
     }
 }
@@ -65,7 +73,7 @@ void launch_extract_burst(cpx* out, const cpx* in, const BurstDesc* desc, int bu
                           cudaStream_t s)
 {
     if (n_bursts <= 0) return;
-    const size_t total = (size_t)n_bursts * ((burst_len + 3) / 4);
+    const size_t total = (size_t)n_bursts * ((burst_len + 127) / 128) * 32; // threads
     extract_burst_kernel<<<grid_for(total, TH), TH, 0, s>>>(out, in, desc, burst_len, cfo ? 1 : 0, n_bursts);
     GFDM_CUDA_CHECK(cudaGetLastError());
 }
@@ -78,24 +86,25 @@ __global__ void __launch_bounds__(TH) map_chunks_kernel(cpx* __restrict__ out, c
     __shared__ cpx pts[256];
     for (int i = threadIdx.x; i < 256; i += TH) pts[i] = i < n_points ? points[i] : cmake(0.f, 0.f);
     __syncthreads();
-    // 4 symbols per thread where the chunk address allows a 32-bit load; the tail and unaligned heads go one by one
-    const size_t head = ((4 - (reinterpret_cast<uintptr_t>(chunks) & 3)) & 3);
-    const size_t h = head < n ? head : n;
-    const size_t quads = (n - h) / 4;
+    // two symbols per thread where the addresses allow a 16-bit load and a 16-byte store (consecutive lanes write
+    // consecutive 16-byte units: every store instruction fills whole lines); head and tail go one by one
+    const bool vec = (reinterpret_cast<uintptr_t>(out) & 15) == ((reinterpret_cast<uintptr_t>(chunks) & 1) ? 8u : 0u);
+    const size_t h0 = vec ? (reinterpret_cast<uintptr_t>(chunks) & 1) : n;
+    const size_t h = h0 < n ? h0 : n;
+    const size_t pairs = (n - h) / 2;
     const size_t stride = (size_t)gridDim.x * blockDim.x, tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    for (size_t q = tid; q < quads; q += stride) {
-        const uint32_t w = *reinterpret_cast<const uint32_t*>(chunks + h + 4 * q);
-        cpx* o = out + h + 4 * q;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) o[j] = pts[(w >> (8 * j)) & 255u];
+    for (size_t q = tid; q < pairs; q += stride) {
+        const unsigned w = *reinterpret_cast<const unsigned short*>(chunks + h + 2 * q);
+        const cpx a = pts[w & 255u], b = pts[w >> 8];
+        *reinterpret_cast<float4*>(out + h + 2 * q) = make_float4(a.x, a.y, b.x, b.y);
     }
     for (size_t i = tid; i < h; i += stride) out[i] = pts[chunks[i]];
-    for (size_t i = h + 4 * quads + tid; i < n; i += stride) out[i] = pts[chunks[i]];
+    for (size_t i = h + 2 * pairs + tid; i < n; i += stride) out[i] = pts[chunks[i]];
 }
 void launch_map_chunks(cpx* out, const unsigned char* chunks, const cpx* points, int n_points, size_t n, cudaStream_t s)
 {
     if (!n) return;
-    map_chunks_kernel<<<grid_for((n + 3) / 4, TH), TH, 0, s>>>(out, chunks, points, n_points, n);
+    map_chunks_kernel<<<grid_for((n + 1) / 2, TH), TH, 0, s>>>(out, chunks, points, n_points, n);
     GFDM_CUDA_CHECK(cudaGetLastError());
 }
 

@@ -12,6 +12,26 @@ namespace gfdm {
 
 static constexpr unsigned TH = 256;
 
+// The copy / gather kernels below move E elements per thread: a CTA owns TH*E consecutive output elements, thread t
+// takes t, t+TH, ... (every access of a warp is one contiguous 256-byte run), all E loads are issued before the
+// first store (enough bytes in flight to cover HBM latency), and the (frame, offset) split costs one 64-bit
+// division per thread instead of one per element.
+static constexpr int EPT = 4;
+struct RowPos {
+    size_t f; // frame
+    int i;    // element inside the frame's row of length W
+    __device__ __forceinline__ RowPos(size_t gid, int W) : f(gid / (size_t)W), i((int)(gid - (gid / (size_t)W) * (size_t)W)) {}
+    __device__ __forceinline__ void advance(int step, int W)
+    {
+        i += step;
+        while (i >= W) {
+            i -= W;
+            ++f;
+        }
+    }
+};
+static inline unsigned blocks_ept(size_t total) { return blocks_for(total, TH * EPT); }
+
 // ---------------------------------------------------------------------------
 // modulator_kernel_cc::generic_work, lib/modulator_kernel_cc.cc:107-134, as a gather:
 // X[b*M+m] = sum_i T[((i+h)%L)*M+m] * D[((b-i+h) mod K)*M+m]   for m < part_len, else 0
@@ -207,26 +227,33 @@ __global__ void __launch_bounds__(TH) map_kernel(cpx* __restrict__ out, const cp
                                                  const int* __restrict__ inv_map, int M, int K, int A,
                                                  int per_timeslot, size_t n_in, size_t in_stride, size_t total)
 {
-    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= total) return;
     const int N = M * K;
-    const size_t f = gid / N;
-    const int r = (int)(gid - f * N);
-    const int k = r / M, t = r - k * M;
-    const int a = inv_map[k];
-    cpx v = cmake(0.f, 0.f);
-    if (a >= 0) {
-        const size_t src = per_timeslot ? (size_t)t * A + a : (size_t)a * M + t;
-        if (src < n_in) v = in[f * in_stride + src];
+    const size_t gid0 = (size_t)blockIdx.x * (TH * EPT) + threadIdx.x;
+    RowPos p(gid0, N);
+    cpx v[EPT];
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) {
+        v[j] = cmake(0.f, 0.f);
+        if (gid0 + (size_t)j * TH < total) {
+            const int k = p.i / M, t = p.i - k * M;
+            const int a = inv_map[k];
+            if (a >= 0) {
+                const size_t src = per_timeslot ? (size_t)t * A + a : (size_t)a * M + t;
+                if (src < n_in) v[j] = in[p.f * in_stride + src];
+            }
+        }
+        p.advance(TH, N);
     }
-    out[gid] = v;
+#pragma unroll
+    for (int j = 0; j < EPT; ++j)
+        if (gid0 + (size_t)j * TH < total) out[gid0 + (size_t)j * TH] = v[j];
 }
 void launch_map(cpx* out, const cpx* in, const int* inv_map, int M, int K, int A, bool per_timeslot, size_t n_in,
                 size_t in_stride, size_t frames, cudaStream_t s)
 {
     const size_t total = frames * (size_t)M * K;
     if (!total) return;
-    map_kernel<<<blocks_for(total, TH), TH, 0, s>>>(out, in, inv_map, M, K, A, per_timeslot ? 1 : 0, n_in, in_stride,
+    map_kernel<<<blocks_ept(total), TH, 0, s>>>(out, in, inv_map, M, K, A, per_timeslot ? 1 : 0, n_in, in_stride,
                                                     total);
     GFDM_CUDA_CHECK(cudaGetLastError());
 }
@@ -238,26 +265,37 @@ __global__ void __launch_bounds__(TH) demap_kernel(cpx* __restrict__ out, const 
                                                    const int* __restrict__ smap, int M, int K, int A, int per_timeslot,
                                                    size_t n_out, size_t out_stride, size_t total)
 {
-    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= total) return;
-    const size_t f = gid / n_out;
-    const size_t i = gid - f * n_out;
-    int a, t;
-    if (per_timeslot) {
-        t = (int)(i / A);
-        a = (int)(i - (size_t)t * A);
-    } else {
-        a = (int)(i / M);
-        t = (int)(i - (size_t)a * M);
+    const size_t gid0 = (size_t)blockIdx.x * (TH * EPT) + threadIdx.x;
+    const int W = (int)n_out;
+    RowPos p(gid0, W);
+    cpx v[EPT];
+    size_t dst[EPT];
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) {
+        dst[j] = p.f * out_stride + p.i;
+        if (gid0 + (size_t)j * TH < total) {
+            int a, t;
+            if (per_timeslot) {
+                t = p.i / A;
+                a = p.i - t * A;
+            } else {
+                a = p.i / M;
+                t = p.i - a * M;
+            }
+            v[j] = in[p.f * (size_t)M * K + (size_t)M * smap[a] + t];
+        }
+        p.advance(TH, W);
     }
-    out[f * out_stride + i] = in[f * (size_t)M * K + (size_t)M * smap[a] + t];
+#pragma unroll
+    for (int j = 0; j < EPT; ++j)
+        if (gid0 + (size_t)j * TH < total) out[dst[j]] = v[j];
 }
 void launch_demap(cpx* out, const cpx* in, const int* smap, int M, int K, int A, bool per_timeslot, size_t n_out,
                   size_t out_stride, size_t frames, cudaStream_t s)
 {
     const size_t total = frames * n_out;
     if (!total) return;
-    demap_kernel<<<blocks_for(total, TH), TH, 0, s>>>(out, in, smap, M, K, A, per_timeslot ? 1 : 0, n_out, out_stride,
+    demap_kernel<<<blocks_ept(total), TH, 0, s>>>(out, in, smap, M, K, A, per_timeslot ? 1 : 0, n_out, out_stride,
                                                       total);
     GFDM_CUDA_CHECK(cudaGetLastError());
 }
@@ -271,24 +309,39 @@ __global__ void __launch_bounds__(TH) add_cp_kernel(cpx* __restrict__ out, const
                                                     const cpx* __restrict__ back, int shift, size_t out_stride,
                                                     size_t total)
 {
-    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= total) return;
     const int W = N + cp + cs;
-    const size_t f = gid / W;
-    const int i = (int)(gid - f * W);
-    int src = i + N - cp - shift;
-    while (src >= N) src -= N;
-    cpx v = in[f * N + src];
-    if (i < ramp) v = cmul_rn(v, front[i]);
-    if (i >= W - ramp) v = cmul_rn(v, back[i - (W - ramp)]);
-    out[f * out_stride + i] = v;
+    const size_t gid0 = (size_t)blockIdx.x * (TH * EPT) + threadIdx.x;
+    RowPos p(gid0, W);
+    cpx v[EPT];
+    size_t dst[EPT];
+    int pos[EPT];
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) {
+        dst[j] = p.f * out_stride + p.i;
+        pos[j] = p.i;
+        if (gid0 + (size_t)j * TH < total) {
+            int src = p.i + N - cp - shift;
+            while (src >= N) src -= N;
+            v[j] = in[p.f * N + src];
+        }
+        p.advance(TH, W);
+    }
+#pragma unroll
+    for (int j = 0; j < EPT; ++j)
+        if (gid0 + (size_t)j * TH < total) {
+            cpx x = v[j];
+            const int i = pos[j];
+            if (i < ramp) x = cmul_rn(x, front[i]);
+            if (i >= W - ramp) x = cmul_rn(x, back[i - (W - ramp)]);
+            out[dst[j]] = x;
+        }
 }
 void launch_add_cp(cpx* out, const cpx* in, int N, int cp, int cs, int ramp, const cpx* front, const cpx* back,
                    int shift, size_t out_stride, size_t frames, cudaStream_t s)
 {
     const size_t total = frames * (size_t)(N + cp + cs);
     if (!total) return;
-    add_cp_kernel<<<blocks_for(total, TH), TH, 0, s>>>(out, in, N, cp, cs, ramp, front, back, shift, out_stride, total);
+    add_cp_kernel<<<blocks_ept(total), TH, 0, s>>>(out, in, N, cp, cs, ramp, front, back, shift, out_stride, total);
     GFDM_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -296,17 +349,23 @@ void launch_add_cp(cpx* out, const cpx* in, int N, int cp, int cs, int ramp, con
 __global__ void __launch_bounds__(TH) remove_cp_kernel(cpx* __restrict__ out, const cpx* __restrict__ in, int N,
                                                        int cp, int W, size_t total)
 {
-    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= total) return;
-    const size_t f = gid / N;
-    const int i = (int)(gid - f * N);
-    out[gid] = in[f * W + cp + i];
+    const size_t gid0 = (size_t)blockIdx.x * (TH * EPT) + threadIdx.x;
+    RowPos p(gid0, N);
+    cpx v[EPT];
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) {
+        if (gid0 + (size_t)j * TH < total) v[j] = in[p.f * W + cp + p.i];
+        p.advance(TH, N);
+    }
+#pragma unroll
+    for (int j = 0; j < EPT; ++j)
+        if (gid0 + (size_t)j * TH < total) out[gid0 + (size_t)j * TH] = v[j];
 }
 void launch_remove_cp(cpx* out, const cpx* in, int N, int cp, int cs, size_t frames, cudaStream_t s)
 {
     const size_t total = frames * (size_t)N;
     if (!total) return;
-    remove_cp_kernel<<<blocks_for(total, TH), TH, 0, s>>>(out, in, N, cp, N + cp + cs, total);
+    remove_cp_kernel<<<blocks_ept(total), TH, 0, s>>>(out, in, N, cp, N + cp + cs, total);
     GFDM_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -314,17 +373,19 @@ void launch_remove_cp(cpx* out, const cpx* in, int N, int cp, int cs, size_t fra
 __global__ void __launch_bounds__(TH) copy_rows_kernel(cpx* __restrict__ out, const cpx* __restrict__ row, int len,
                                                        size_t out_stride, size_t total)
 {
-    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= total) return;
-    const size_t f = gid / len;
-    const int i = (int)(gid - f * len);
-    out[f * out_stride + i] = row[i];
+    const size_t gid0 = (size_t)blockIdx.x * (TH * EPT) + threadIdx.x;
+    RowPos p(gid0, len);
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) {
+        if (gid0 + (size_t)j * TH < total) out[p.f * out_stride + p.i] = row[p.i];
+        p.advance(TH, len);
+    }
 }
 void launch_copy_rows(cpx* out, const cpx* row, int len, size_t out_stride, size_t frames, cudaStream_t s)
 {
     const size_t total = frames * (size_t)len;
     if (!total) return;
-    copy_rows_kernel<<<blocks_for(total, TH), TH, 0, s>>>(out, row, len, out_stride, total);
+    copy_rows_kernel<<<blocks_ept(total), TH, 0, s>>>(out, row, len, out_stride, total);
     GFDM_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -449,6 +510,129 @@ void launch_est_interp(cpx* frame, const cpx* filt, int M, int K, int A, int dc_
     const size_t total = frames * (size_t)M * K;
     if (!total) return;
     est_interp_kernel<<<blocks_for(total, TH), TH, 0, s>>>(frame, filt, M, K, A, dc_free ? 1 : 0, total);
+    GFDM_CUDA_CHECK(cudaGetLastError());
+}
+
+__device__ __forceinline__ void stg_stream_cpx(cpx* p, cpx v)
+{
+    asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
+}
+
+// ---------------------------------------------------------------------------
+// estimate_frame (:285-294) as ONE kernel for power-of-two fft_len: a CTA keeps a frame's preamble halves in shared
+// memory, runs both K-point transforms there (Stockham autosort, radix 2, twiddles from the double-precision table),
+// forms H, the 9-tap filtered estimate, and streams the N interpolated bins out -- 8*(2K + N) bytes of HBM traffic
+// per frame, against four kernels with three intermediate arrays.  Arithmetic after the transforms is the unfused
+// fp32 of the stage kernels above (same bits); grid-stride over frames, CTAs sized by occupancy.
+__global__ void __launch_bounds__(TH) est_fused_kernel(cpx* __restrict__ frame, const cpx* __restrict__ rx,
+                                                       const cpx* __restrict__ tw, const cpx* __restrict__ inv0,
+                                                       const cpx* __restrict__ inv1, const float* __restrict__ g, int M,
+                                                       int K, int A, int off, size_t frames)
+{
+    extern __shared__ __align__(16) unsigned char est_smem[];
+    cpx* xa = reinterpret_cast<cpx*>(est_smem); // [2][K] ping
+    cpx* xb = xa + 2 * K;                       // [2][K] pong; later H [K] and filt [A+off]
+    const int tid = threadIdx.x;
+    const int N = M * K, n_est = A + off, half = n_est / 2;
+    const int center = N / 2, dead_half = M * (K - A) / 2;
+    float gt[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) gt[t] = g[t];
+    const int so0 = tid / M, j0 = tid - so0 * M, qTH = (int)TH / M, rTH = (int)TH - qTH * M; // walk of the interpolation loops
+    for (size_t f = blockIdx.x; f < frames; f += gridDim.x) {
+        const cpx* in = rx + f * 2 * (size_t)K;
+        for (int i = tid; i < 2 * K; i += TH) xa[i] = in[i];
+        __syncthreads();
+        // both transforms at once: butterfly index j < K/2 of half h
+        cpx* src = xa;
+        cpx* dst = xb;
+        for (int Ns = 1; Ns < K; Ns <<= 1) {
+            for (int w = tid; w < K; w += TH) {
+                const int h = w >= K / 2, j = w - h * (K / 2);
+                const int k = j & (Ns - 1);
+                const cpx a = src[h * K + j];
+                const cpx b = cmul(src[h * K + j + K / 2], tw[k * (K / (2 * Ns))]);
+                const int j0 = ((j - k) << 1) + k;
+                dst[h * K + j0] = cadd(a, b);
+                dst[h * K + j0 + Ns] = csub(a, b);
+            }
+            __syncthreads();
+            cpx* t = src;
+            src = dst;
+            dst = t;
+        }
+        // H = F0 * inv0 + F1 * inv1 (:121-143) -> dst[0..K)
+        for (int q = tid; q < K; q += TH) {
+            const cpx a = cmul_rn(src[q], inv0[q]);
+            const cpx b = cmul_rn(src[K + q], inv1[q]);
+            dst[q] = cmake(__fadd_rn(b.x, a.x), __fadd_rn(b.y, a.y));
+        }
+        __syncthreads();
+        // reorder + edge replicate + 9-tap correlation (:145-185) -> src[0..n_est)
+        for (int i = tid; i < n_est; i += TH) {
+            float re = 0.f, im = 0.f;
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                const cpx v = est_padded(dst, i + t, K, A, off);
+                re = __fadd_rn(re, __fmul_rn(v.x, gt[t]));
+                im = __fadd_rn(im, __fmul_rn(v.y, gt[t]));
+            }
+            src[i] = cmake(re, im);
+        }
+        __syncthreads();
+        // piecewise-linear interpolation to N bins (:238-274): the cases of est_interp_kernel as four division-free
+        // loops (thread t walks bins t, t+TH, ...: segment and offset advance by TH/M and TH%M); the reference's
+        // running sum e[i] + inc + ... + inc (j times) is evaluated as fma(j, inc, e[i]) -- at most j ulps apart
+        const cpx* e = src;
+        cpx* o = frame + f * (size_t)N;
+        const float step = 1.0f / (float)M;
+        auto ramp = [&](int lo, int n_bins, int seg0) {
+            int seg = seg0 + so0, j = j0;
+            for (int r = tid; r < n_bins; r += TH) {
+                const cpx e0 = e[seg], d = csub(e[seg + 1], e0);
+                const float fj = (float)j;
+                stg_stream_cpx(o + lo + r, cmake(fmaf(fj, d.x * step, e0.x), fmaf(fj, d.y * step, e0.y)));
+                j += rTH;
+                seg += qTH;
+                if (j >= M) {
+                    j -= M;
+                    ++seg;
+                }
+            }
+        };
+        ramp(0, (n_est - 1 - half) * M, half);          // last loop of the reference: i in [half, n_est-1)
+        ramp(center + dead_half, half * M, 0);          // i in [0, half)
+        {
+            const cpx hi = e[n_est - 1], lo = e[0];
+            for (int b2 = M * A / 2 + tid; b2 < center; b2 += TH) stg_stream_cpx(o + b2, hi);
+            for (int b2 = center + tid; b2 < center + dead_half; b2 += TH) stg_stream_cpx(o + b2, lo);
+        }
+        __syncthreads(); // src/dst are reused by the next frame
+    }
+}
+bool est_fused_supported(int K, int A, int dc_free)
+{
+    // even A: the four bin ranges of the interpolation are then disjoint, so their loops need no ordering
+    return K >= 8 && K <= 4096 && (K & (K - 1)) == 0 && A >= 2 && A % 2 == 0 && A + (dc_free ? 1 : 0) <= K;
+}
+void launch_est_fused(cpx* frame, const cpx* rx, const cpx* tw, const cpx* inv0, const cpx* inv1, const float* g, int M,
+                      int K, int A, int dc_free, size_t frames, cudaStream_t s)
+{
+    if (!frames) return;
+    const size_t smem = sizeof(cpx) * 4 * (size_t)K;
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        GFDM_CUDA_CHECK(cudaGetDevice(&dev));
+        GFDM_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    if (smem > 48 * 1024)
+        GFDM_CUDA_CHECK(cudaFuncSetAttribute(est_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    GFDM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, est_fused_kernel, (int)TH, smem));
+    const size_t cap = (size_t)sms * (per_sm > 0 ? per_sm : 1);
+    est_fused_kernel<<<(unsigned)(frames < cap ? frames : cap), TH, smem, s>>>(frame, rx, tw, inv0, inv1, g, M, K, A,
+                                                                                dc_free ? 1 : 0, frames);
     GFDM_CUDA_CHECK(cudaGetLastError());
 }
 

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Device-resident throughput of the chain entry points around the modulator/receiver
 against their algorithmic bytes.  One JSON line per measurement; CUDA-event timing on the
-handle's stream, buffers larger than L2.  usage (GPU box): python tools/chain_bench.py [tx] [rx] [est] [adv]"""
+handle's stream, buffers larger than L2.  usage (GPU box): python tools/chain_bench.py [tx] [rx] [copy] [next]"""
 import json
 import os
 import sys
@@ -74,9 +74,115 @@ def tx_chain(M, K, A, cp, cs, frames, shifts=(0,)):
     tx.set_chain_fusion(True)
 
 
+def rx_rows(M, K, A, frames, ic_iter=4):
+    """Receiver-side rows at one shape: equalising receiver (24N bytes/frame), preamble channel estimator
+    (8*(2K+N)), advanced receiver with `ic_iter` SIC iterations resident on the SM (24N regardless of ic_iter)."""
+    rng = np.random.default_rng(11)
+    N = M * K
+    shape = 'K=%d M=%d A=%d' % (K, M, A)
+    taps = design.get_frequency_domain_filter('rrc', 0.5, M, K, 2)
+    smap = design.get_subcarrier_map(K, A, dc_free=True)
+    d_x = torch.from_numpy(crand(rng, frames, N)).cuda()
+    d_h = torch.from_numpy((1 + 0.3 * crand(rng, frames, N)).astype(np.complex64)).cuda()
+    d_y = torch.empty_like(d_x)
+    rx = capi.Demodulator(M, K, 2, np.conj(taps), lib=lib)
+    rx.set_stream(stream.cuda_stream)
+    ms = timed(lambda: rx.demodulate_ptr(d_y.data_ptr(), d_x.data_ptr(), d_h.data_ptr(), frames))
+    report('receiver_kernel_cc::generic_work_equalize', shape, frames, ms, 24 * N, rx.last_kernel())
+    for it in (0, ic_iter):
+        adv = capi.Advanced_receiver(M, K, 2, np.conj(taps), smap, it, capi.qpsk_constellation(), 0, lib=lib)
+        adv.set_stream(stream.cuda_stream)
+        ms = timed(lambda: adv.demodulate_ptr(d_y.data_ptr(), d_x.data_ptr(), d_h.data_ptr(), frames))
+        report('advanced_receiver_kernel_cc::generic_work_equalize, %d SIC iterations' % it, shape, frames, ms, 24 * N,
+               adv.last_kernel())
+    preamble = crand(rng, 2 * K)
+    est = capi.Preamble_channel_estimator(M, K, A, True, 0, preamble, lib=lib)
+    est.set_stream(stream.cuda_stream)
+    d_p = torch.from_numpy(crand(rng, frames, 2 * K)).cuda()
+    ms = timed(lambda: est.estimate_frame_ptr(d_h.data_ptr(), d_p.data_ptr(), frames))
+    report('preamble_channel_estimator_cc::estimate_frame', shape, frames, ms, 8 * (2 * K + N), est.last_kernel())
+
+
+def copy_rows(M, K, A, cp, cs, frames):
+    """Integer / copy rows: resource mapper, demapper, cyclic prefixer (add with window, remove), remove_prefix."""
+    rng = np.random.default_rng(13)
+    N = M * K
+    shape = 'K=%d M=%d A=%d cp=%d cs=%d' % (K, M, A, cp, cs)
+    smap = design.get_subcarrier_map(K, A, dc_free=True)
+    mp = capi.Resource_mapper(M, K, A, smap, True, lib=lib)
+    mp.set_stream(stream.cuda_stream)
+    d_c = torch.from_numpy(crand(rng, frames, A * M)).cuda()
+    d_g = torch.empty((frames, N), dtype=torch.complex64, device='cuda')
+    ms = timed(lambda: mp.map_ptr(d_g.data_ptr(), d_c.data_ptr(), A * M, frames))
+    report('resource_mapper_kernel_cc::map_to_resources', shape, frames, ms, 8 * (A * M + N), mp.last_kernel())
+    ms = timed(lambda: mp.demap_ptr(d_c.data_ptr(), d_g.data_ptr(), A * M, frames))
+    report('resource_mapper_kernel_cc::demap_from_resources', shape, frames, ms, 8 * (2 * A * M), mp.last_kernel())
+    W = N + cp + cs
+    window = design.get_raised_cosine_ramp(cs, W)
+    pf = capi.Cyclic_prefixer(N, cp, cs, cs, window, lib=lib)
+    pf.set_stream(stream.cuda_stream)
+    d_f = torch.empty((frames, W), dtype=torch.complex64, device='cuda')
+    ms = timed(lambda: pf.add_ptr(d_f.data_ptr(), d_g.data_ptr(), 0, frames))
+    report('add_cyclic_prefix_cc::add_cyclic_prefix', shape, frames, ms, 8 * (N + W), pf.last_kernel())
+    ms = timed(lambda: pf.remove_ptr(d_g.data_ptr(), d_f.data_ptr(), frames))
+    report('add_cyclic_prefix_cc::remove_cyclic_prefix', shape, frames, ms, 8 * (2 * N), pf.last_kernel())
+    rp = capi.Remove_prefix(W, N, cp, lib=lib)
+    rp.set_stream(stream.cuda_stream)
+    ms = timed(lambda: rp.work_ptr(d_g.data_ptr(), d_f.data_ptr(), frames))
+    report('remove_prefix_cc', shape, frames, ms, 8 * (2 * N), rp.last_kernel())
+
+
+def next_rows(M, K, frames):
+    """Rows either side of the path: symbol mapping kernels, burst extraction, byte-wide chain entries."""
+    rng = np.random.default_rng(17)
+    N = M * K
+    n = frames * N
+    shape = 'K=%d M=%d' % (K, M)
+    sm = capi.Symbol_mapper((design.qam16_points(), capi.DECISION_NEAREST), lib=lib)
+    sm.set_stream(stream.cuda_stream)
+    d_ch = torch.randint(0, 16, (frames, N), dtype=torch.uint8, device='cuda')
+    d_s = torch.empty((frames, N), dtype=torch.complex64, device='cuda')
+    ms = timed(lambda: sm.map_chunks_ptr(d_s.data_ptr(), d_ch.data_ptr(), n))
+    report('symbol mapper: chunks -> points', shape, frames, ms, 9 * N, sm.last_kernel())
+    d_s.add_(0.1 * torch.randn_like(d_s))
+    ms = timed(lambda: sm.decide_ptr(d_ch.data_ptr(), d_s.data_ptr(), n))
+    report('symbol mapper: hard decisions', shape, frames, ms, 9 * N, sm.last_kernel())
+    taps = design.get_frequency_domain_filter('rrc', 0.5, M, K, 2)
+    mod, rx = capi.Modulator(M, K, 2, taps, lib=lib), capi.Demodulator(M, K, 2, np.conj(taps), lib=lib)
+    mod.set_stream(stream.cuda_stream)
+    rx.set_stream(stream.cuda_stream)
+    d_x = torch.empty_like(d_s)
+    ms = timed(lambda: mod.modulate_chunks_ptr(sm, d_x.data_ptr(), d_ch.data_ptr(), frames))
+    report('modulator_kernel_cc from chunks', shape, frames, ms, 9 * N, mod.last_kernel())
+    ms = timed(lambda: rx.demodulate_decide_ptr(sm, d_ch.data_ptr(), d_x.data_ptr(), 0, frames))
+    report('receiver_kernel_cc to hard decisions', shape, frames, ms, 9 * N, rx.last_kernel())
+    # extract_burst: one burst per frame-sized slot of a long stream, backoff 8, with and without CFO correction
+    burst = N + 96
+    starts = np.arange(frames, dtype=np.int64) * (burst + 32) + 40
+    stream_len = int(starts[-1] + burst + 8)
+    d_in = torch.from_numpy(crand(rng, stream_len)).cuda()
+    d_b = torch.empty((frames, burst), dtype=torch.complex64, device='cuda')
+    scales = rng.uniform(0.5, 2, frames).astype(np.float32)
+    rots = np.exp(1j * rng.uniform(-1e-3, 1e-3, frames)).astype(np.complex64)
+    for cfo in (False, True):
+        eb = capi.Extract_burst(burst, 8, cfo, lib=lib)
+        eb.set_stream(stream.cuda_stream)
+        ms = timed(lambda: eb.work_ptr(d_b.data_ptr(), frames, d_in.data_ptr(), stream_len, starts, scales, rots))
+        report('extract_burst_cc (%s)' % ('scale + CFO rotation' if cfo else 'scale only'), 'burst_len=%d' % burst, frames, ms,
+               16 * burst, eb.last_kernel())
+
+
 if __name__ == '__main__':
     what = sys.argv[1:] or ['tx']
     if 'tx' in what:
         tx_chain(9, 64, 52, 16, 8, 1 << 16)            # BASELINE configs[1]
         tx_chain(15, 1024, 832, 64, 32, 4096)           # headline shape with CP
         tx_chain(15, 256, 208, 32, 16, 1 << 14, (0, 16))
+    if 'rx' in what:
+        rx_rows(15, 256, 208, 1 << 14)                  # BASELINE configs[3]: estimator + advanced receiver, 4 SIC iterations
+        rx_rows(15, 1024, 832, 4096)
+    if 'copy' in what:
+        copy_rows(9, 64, 52, 16, 8, 1 << 16)
+        copy_rows(15, 1024, 832, 64, 32, 4096)
+    if 'next' in what:
+        next_rows(15, 1024, 4096)
