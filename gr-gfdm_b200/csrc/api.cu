@@ -520,6 +520,19 @@ static void receiver_td(gfdm_receiver* h, cpx* out, const cpx* R, size_t frames)
     h->work_c.ensure(el * sizeof(cpx));
     h->launches += fft_exec(h->fft_m, out, R, h->work_c.as<cpx>(), frames * h->K, true, (float)(1.0 / h->M), h->stream);
 }
+// both results of the receiver for the cancellation loop: R (kept frequency blocks) and y = IFFT_M(R)/M.  With a
+// fused kernel that is two launches of it (the second transform is cheaper there than a staged M-point pass over HBM)
+static void receiver_fd_td(gfdm_receiver* h, cpx* R, cpx* y, const cpx* in, const cpx* eq, size_t frames)
+{
+    if (!frames) return;
+    if (h->fused.available() && (!eq || h->fused.supports_eq()) && aligned16(R) && aligned16(y) && aligned16(in) &&
+        aligned16(eq)) {
+        h->launches += h->fused.demodulate(y, R, in, eq, frames, h->stream);
+        return;
+    }
+    receiver_fd(h, R, in, eq, frames);
+    receiver_td(h, y, R, frames);
+}
 // generic_work[_equalize] (:322-334)
 static void receiver_run(gfdm_receiver* h, cpx* out, const cpx* in, const cpx* eq, size_t frames)
 {
@@ -687,17 +700,43 @@ static void advanced_run(gfdm_advanced_receiver* h, cpx* out, const cpx* in, con
     cpx* FB = h->freq_block.as<cpx>();
     cpx* IT = h->ic_time.as<cpx>();
     cpx* IF = h->ic_freq.as<cpx>();
-    receiver_fd(h, FB, in, eq, frames);
-    receiver_td(h, out, FB, frames);
-    for (int j = 0; j < h->ic_iter; ++j) {
-        launch_decide(IT, out, h->d_active, h->d_points, h->n_points, h->rule, h->M, h->K, frames, h->stream);
-        h->launches += 1;
-        if (h->phase_comp > 0 && j == 0) {
-            launch_phase_rotate(FB, IT, out, h->d_smap, (int)h->smap.size(), h->M, h->K, frames, h->stream);
+    const bool one_kernel_iter = sic_iter_supported(h->M, h->K, h->n_points, frames);
+    const bool staged_first = !one_kernel_iter || (h->phase_comp > 0 && h->ic_iter > 0);
+    {
+        // soft symbols go where the first consumer reads them (see the ping-pong below)
+        const int rest0 = std::max(0, h->ic_iter);
+        cpx* y0 = (staged_first || rest0 % 2 == 0) ? out : IT;
+        receiver_fd_td(h, FB, y0, in, eq, frames);
+    }
+    // iterations that need no phase estimate run as ONE kernel each, ping-ponging between `out` and IT; the first
+    // buffer is chosen so that the last iteration lands in `out`
+    int j0 = 0;
+    if (staged_first) {
+        const int staged = one_kernel_iter ? 1 : h->ic_iter; // with phase compensation only iteration 0 is staged
+        for (int j = 0; j < staged; ++j) {
+            launch_decide(IT, out, h->d_active, h->d_points, h->n_points, h->rule, h->M, h->K, frames, h->stream);
             h->launches += 1;
+            if (h->phase_comp > 0 && j == 0) {
+                launch_phase_rotate(FB, IT, out, h->d_smap, (int)h->smap.size(), h->M, h->K, frames, h->stream);
+                h->launches += 1;
+            }
+            receiver_cancel(h, IF, IT, FB, frames);
+            receiver_td(h, out, IF, frames);
         }
-        receiver_cancel(h, IF, IT, FB, frames);
-        receiver_td(h, out, IF, frames);
+        j0 = staged;
+    }
+    if (one_kernel_iter) {
+        const int rest = std::max(0, h->ic_iter - j0);
+        cpx* cur = (rest % 2 == 0) ? out : IT;
+        cpx* nxt = (rest % 2 == 0) ? IT : out;
+        if (j0 != 0 && cur != out) GFDM_CUDA_CHECK(cudaMemcpyAsync(cur, out, el * sizeof(cpx), cudaMemcpyDeviceToDevice, h->stream));
+        for (int j = 0; j < rest; ++j) {
+            launch_sic_iter(nxt, cur, FB, h->d_ic, h->d_active, h->d_points, h->n_points, h->rule, h->M, h->K, frames, h->stream);
+            h->launches += 1;
+            std::swap(cur, nxt);
+        }
+        h->last_kernel = "receiver -> sic_iter_kernel per iteration";
+        return;
     }
     h->last_kernel = "generic:advanced_receiver";
 }
@@ -1511,7 +1550,13 @@ int gfdm_remove_prefix_work_batch(gfdm_remove_prefix* h, gfdm_complex* out, cons
 struct gfdm_extract_burst : HandleBase {
     int burst_len = 0, tag_backoff = 0;
     bool cfo = false;
-    DeviceBuf d_desc;
+    // burst descriptors: two pinned host slots + device copies, so that a DEVICE call never waits for the GPU
+    // (slot i is rewritten only after the copy that read it two calls ago has completed)
+    BurstDesc* h_desc[2] = { nullptr, nullptr };
+    size_t h_cap[2] = { 0, 0 };
+    DeviceBuf d_desc[2];
+    cudaEvent_t ev_copied[2] = { nullptr, nullptr };
+    int slot = 0;
 };
 int gfdm_extract_burst_create(gfdm_extract_burst** out, int burst_len, int tag_backoff, int activate_cfo_correction)
 {
@@ -1527,7 +1572,11 @@ void gfdm_extract_burst_destroy(gfdm_extract_burst* h)
 {
     if (!h) return;
     cudaSetDevice(h->device);
-    h->d_desc.release();
+    for (int i = 0; i < 2; ++i) {
+        h->d_desc[i].release();
+        if (h->h_desc[i]) cudaFreeHost(h->h_desc[i]);
+        if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
+    }
     h->close();
     delete h;
 }
@@ -1551,21 +1600,29 @@ int gfdm_extract_burst_work(gfdm_extract_burst* h, gfdm_complex* out, int max_bu
     // descriptor per produced burst; the samples are touched by the kernel only
     const long long BL = h->burst_len, noutput_items = (long long)max_bursts * BL, avail_items = n_in;
     long long consumed_items = avail_items, produced_items = 0;
-    std::vector<BurstDesc> desc;
+    const int sl = h->slot;
+    h->slot ^= 1;
+    if (!h->ev_copied[sl]) GFDM_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_copied[sl], cudaEventDisableTiming));
+    GFDM_CUDA_CHECK(cudaEventSynchronize(h->ev_copied[sl])); // the copy that last read this slot (no-op when never recorded)
+    const size_t need = (size_t)std::min<long long>(n_tags, max_bursts);
+    if (need > h->h_cap[sl]) {
+        if (h->h_desc[sl]) cudaFreeHost(h->h_desc[sl]);
+        h->h_desc[sl] = nullptr;
+        h->h_cap[sl] = 0;
+        GFDM_CUDA_CHECK(cudaMallocHost(reinterpret_cast<void**>(&h->h_desc[sl]), sizeof(BurstDesc) * need));
+        h->h_cap[sl] = need;
+    }
+    BurstDesc* desc = h->h_desc[sl];
+    int nb = 0;
     for (int t = 0; t < n_tags; ++t) {
         const long long burst_start = burst_starts[t];
         if (avail_items - burst_start >= BL && produced_items + BL <= noutput_items) {
             BurstDesc d{};
             d.start = burst_start - h->tag_backoff;
             d.scale = scale_factors ? scale_factors[t] : 1.0f;
-            // get_phase_rotation (:88-96): inc = conj(pr)/|pr| rounded to complex<float>; the kernel rotates by its angle
-            const cf pr = phase_rotations ? cf(phase_rotations[t].re, phase_rotations[t].im) : cf(1.0f, 0.0f);
-            const double scale = 1.0 / std::abs(pr);
-            const cf inc((float)(scale * pr.real()), (float)(-1.0f * scale * pr.imag()));
-            d.angle = std::atan2((double)inc.imag(), (double)inc.real());
-            d.inc32_re = std::cos(32.0 * d.angle);
-            d.inc32_im = std::sin(32.0 * d.angle);
-            desc.push_back(d);
+            d.pr_re = phase_rotations ? phase_rotations[t].re : 1.0f; // get_phase_rotation (:88-96) runs on the device
+            d.pr_im = phase_rotations ? phase_rotations[t].im : 0.0f;
+            desc[nb++] = d;
             produced_items += BL;
             consumed_items = burst_start + BL;
         } else {
@@ -1573,15 +1630,13 @@ int gfdm_extract_burst_work(gfdm_extract_burst* h, gfdm_complex* out, int max_bu
             break;
         }
     }
-    const int nb = (int)desc.size();
     if (nb > 0) {
-        h->d_desc.ensure(sizeof(BurstDesc) * desc.size());
-        GFDM_CUDA_CHECK(cudaMemcpyAsync(h->d_desc.p, desc.data(), sizeof(BurstDesc) * desc.size(), cudaMemcpyHostToDevice, h->stream));
-        GFDM_CUDA_CHECK(cudaStreamSynchronize(h->stream)); // `desc` is pageable and dies with this call
+        h->d_desc[sl].ensure(sizeof(BurstDesc) * (size_t)nb);
+        GFDM_CUDA_CHECK(cudaMemcpyAsync(h->d_desc[sl].p, desc, sizeof(BurstDesc) * (size_t)nb, cudaMemcpyHostToDevice, h->stream));
+        GFDM_CUDA_CHECK(cudaEventRecord(h->ev_copied[sl], h->stream));
         const cpx* di = st.in(in, (size_t)n_in, h->stage_in);
         cpx* dout = st.out(out, (size_t)nb * BL, h->stage_out);
-        launch_extract_burst(dout, di, h->d_desc.as<BurstDesc>(), h->burst_len, h->cfo, nb, h->stream);
-        h->launches += 1;
+        h->launches += launch_extract_burst(dout, di, h->d_desc[sl].as<BurstDesc>(), h->burst_len, h->cfo, nb, h->stream);
         h->last_kernel = "extract_burst_kernel";
         st.finish(out, (size_t)nb * BL, h->stage_out);
     }

@@ -28,6 +28,10 @@ void launch_rx_filter(cpx* R, const cpx* Y, const cpx* taps, int M, int K, int L
 void launch_eq_divide(cpx* out, const cpx* Y, const cpx* eq, size_t n, cudaStream_t s);
 void launch_neighbor_sum(cpx* out, const cpx* td, int M, int K, size_t frames, cudaStream_t s);
 void launch_ic_subtract(cpx* out, const cpx* fd, const cpx* F, const cpx* ic_taps, int M, int K, size_t frames, cudaStream_t s);
+// one whole cancellation iteration (decide neighbours, re-modulate, subtract, back to time domain): y_out != y_in
+bool sic_iter_supported(int M, int K, int n_points, size_t frames);
+void launch_sic_iter(cpx* y_out, const cpx* y_in, const cpx* fb, const cpx* ic_taps, const unsigned char* active,
+                     const cpx* points, int n_points, int rule, int M, int K, size_t frames, cudaStream_t s);
 void launch_decide(cpx* out, const cpx* in, const unsigned char* active, const cpx* points, int n_points, int rule,
                    int M, int K, size_t frames, cudaStream_t s);
 void launch_phase_rotate(cpx* R, const cpx* decided, const cpx* soft, const int* smap, int n_map, int M, int K,
@@ -55,13 +59,15 @@ void launch_energy(float* out, const cpx* in, size_t n, cudaStream_t s);
 // extract_burst_cc (lib/extract_burst_cc_impl.cc:117-242): one descriptor per produced burst
 struct BurstDesc {
     long long start;       // index of the burst's first sample in the stream window (negative: zeros in front)
-    double angle;              // CFO rotation per sample (radians), = arg(inc)
-    double inc32_re, inc32_im; // cos/sin(32*angle): one warp step
-    float scale;           // power normalisation factor
+    double angle;              // CFO rotation per sample (radians), = arg(inc)        } filled on the device by
+    double inc32_re, inc32_im; // cos/sin(32*angle): one warp step                     } burst_prepare_kernel
+    float scale;               // power normalisation factor
+    float pr_re, pr_im;        // the tag's phase_rotation
     int pad;
 };
-void launch_extract_burst(cpx* out, const cpx* in, const BurstDesc* desc, int burst_len, bool cfo, int n_bursts,
-                          cudaStream_t s);
+// desc: start, scale and phase_rotation set by the host; with cfo the rotation constants are derived on the device
+// first (one more launch).  Returns the number of launches.
+int launch_extract_burst(cpx* out, const cpx* in, BurstDesc* desc, int burst_len, bool cfo, int n_bursts, cudaStream_t s);
 // symbol mapping (python/pygfdm/symbolmapping.py:27-47): chunk = constellation point index, one byte per symbol
 void launch_map_chunks(cpx* out, const unsigned char* chunks, const cpx* points, int n_points, size_t n, cudaStream_t s);
 void launch_decide_chunks(unsigned char* chunks, const cpx* in, const cpx* points, int n_points, int rule,

@@ -35,6 +35,19 @@
 
 namespace gfdm {
 
+// transmitter chain, stage C: the few output positions that carry a window ramp and/or are written twice (cyclic
+// prefix / suffix).  Out of line so that the unrolled common case stays one compare and one store.
+static __device__ __noinline__ void tx_store_edge(cpx* o, int i, cpx v, int N, int W, int ramp, const cpx* front,
+                                                  const cpx* back)
+{
+    for (; i < W; i += N) {
+        cpx val = v;
+        if (i < ramp) val = cmul_rn(val, __ldg(front + i));
+        if (i >= W - ramp) val = cmul_rn(val, __ldg(back + (i - (W - ramp))));
+        stg_stream(o + i, val);
+    }
+}
+
 // ----------------------------------------------------------------------------------------
 // Fused modulator.  in/out: [n_frames][N]; table: C_tx [M][K]; tw: W_K^{n0*k1} as [k1][n0].
 // Shared memory: R = row buffer (also holds the tail of the staged input), P = prefetch region
@@ -113,10 +126,21 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_mod_kernel(cpx* __restric
         if (bytes) bulk_load(buf, in + (size_t)gg * F * EL + PF, bytes, bar_r);
     };
     // transmitter: position of this thread's subcarrier(s) in the sorted subcarrier map (-1: unused)
-    int slot[IPT];
+    // The gather of stage A is loop invariant: staged index of timeslot 0, stride over timeslots, and how many
+    // timeslots lie inside the n_in symbols the caller supplied (the rest, and unused subcarriers, are zero).
+    int g_e0[IPT], g_mv[IPT];
+    const int g_st = tx.per_timeslot ? tx.A : 1;
     if constexpr (TXF) {
 #pragma unroll
-        for (int j = 0; j < IPT; ++j) slot[j] = __ldg(tx.inv_map + (tid + j * T) % K);
+        for (int j = 0; j < IPT; ++j) {
+            const int it = tid + j * T, f = it / K;
+            const int a = __ldg(tx.inv_map + (it - f * K));
+            const int s0 = tx.per_timeslot ? a : a * M; // src of timeslot 0
+            int mv = 0;
+            if (a >= 0 && s0 < tx.n_in) mv = min(M, (tx.n_in - s0 + g_st - 1) / g_st);
+            g_e0[j] = f * tx.n_in + s0;
+            g_mv[j] = mv;
+        }
     }
 
     int g = blockIdx.x;
@@ -156,18 +180,16 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_mod_kernel(cpx* __restric
             // a*M + m (per subcarrier) of the frame's compact vector; beyond n_in and on unused subcarriers: zero
 #pragma unroll
             for (int j = 0; j < IPT; ++j) {
-                const int f = (tid + j * T) / K, a = slot[j];
+                int e = g_e0[j];
 #pragma unroll
                 for (int m = 0; m < M; ++m) {
-                    const int src = tx.per_timeslot ? m * tx.A + a : a * M + m;
-                    const int e = f * tx.n_in + src;
                     cpx val = cmake(0.f, 0.f);
-                    if constexpr (CHK) {
-                        if (a >= 0 && src < tx.n_in) val = lookup(pre_b[e]);
-                    } else {
-                        if (a >= 0 && src < tx.n_in) val = (e < PF) ? pre[e] : buf[e - PF];
+                    if (m < g_mv[j]) {
+                        if constexpr (CHK) val = lookup(pre_b[e]);
+                        else val = (e < PF) ? pre[e] : buf[e - PF];
                     }
                     v[j][m] = val;
+                    e += g_st;
                 }
             }
         }
@@ -233,21 +255,19 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_mod_kernel(cpx* __restric
                 }
             } else if (f < fh) {
                 // add_cyclic_prefix: o[i] = x[(i + N - cp - s) mod N], i < W = N + cp + cs  <=>  sample n goes to
-                // i = (n + cp + s) mod N and again to i + N while that is < W; ramps on the first / last samples
-                const int W = N + tx.cp + tx.cs, os = tx.P + W;
+                // i = (n + cp + s) mod N and again to i + N while that is < W; ramps on the first / last samples.
+                // Positions lo <= i < hi are neither ramped nor duplicated: one compare, one store.
+                const int W = N + tx.cp + tx.cs, os = tx.P + W, dup = tx.cp + tx.cs;
+                const int lo = max(tx.ramp, dup), hi = max(lo, min(N, W - tx.ramp));
                 for (int a = 0; a < tx.n_ant; ++a) {
                     cpx* o = out + (size_t)a * tx.ant_stride + ((size_t)g * F + f) * os + tx.P;
-                    const int i0 = n1 + tx.cp + tx.shift[a];
+                    int i = (n1 + tx.cp + tx.shift[a]) % N;
 #pragma unroll
                     for (int n2 = 0; n2 < M; ++n2) {
-                        int i = i0 + n2 * K;
+                        if ((unsigned)(i - lo) < (unsigned)(hi - lo)) stg_stream(o + i, v[j][n2]);
+                        else tx_store_edge(o, i, v[j][n2], N, W, tx.ramp, tx.front, tx.back);
+                        i += K;
                         i = i >= N ? i - N : i;
-                        for (; i < W; i += N) {
-                            cpx val = v[j][n2];
-                            if (i < tx.ramp) val = cmul_rn(val, __ldg(tx.front + i));
-                            if (i >= W - tx.ramp) val = cmul_rn(val, __ldg(tx.back + (i - (W - tx.ramp))));
-                            stg_stream(o + i, val);
-                        }
                     }
                 }
             }
@@ -257,9 +277,9 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_mod_kernel(cpx* __restric
             const int os = tx.P + N + tx.cp + tx.cs;
             for (int a = 0; a < tx.n_ant; ++a) {
                 const cpx* p = tx.preambles + (size_t)tx.pre_idx[a] * tx.P;
-                for (int idx = tid; idx < fh * tx.P; idx += T) {
-                    const int f = idx / tx.P, i = idx - f * tx.P;
-                    stg_stream(out + (size_t)a * tx.ant_stride + ((size_t)g * F + f) * os + i, ldg_nc(p + i));
+                for (int f = 0; f < fh; ++f) {
+                    cpx* o = out + (size_t)a * tx.ant_stride + ((size_t)g * F + f) * os;
+                    for (int i = tid; i < tx.P; i += T) stg_stream(o + i, ldg_nc(p + i));
                 }
             }
         }

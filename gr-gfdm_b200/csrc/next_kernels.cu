@@ -69,13 +69,28 @@ __global__ void __launch_bounds__(TH) extract_burst_kernel(cpx* __restrict__ out
         }
     }
 }
-void launch_extract_burst(cpx* out, const cpx* in, const BurstDesc* desc, int burst_len, bool cfo, int n_bursts,
-                          cudaStream_t s)
+// get_phase_rotation (lib/extract_burst_cc_impl.cc:88-96): inc = conj(pr)/|pr| rounded to complex<float>; the
+// extraction kernel rotates by the angle of that number.  One thread per burst (keeps the trigonometry off the host,
+// which would otherwise pace the calls).
+__global__ void __launch_bounds__(TH) burst_prepare_kernel(BurstDesc* __restrict__ desc, int n_bursts)
 {
-    if (n_bursts <= 0) return;
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_bursts) return;
+    const float pr = desc[b].pr_re, pi = desc[b].pr_im;
+    const double scale = 1.0 / (double)hypotf(pr, pi);
+    const float ir = (float)(scale * (double)pr), ii = (float)(-1.0f * scale * (double)pi);
+    const double angle = atan2((double)ii, (double)ir);
+    desc[b].angle = angle;
+    sincos(32.0 * angle, &desc[b].inc32_im, &desc[b].inc32_re);
+}
+int launch_extract_burst(cpx* out, const cpx* in, BurstDesc* desc, int burst_len, bool cfo, int n_bursts, cudaStream_t s)
+{
+    if (n_bursts <= 0) return 0;
+    if (cfo) burst_prepare_kernel<<<blocks_for((size_t)n_bursts, TH), TH, 0, s>>>(desc, n_bursts);
     const size_t total = (size_t)n_bursts * ((burst_len + 127) / 128) * 32; // threads
     extract_burst_kernel<<<grid_for(total, TH), TH, 0, s>>>(out, in, desc, burst_len, cfo ? 1 : 0, n_bursts);
     GFDM_CUDA_CHECK(cudaGetLastError());
+    return cfo ? 2 : 1;
 }
 
 // ---------------------------------------------------------------------------------------------

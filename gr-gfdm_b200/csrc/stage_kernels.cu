@@ -7,6 +7,7 @@
 // every global store is coalesced; scatters of the reference are restated as
 // gathers (no atomics).
 #include "engine.h"
+#include "regfft.cuh"
 
 namespace gfdm {
 
@@ -150,6 +151,103 @@ void launch_ic_subtract(cpx* out, const cpx* fd, const cpx* F, const cpx* ic_tap
     if (!total) return;
     ic_subtract_kernel<<<blocks_for(total, TH), TH, 0, s>>>(out, fd, F, ic_taps, M, total);
     GFDM_CUDA_CHECK(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------
+// One interference-cancellation iteration as ONE kernel, for the shapes whose whole loop is not resident in the
+// fused receiver (lib/advanced_receiver_kernel_cc.cc:56-76 = map_symbols_to_constellation_points :109-123,
+// cancel_sc_interference lib/receiver_kernel_cc.cc:274-299, transform_subcarriers_to_td :211-225):
+//   y'_k = IFFT_M( R_k - ic (.) FFT_M( dec(y_{k-1}) + dec(y_{k+1}) ) ) / M,   dec = hard decision (0 on unused subcarriers)
+// A CTA owns SB consecutive subcarriers of one frame: their soft symbols plus one halo record either side and their
+// kept frequency blocks R are staged in shared memory with full-line accesses, thread <-> subcarrier does the two
+// M-point transforms in registers, results leave through shared memory again.  Traffic: read y and R once, write y'
+// once (24 bytes per symbol and iteration) instead of five kernels and four intermediate arrays.
+static constexpr int SB = 128;
+template <int M>
+__global__ void __launch_bounds__(SB) sic_iter_kernel(cpx* __restrict__ y_out, const cpx* __restrict__ y_in,
+                                                      const cpx* __restrict__ fb, const cpx* __restrict__ ic_taps,
+                                                      const unsigned char* __restrict__ active,
+                                                      const cpx* __restrict__ points, int n_points, int rule, int K)
+{
+    extern __shared__ __align__(16) unsigned char sic_smem[];
+    cpx* ys = reinterpret_cast<cpx*>(sic_smem); // [SB + 2][M]: record 0 = subcarrier k0-1, record SB+1 = k0+SB
+    cpx* rs = ys + (SB + 2) * M;                // [SB][M]: R in, y' out
+    __shared__ cpx pts[64];
+    __shared__ cpx ic_s[M];
+    const int tid = threadIdx.x;
+    const int blocks_per_frame = (K + SB - 1) / SB;
+    const size_t f = blockIdx.x / blocks_per_frame;
+    const int k0 = (int)(blockIdx.x - f * blocks_per_frame) * SB;
+    const int nb = min(SB, K - k0);
+    const cpx* yf = y_in + f * (size_t)K * M;
+    for (int i = tid; i < 64; i += SB) pts[i] = i < n_points ? points[i] : cmake(0.f, 0.f);
+    for (int i = tid; i < M; i += SB) ic_s[i] = ic_taps[i];
+    for (int i = tid; i < nb * M; i += SB) {
+        ys[M + i] = yf[(size_t)k0 * M + i];
+        rs[i] = fb[(f * K + k0) * (size_t)M + i];
+    }
+    const int kp = k0 == 0 ? K - 1 : k0 - 1, kn = k0 + nb >= K ? 0 : k0 + nb;
+    for (int i = tid; i < M; i += SB) {
+        ys[i] = yf[(size_t)kp * M + i];
+        ys[(nb + 1) * M + i] = yf[(size_t)kn * M + i];
+    }
+    __syncthreads();
+    if (tid < nb) {
+        const int k = k0 + tid;
+        const bool ap = active[k == 0 ? K - 1 : k - 1] != 0, an = active[k == K - 1 ? 0 : k + 1] != 0;
+        const cpx* prev = ys + tid * M;       // record of subcarrier k-1
+        const cpx* next = ys + (tid + 2) * M; // record of subcarrier k+1
+        cpx d[M];
+#pragma unroll
+        for (int m = 0; m < M; ++m) {
+            const cpx a = ap ? pts[decide_symbol(prev[m], pts, n_points, rule)] : cmake(0.f, 0.f);
+            const cpx b = an ? pts[decide_symbol(next[m], pts, n_points, rule)] : cmake(0.f, 0.f);
+            d[m] = cadd(a, b);
+        }
+        rf::FFTN<M, -1>::run(d);
+        cpx* mine = rs + tid * M;
+        const float inv_m = 1.0f / (float)M;
+#pragma unroll
+        for (int m = 0; m < M; ++m) d[m] = csub(mine[m], cmul(ic_s[m], d[m]));
+        rf::FFTN<M, +1>::run(d);
+#pragma unroll
+        for (int m = 0; m < M; ++m) mine[m] = cscale(d[m], inv_m);
+    }
+    __syncthreads();
+    cpx* of = y_out + (f * K + k0) * (size_t)M;
+    for (int i = tid; i < nb * M; i += SB) of[i] = rs[i];
+}
+template <int M>
+static void launch_sic_iter_m(cpx* y_out, const cpx* y_in, const cpx* fb, const cpx* ic_taps, const unsigned char* active,
+                              const cpx* points, int n_points, int rule, int K, size_t frames, cudaStream_t s)
+{
+    const size_t smem = sizeof(cpx) * (size_t)(2 * SB + 2) * M;
+    if (smem > 48 * 1024)
+        GFDM_CUDA_CHECK(cudaFuncSetAttribute(sic_iter_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t blocks = frames * (size_t)((K + SB - 1) / SB);
+    sic_iter_kernel<M><<<(unsigned)blocks, SB, smem, s>>>(y_out, y_in, fb, ic_taps, active, points, n_points, rule, K);
+    GFDM_CUDA_CHECK(cudaGetLastError());
+}
+bool sic_iter_supported(int M, int K, int n_points, size_t frames)
+{
+    switch (M) {
+    case 2: case 3: case 4: case 5: case 7: case 8: case 9: case 15: case 16: case 21: case 25: break;
+    default: return false;
+    }
+    return K >= 2 && n_points >= 1 && n_points <= 64 && frames * (size_t)((K + SB - 1) / SB) < ((size_t)1 << 31);
+}
+void launch_sic_iter(cpx* y_out, const cpx* y_in, const cpx* fb, const cpx* ic_taps, const unsigned char* active,
+                     const cpx* points, int n_points, int rule, int M, int K, size_t frames, cudaStream_t s)
+{
+    if (!frames) return;
+#define GFDM_SIC_CASE(MM) \
+    case MM: launch_sic_iter_m<MM>(y_out, y_in, fb, ic_taps, active, points, n_points, rule, K, frames, s); break;
+    switch (M) {
+        GFDM_SIC_CASE(2) GFDM_SIC_CASE(3) GFDM_SIC_CASE(4) GFDM_SIC_CASE(5) GFDM_SIC_CASE(7) GFDM_SIC_CASE(8)
+        GFDM_SIC_CASE(9) GFDM_SIC_CASE(15) GFDM_SIC_CASE(16) GFDM_SIC_CASE(21) GFDM_SIC_CASE(25)
+    default: throw std::invalid_argument("sic_iter: unsupported timeslot count");
+    }
+#undef GFDM_SIC_CASE
 }
 
 // map_symbols_to_constellation_points, lib/advanced_receiver_kernel_cc.cc:109-123 (decide_symbol: common.cuh)

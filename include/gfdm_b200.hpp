@@ -552,7 +552,132 @@ private:
     std::vector<int> d_cyclic_shifts;
 };
 
+// ---------------------------------------------------------------------------
+// The rows either side of the path.  The reference has them as GNU Radio blocks
+// (remove_prefix_cc, extract_burst_cc) or stock gr-digital blocks / pygfdm helpers (symbol mapping); these
+// classes are what the blocks' general_work() would own and call.
+
+// lib/remove_prefix_cc_impl.cc:44-61,84-115
+class remove_prefix : public stream_control<remove_prefix>
+{
+public:
+    typedef std::complex<float> gfdm_complex;
+    remove_prefix(int frame_len, int block_len, int offset) : d_block_len(block_len), d_frame_len(frame_len)
+    {
+        detail::check(gfdm_remove_prefix_create(d_h.out(), frame_len, block_len, offset));
+    }
+    int block_len() const { return d_block_len; }
+    int frame_len() const { return d_frame_len; }
+    void work_batch(gfdm_complex* p_out, const gfdm_complex* p_in, int n_frames, int mem = GFDM_MEM_HOST)
+    {
+        detail::check(gfdm_remove_prefix_work_batch(d_h.get(), detail::c(p_out), detail::c(p_in), n_frames, mem));
+    }
+    void* raw() const { return d_h.get(); }
+
+private:
+    detail::handle<gfdm_remove_prefix, gfdm_remove_prefix_destroy> d_h;
+    int d_block_len, d_frame_len;
+};
+
+// lib/extract_burst_cc_impl.cc:43-242; one general_work() call per work()
+class extract_burst : public stream_control<extract_burst>
+{
+public:
+    typedef std::complex<float> gfdm_complex;
+    struct result {
+        int n_produced;        // bursts written
+        long long n_consumed;  // items the block would consume_each()
+    };
+    extract_burst(int burst_len, int tag_backoff, bool activate_cfo_correction = false) : d_burst_len(burst_len)
+    {
+        detail::check(gfdm_extract_burst_create(d_h.out(), burst_len, tag_backoff, activate_cfo_correction ? 1 : 0));
+    }
+    int burst_len() const { return d_burst_len; }
+    void activate_cfo_compensation(bool on) { detail::check(gfdm_extract_burst_activate_cfo_compensation(d_h.get(), on ? 1 : 0)); }
+    // tags sorted by offset: burst_starts relative to p_in[0]; scale_factors / phase_rotations may be empty (1.0 / 1+0j)
+    result work(gfdm_complex* p_out, int max_bursts, const gfdm_complex* p_in, long long n_in,
+                const std::vector<long long>& burst_starts, const std::vector<float>& scale_factors = {},
+                const std::vector<gfdm_complex>& phase_rotations = {}, int mem = GFDM_MEM_HOST)
+    {
+        if ((!scale_factors.empty() && scale_factors.size() != burst_starts.size()) ||
+            (!phase_rotations.empty() && phase_rotations.size() != burst_starts.size()))
+            throw std::invalid_argument("tag arrays MUST have the same length");
+        result r{ 0, 0 };
+        detail::check(gfdm_extract_burst_work(d_h.get(), detail::c(p_out), max_bursts, detail::c(p_in), n_in,
+                                              burst_starts.data(), scale_factors.empty() ? nullptr : scale_factors.data(),
+                                              phase_rotations.empty() ? nullptr : detail::c(phase_rotations.data()),
+                                              (int)burst_starts.size(), &r.n_produced, &r.n_consumed, mem));
+        return r;
+    }
+    void* raw() const { return d_h.get(); }
+
+private:
+    detail::handle<gfdm_extract_burst, gfdm_extract_burst_destroy> d_h;
+    int d_burst_len;
+};
+
+// python/pygfdm/symbolmapping.py:27-47 (bits2symbols / symbols2bits), gr-digital chunks_to_symbols / constellation
+// decoder (python/qa_advanced_receiver_sb_cc.py:97-99)
+class symbol_mapper : public stream_control<symbol_mapper>
+{
+public:
+    typedef std::complex<float> gfdm_complex;
+    explicit symbol_mapper(const constellation& c)
+    {
+        const gfdm_constellation cc = { detail::c(c.points.data()), (int)c.points.size(), c.decision_rule };
+        detail::check(gfdm_symbol_mapper_create(d_h.out(), &cc));
+    }
+    int n_points() const { return gfdm_symbol_mapper_n_points(d_h.get()); }
+    int bits_per_symbol() const { return gfdm_symbol_mapper_bits_per_symbol(d_h.get()); }
+    void map_chunks(gfdm_complex* p_out, const unsigned char* chunks, size_t n_symbols, int mem = GFDM_MEM_HOST)
+    {
+        detail::check(gfdm_symbol_mapper_map_chunks_batch(d_h.get(), detail::c(p_out), chunks, n_symbols, mem));
+    }
+    void decide(unsigned char* chunks_out, const gfdm_complex* p_in, size_t n_symbols, int mem = GFDM_MEM_HOST)
+    {
+        detail::check(gfdm_symbol_mapper_decide_batch(d_h.get(), chunks_out, detail::c(p_in), n_symbols, mem));
+    }
+    void bits2symbols(gfdm_complex* p_out, const unsigned char* bits, size_t n_symbols, int mem = GFDM_MEM_HOST)
+    {
+        detail::check(gfdm_symbol_mapper_bits2symbols_batch(d_h.get(), detail::c(p_out), bits, n_symbols, mem));
+    }
+    void symbols2bits(unsigned char* bits_out, const gfdm_complex* p_in, size_t n_symbols, int mem = GFDM_MEM_HOST)
+    {
+        detail::check(gfdm_symbol_mapper_symbols2bits_batch(d_h.get(), bits_out, detail::c(p_in), n_symbols, mem));
+    }
+    // the same mapping fused into the kernels of the path (one byte per symbol on the symbol side)
+    void modulate_chunks(modulator_kernel_cc& mod, gfdm_complex* p_out, const unsigned char* chunks, int n_frames,
+                         int mem = GFDM_MEM_HOST)
+    {
+        detail::check(gfdm_modulator_work_chunks_batch(static_cast<gfdm_modulator*>(mod.raw()), d_h.get(), detail::c(p_out),
+                                                       chunks, n_frames, mem));
+    }
+    void transmit_chunks(transmitter_kernel& tx, gfdm_complex* p_out, const unsigned char* chunks, int ninput_size,
+                         int n_frames, int mem = GFDM_MEM_HOST)
+    {
+        detail::check(gfdm_transmitter_work_chunks_batch(static_cast<gfdm_transmitter*>(tx.raw()), d_h.get(),
+                                                         detail::c(p_out), chunks, ninput_size, n_frames, mem));
+    }
+    void demodulate_decide(receiver_kernel_cc& rx, unsigned char* chunks_out, const gfdm_complex* p_in,
+                           const gfdm_complex* f_eq_in, int n_frames, int mem = GFDM_MEM_HOST)
+    {
+        detail::check(gfdm_receiver_work_decide_batch(static_cast<gfdm_receiver*>(rx.raw()), d_h.get(), chunks_out,
+                                                      detail::c(p_in), detail::c(f_eq_in), n_frames, mem));
+    }
+    void demap_chunks(resource_mapper_kernel_cc& mapper, unsigned char* p_out, const unsigned char* p_in,
+                      size_t size_per_frame, int n_frames, int mem = GFDM_MEM_HOST)
+    {
+        detail::check(gfdm_resource_mapper_demap_chunks_batch(static_cast<gfdm_resource_mapper*>(mapper.raw()), p_out, p_in,
+                                                              size_per_frame, n_frames, mem));
+    }
+    void* raw() const { return d_h.get(); }
+
+private:
+    detail::handle<gfdm_symbol_mapper, gfdm_symbol_mapper_destroy> d_h;
+};
+
 } // namespace gfdm
 } // namespace gr
+
 
 #endif /* INCLUDED_GFDM_B200_HPP */

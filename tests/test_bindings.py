@@ -89,7 +89,10 @@ int main(int argc, char** argv)
     try { modulator_kernel_cc m(6, 16, 2, std::vector<cf>(10, cf(1, 0))); } catch (const std::invalid_argument&) { ++caught; }
     try { receiver_kernel_cc r(5, 16, 1, std::vector<cf>(5, cf(1, 0))); } catch (const std::invalid_argument&) { ++caught; }
     try { resource_mapper_kernel_cc r(5, 32, 4, { 1, 2, 2, 3 }, true); } catch (const std::invalid_argument&) { ++caught; }
-    if (caught != 3) { printf("FAIL exceptions %d\n", caught); return 1; }
+    try { remove_prefix r(100, 90, 11); } catch (const std::invalid_argument&) { ++caught; }
+    try { extract_burst e(0, 0); } catch (const std::invalid_argument&) { ++caught; }
+    try { symbol_mapper s(constellation{ std::vector<cf>(5, cf(1, 0)), GFDM_DECISION_QPSK_SIGN }); } catch (const std::invalid_argument&) { ++caught; }
+    if (caught != 6) { printf("FAIL exceptions %d\n", caught); return 1; }
     if (argc < 4) { printf("OK exceptions\n"); return 0; }
     // round trip on the device: argv[1] taps (M*L cf), argv[2] symbols (N cf) -> argv[3] soft symbols
     const int M = 5, K = 16, L = 2, N = M * K;
@@ -110,6 +113,32 @@ int main(int argc, char** argv)
     double err = 0, nrm = 0;   // the 2-D path runs the stages separately: same result up to fp32 rounding
     for (int i = 0; i < N; ++i) { err += std::norm(y[i] - y2[i]); nrm += std::norm(y[i]); }
     if (!(err <= 1e-10 * nrm)) { printf("FAIL legacy 2-D path differs (%g)\n", err / nrm); return 3; }
+    // rows either side of the path: chunks -> modulate == lookup -> modulate; decisions == deciding the soft symbols;
+    // remove_prefix / extract_burst copy what they should
+    {
+        symbol_mapper sm(constellation::qpsk());
+        std::vector<unsigned char> ch(N), dec(N), dec2(N);
+        for (int i = 0; i < N; ++i) ch[i] = (unsigned char)((i * 7 + 3) % 4);
+        std::vector<cf> s1(N), x1(N), x2(N), soft(N);
+        sm.map_chunks(s1.data(), ch.data(), N);
+        mod.generic_work(x1.data(), s1.data());
+        sm.modulate_chunks(mod, x2.data(), ch.data(), 1);
+        if (memcmp(x1.data(), x2.data(), sizeof(cf) * N)) { printf("FAIL modulate_chunks\n"); return 4; }
+        sm.demodulate_decide(dem, dec.data(), x2.data(), nullptr, 1);
+        dem.generic_work(soft.data(), x2.data());
+        sm.decide(dec2.data(), soft.data(), N);
+        if (memcmp(dec.data(), dec2.data(), N)) { printf("FAIL demodulate_decide\n"); return 4; }
+        remove_prefix rp(N + 12, N, 8);
+        std::vector<cf> fr(2 * (N + 12)), blk(2 * N);
+        for (size_t i = 0; i < fr.size(); ++i) fr[i] = cf((float)i, -(float)i);
+        rp.work_batch(blk.data(), fr.data(), 2);
+        if (blk[0] != fr[8] || blk[N] != fr[N + 12 + 8] || blk[2 * N - 1] != fr[N + 12 + 8 + N - 1]) { printf("FAIL remove_prefix\n"); return 4; }
+        extract_burst eb(16, 2);
+        std::vector<cf> bursts(2 * 16);
+        extract_burst::result r = eb.work(bursts.data(), 2, fr.data(), (long long)fr.size(), { 1, 40 }, { 2.0f, 0.5f });
+        if (r.n_produced != 2 || r.n_consumed != 56 || bursts[0] != cf(0, 0) || bursts[1] != fr[0] * 2.0f || bursts[16] != fr[38] * 0.5f) {
+            printf("FAIL extract_burst %d %lld\n", r.n_produced, r.n_consumed); return 4; }
+    }
     f = fopen(argv[3], "wb"); fwrite(y.data(), sizeof(cf), y.size(), f); fclose(f);
     printf("OK %d launches\n", (int)(mod.launch_count() + dem.launch_count()));
     return 0;

@@ -20,7 +20,13 @@ PEAK = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))).get('hbm_gbs',
 stream = torch.cuda.Stream()
 
 
-def timed(fn, steps=10, warmup=3):
+STEPS = int(os.environ.get('CHAIN_STEPS', '10'))   # 1 under ncu
+WARMUP = int(os.environ.get('CHAIN_WARMUP', '3'))
+
+
+def timed(fn, steps=None, warmup=None):
+    steps = STEPS if steps is None else steps
+    warmup = WARMUP if warmup is None else warmup
     with torch.cuda.stream(stream):
         for _ in range(warmup):
             fn()
