@@ -95,31 +95,40 @@ int launch_extract_burst(cpx* out, const cpx* in, BurstDesc* desc, int burst_len
 
 // ---------------------------------------------------------------------------------------------
 // symbol mapping.  The constellation (<= 256 points) sits in shared memory.
+// Both directions walk the symbols in tiles of TILE = 16*TH: the byte side of a tile moves as one 16-byte access per
+// thread (when the tile is 16-byte aligned in memory), the complex side as 16 accesses per thread with consecutive
+// lanes on consecutive symbols (256-byte lines, 16 independent requests in flight), shared memory in between.
+static constexpr int TILE = 16 * TH;
+
 __global__ void __launch_bounds__(TH) map_chunks_kernel(cpx* __restrict__ out, const unsigned char* __restrict__ chunks,
                                                         const cpx* __restrict__ points, int n_points, size_t n)
 {
     __shared__ cpx pts[256];
+    __shared__ __align__(16) unsigned char tile[TILE];
     for (int i = threadIdx.x; i < 256; i += TH) pts[i] = i < n_points ? points[i] : cmake(0.f, 0.f);
-    __syncthreads();
-    // two symbols per thread where the addresses allow a 16-bit load and a 16-byte store (consecutive lanes write
-    // consecutive 16-byte units: every store instruction fills whole lines); head and tail go one by one
-    const bool vec = (reinterpret_cast<uintptr_t>(out) & 15) == ((reinterpret_cast<uintptr_t>(chunks) & 1) ? 8u : 0u);
-    const size_t h0 = vec ? (reinterpret_cast<uintptr_t>(chunks) & 1) : n;
-    const size_t h = h0 < n ? h0 : n;
-    const size_t pairs = (n - h) / 2;
-    const size_t stride = (size_t)gridDim.x * blockDim.x, tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    for (size_t q = tid; q < pairs; q += stride) {
-        const unsigned w = *reinterpret_cast<const unsigned short*>(chunks + h + 2 * q);
-        const cpx a = pts[w & 255u], b = pts[w >> 8];
-        *reinterpret_cast<float4*>(out + h + 2 * q) = make_float4(a.x, a.y, b.x, b.y);
+    const bool vec = (reinterpret_cast<uintptr_t>(chunks) & 15) == 0; // tiles start at multiples of 4096
+    const size_t n_tiles = (n + TILE - 1) / TILE;
+    for (size_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const size_t base = t * TILE;
+        const int cnt = (int)(n - base < (size_t)TILE ? n - base : (size_t)TILE);
+        __syncthreads(); // the previous tile has been consumed (and pts is in place)
+        if (vec && cnt == TILE) {
+            reinterpret_cast<uint4*>(tile)[threadIdx.x] = reinterpret_cast<const uint4*>(chunks + base)[threadIdx.x];
+        } else {
+            for (int i = threadIdx.x; i < cnt; i += TH) tile[i] = chunks[base + i];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int i = threadIdx.x + j * TH;
+            if (i < cnt) out[base + i] = pts[tile[i]];
+        }
     }
-    for (size_t i = tid; i < h; i += stride) out[i] = pts[chunks[i]];
-    for (size_t i = h + 2 * pairs + tid; i < n; i += stride) out[i] = pts[chunks[i]];
 }
 void launch_map_chunks(cpx* out, const unsigned char* chunks, const cpx* points, int n_points, size_t n, cudaStream_t s)
 {
     if (!n) return;
-    map_chunks_kernel<<<grid_for((n + 1) / 2, TH), TH, 0, s>>>(out, chunks, points, n_points, n);
+    map_chunks_kernel<<<grid_for((n + 15) / 16, TH), TH, 0, s>>>(out, chunks, points, n_points, n);
     GFDM_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -129,28 +138,37 @@ __global__ void __launch_bounds__(TH) decide_chunks_kernel(unsigned char* __rest
 {
     __shared__ cpx pts[256];
     __shared__ unsigned char lut[64];
+    __shared__ __align__(16) unsigned char tile[TILE];
     for (int i = threadIdx.x; i < 256; i += TH) pts[i] = i < n_points ? points[i] : cmake(0.f, 0.f);
     if (threadIdx.x < 64) lut[threadIdx.x] = grid.lut[threadIdx.x];
-    __syncthreads();
-    const size_t head = ((4 - (reinterpret_cast<uintptr_t>(chunks) & 3)) & 3);
-    const size_t h = head < n ? head : n;
-    const size_t quads = (n - h) / 4;
-    const size_t stride = (size_t)gridDim.x * blockDim.x, tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    for (size_t q = tid; q < quads; q += stride) {
-        const cpx* x = in + h + 4 * q;
-        uint32_t w = 0;
+    const bool vec = (reinterpret_cast<uintptr_t>(chunks) & 15) == 0;
+    const size_t n_tiles = (n + TILE - 1) / TILE;
+    for (size_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const size_t base = t * TILE;
+        const int cnt = (int)(n - base < (size_t)TILE ? n - base : (size_t)TILE);
+        cpx x[16];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) w |= (uint32_t)decide_symbol_grid(x[j], pts, n_points, rule, grid, lut) << (8 * j);
-        *reinterpret_cast<uint32_t*>(chunks + h + 4 * q) = w;
+        for (int j = 0; j < 16; ++j) {
+            const int i = threadIdx.x + j * TH;
+            x[j] = i < cnt ? ldg_stream_cpx(in + base + i) : cmake(0.f, 0.f);
+        }
+        __syncthreads(); // the previous tile has been written out (and pts / lut are in place)
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            tile[threadIdx.x + j * TH] = (unsigned char)decide_symbol_grid(x[j], pts, n_points, rule, grid, lut);
+        __syncthreads();
+        if (vec && cnt == TILE) {
+            reinterpret_cast<uint4*>(chunks + base)[threadIdx.x] = reinterpret_cast<const uint4*>(tile)[threadIdx.x];
+        } else {
+            for (int i = threadIdx.x; i < cnt; i += TH) chunks[base + i] = tile[i];
+        }
     }
-    for (size_t i = tid; i < h; i += stride) chunks[i] = (unsigned char)decide_symbol_grid(in[i], pts, n_points, rule, grid, lut);
-    for (size_t i = h + 4 * quads + tid; i < n; i += stride) chunks[i] = (unsigned char)decide_symbol_grid(in[i], pts, n_points, rule, grid, lut);
 }
 void launch_decide_chunks(unsigned char* chunks, const cpx* in, const cpx* points, int n_points, int rule,
                           const DecideGrid& grid, size_t n, cudaStream_t s)
 {
     if (!n) return;
-    decide_chunks_kernel<<<grid_for((n + 3) / 4, TH), TH, 0, s>>>(chunks, in, points, n_points, rule, grid, n);
+    decide_chunks_kernel<<<grid_for((n + 15) / 16, TH), TH, 0, s>>>(chunks, in, points, n_points, rule, grid, n);
     GFDM_CUDA_CHECK(cudaGetLastError());
 }
 

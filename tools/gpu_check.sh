@@ -19,3 +19,9 @@ echo "== ncu full"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:fused_ -s 6 -c 2 -f -o $OUT/${TAG}_fused \
     python bench.py --steps 1 --warmup 3 --no-cpu --no-e2e > $OUT/${TAG}_full_bench.log 2>&1
 ls -la $OUT
+echo "== per-row chain bench"
+timeout 600 python tools/chain_bench.py tx rx copy next > $OUT/${TAG}_chain_bench.jsonl 2> $OUT/${TAG}_chain_bench.err
+rm -f $OUT/${TAG}_fused.ncu-rep.tmp
+# the full ncu report is summarised on the box as well (tools/ncu_summary.py), in case it is too large to travel
+ncu -i $OUT/${TAG}_fused.ncu-rep --page raw --csv > $OUT/${TAG}_fused_raw.csv 2>/dev/null && python tools/ncu_summary.py $OUT/${TAG}_fused_raw.csv > $OUT/${TAG}_c3_fused_ncu_full.txt
+ls -la $OUT | tail -30
