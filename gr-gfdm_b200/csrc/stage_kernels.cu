@@ -388,11 +388,57 @@ __global__ void __launch_bounds__(TH) demap_kernel(cpx* __restrict__ out, const 
     for (int j = 0; j < EPT; ++j)
         if (gid0 + (size_t)j * TH < total) out[dst[j]] = v[j];
 }
+// per-timeslot order is a transpose between the grid ([k][t]) and the compact vector ([t][a]).  For wide grids a CTA
+// moves a tile of TS slots through shared memory so that both sides see contiguous runs (grid side: whole records,
+// compact side: TS consecutive slots of one timeslot); measured on B200: 56.6 -> 65 % of the copy roofline at K = 1024,
+// but slower than the 4-elements-per-thread gather for small grids (K = 64: 85 -> 50 %), hence the K >= 512 switch.
+// The same tiling gained nothing for map_to_resources (73 -> 74 %) and is not used there.
+static constexpr int TS = 64;
+__global__ void __launch_bounds__(TH) demap_tiled_kernel(cpx* __restrict__ out, const cpx* __restrict__ in,
+                                                         const int* __restrict__ smap, int M, int K, int A, size_t n_out,
+                                                         size_t out_stride)
+{
+    extern __shared__ __align__(16) unsigned char map_smem[];
+    cpx* tile = reinterpret_cast<cpx*>(map_smem); // [TS][M]
+    __shared__ int sub[TS];
+    const int tiles = (A + TS - 1) / TS;
+    const size_t f = blockIdx.x / tiles;
+    const int a0 = (int)(blockIdx.x - f * tiles) * TS;
+    const int na = min(TS, A - a0);
+    if ((int)threadIdx.x < TS) sub[threadIdx.x] = (int)threadIdx.x < na ? smap[a0 + threadIdx.x] : 0;
+    __syncthreads();
+    const cpx* src = in + f * (size_t)M * K;
+    // records of the tile's subcarriers: consecutive threads on consecutive elements of a record
+    int j = threadIdx.x / M, t = threadIdx.x - j * M;
+    const int qj = (int)TH / M, rt = (int)TH - qj * M;
+    for (int i = threadIdx.x; i < na * M; i += TH) {
+        tile[i] = src[(size_t)sub[j] * M + t];
+        t += rt;
+        j += qj;
+        if (t >= M) {
+            t -= M;
+            ++j;
+        }
+    }
+    __syncthreads();
+    cpx* dst = out + f * out_stride;
+    for (int i = threadIdx.x; i < M * TS; i += TH) {
+        const int tt = i / TS, jj = i - tt * TS;
+        const size_t e = (size_t)tt * A + a0 + jj;
+        if (jj < na && e < n_out) dst[e] = tile[jj * M + tt];
+    }
+}
 void launch_demap(cpx* out, const cpx* in, const int* smap, int M, int K, int A, bool per_timeslot, size_t n_out,
                   size_t out_stride, size_t frames, cudaStream_t s)
 {
     const size_t total = frames * n_out;
     if (!total) return;
+    const size_t tiled_blocks = frames * (size_t)((A + TS - 1) / TS);
+    if (per_timeslot && K >= 512 && M <= 96 && A > 0 && tiled_blocks < ((size_t)1 << 31)) {
+        demap_tiled_kernel<<<(unsigned)tiled_blocks, TH, sizeof(cpx) * TS * M, s>>>(out, in, smap, M, K, A, n_out, out_stride);
+        GFDM_CUDA_CHECK(cudaGetLastError());
+        return;
+    }
     demap_kernel<<<blocks_ept(total), TH, 0, s>>>(out, in, smap, M, K, A, per_timeslot ? 1 : 0, n_out, out_stride,
                                                       total);
     GFDM_CUDA_CHECK(cudaGetLastError());
