@@ -664,7 +664,7 @@ __device__ __forceinline__ void stg_stream_cpx(cpx* p, cpx v)
 
 // ---------------------------------------------------------------------------
 // estimate_frame (:285-294) as ONE kernel for power-of-two fft_len: a CTA keeps a frame's preamble halves in shared
-// memory, runs both K-point transforms there (Stockham autosort, radix 2, twiddles from the double-precision table),
+// memory, runs both K-point transforms there (Stockham autosort, radix 4 (+ one radix-2 pass), double-precision twiddle table),
 // forms H, the 9-tap filtered estimate, and streams the N interpolated bins out -- 8*(2K + N) bytes of HBM traffic
 // per frame, against four kernels with three intermediate arrays.  Arithmetic after the transforms is the unfused
 // fp32 of the stage kernels above (same bits); grid-stride over frames, CTAs sized by occupancy.
@@ -676,6 +676,7 @@ __global__ void __launch_bounds__(TH) est_fused_kernel(cpx* __restrict__ frame, 
     extern __shared__ __align__(16) unsigned char est_smem[];
     cpx* xa = reinterpret_cast<cpx*>(est_smem); // [2][K] ping
     cpx* xb = xa + 2 * K;                       // [2][K] pong; later H [K] and filt [A+off]
+    cpx* tws = xb + 2 * K;                      // [K] twiddles W_K^e
     const int tid = threadIdx.x;
     const int N = M * K, n_est = A + off, half = n_est / 2;
     const int center = N / 2, dead_half = M * (K - A) / 2;
@@ -683,27 +684,57 @@ __global__ void __launch_bounds__(TH) est_fused_kernel(cpx* __restrict__ frame, 
 #pragma unroll
     for (int t = 0; t < 9; ++t) gt[t] = g[t];
     const int so0 = tid / M, j0 = tid - so0 * M, qTH = (int)TH / M, rTH = (int)TH - qTH * M; // walk of the interpolation loops
+    for (int i = tid; i < K; i += TH) tws[i] = tw[i];
     for (size_t f = blockIdx.x; f < frames; f += gridDim.x) {
         const cpx* in = rx + f * 2 * (size_t)K;
         for (int i = tid; i < 2 * K; i += TH) xa[i] = in[i];
         __syncthreads();
-        // both transforms at once: butterfly index j < K/2 of half h
+        // both transforms at once (half h = which preamble half).  Radix-4 Stockham passes while they fit, one radix-2
+        // pass at the end for K = 2 * 4^n; twiddles W_K^e from the shared-memory copy of the double-precision table
         cpx* src = xa;
         cpx* dst = xb;
-        for (int Ns = 1; Ns < K; Ns <<= 1) {
+        int Ns = 1;
+        const int Q = K / 4;
+        // radix 4 pays when a pass keeps every thread busy (2*K/4 >= TH butterflies); measured on B200: K = 1024
+        // 0.194 -> 0.175 ms, but K = 256 0.208 -> 0.272 ms, so short transforms stay on radix 2
+        for (; K >= 2 * (int)TH && Ns * 4 <= K; Ns <<= 2) {
+            const int sh = K / (4 * Ns);
+            for (int w = tid; w < 2 * Q; w += TH) {
+                const int h = w >= Q, j = w - h * Q;
+                const int k = j & (Ns - 1);
+                const cpx* x = src + h * K + j;
+                const cpx v0 = x[0];
+                const cpx v1 = cmul(x[Q], tws[k * sh]);
+                const cpx v2 = cmul(x[2 * Q], tws[2 * k * sh]);
+                const cpx v3 = cmul(x[3 * Q], tws[3 * k * sh]);
+                const cpx a = cadd(v0, v2), b = csub(v0, v2), c = cadd(v1, v3);
+                const cpx t = csub(v1, v3);
+                const cpx d = cmake(t.y, -t.x); // -j (v1 - v3)
+                cpx* y = dst + h * K + ((j - k) << 2) + k;
+                y[0] = cadd(a, c);
+                y[Ns] = cadd(b, d);
+                y[2 * Ns] = csub(a, c);
+                y[3 * Ns] = csub(b, d);
+            }
+            __syncthreads();
+            cpx* t2 = src;
+            src = dst;
+            dst = t2;
+        }
+        for (; Ns < K; Ns <<= 1) {
             for (int w = tid; w < K; w += TH) {
                 const int h = w >= K / 2, j = w - h * (K / 2);
                 const int k = j & (Ns - 1);
                 const cpx a = src[h * K + j];
-                const cpx b = cmul(src[h * K + j + K / 2], tw[k * (K / (2 * Ns))]);
+                const cpx b = cmul(src[h * K + j + K / 2], tws[k * (K / (2 * Ns))]);
                 const int j0 = ((j - k) << 1) + k;
                 dst[h * K + j0] = cadd(a, b);
                 dst[h * K + j0 + Ns] = csub(a, b);
             }
             __syncthreads();
-            cpx* t = src;
+            cpx* t2 = src;
             src = dst;
-            dst = t;
+            dst = t2;
         }
         // H = F0 * inv0 + F1 * inv1 (:121-143) -> dst[0..K)
         for (int q = tid; q < K; q += TH) {
@@ -763,7 +794,7 @@ void launch_est_fused(cpx* frame, const cpx* rx, const cpx* tw, const cpx* inv0,
                       int K, int A, int dc_free, size_t frames, cudaStream_t s)
 {
     if (!frames) return;
-    const size_t smem = sizeof(cpx) * 4 * (size_t)K;
+    const size_t smem = sizeof(cpx) * 5 * (size_t)K;
     static int sms = 0;
     if (!sms) {
         int dev = 0;
