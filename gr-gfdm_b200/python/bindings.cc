@@ -376,4 +376,98 @@ PYBIND11_MODULE(gfdm_python, m)
             });
             return result;
         });
+
+    // ------------------------------------------------------------------ rows either side of the path
+    typedef py::array_t<unsigned char, py::array::c_style | py::array::forcecast> barray;
+    py::class_<symbol_mapper>(m, "Symbol_mapper")
+        .def(py::init([](std::vector<cf> points, int decision_rule) {
+                 constellation c{ std::move(points), decision_rule };
+                 if (c.points.empty()) c = constellation::qpsk();
+                 return new symbol_mapper(c);
+             }),
+             py::arg("constellation_points") = std::vector<cf>(), py::arg("decision_rule") = (int)GFDM_DECISION_NEAREST)
+        .def("n_points", &symbol_mapper::n_points)
+        .def("bits_per_symbol", &symbol_mapper::bits_per_symbol)
+        .def("map_chunks",
+             [](symbol_mapper& self, const barray chunks) {
+                 py::buffer_info b = chunks.request();
+                 auto result = py::array_t<cf>(b.size);
+                 cf* out = static_cast<cf*>(result.request().ptr);
+                 nogil([&] { self.map_chunks(out, static_cast<const unsigned char*>(b.ptr), (size_t)b.size); });
+                 return result;
+             })
+        .def("decide",
+             [](symbol_mapper& self, const carray symbols) {
+                 py::buffer_info b = symbols.request();
+                 auto result = py::array_t<unsigned char>(b.size);
+                 unsigned char* out = static_cast<unsigned char*>(result.request().ptr);
+                 nogil([&] { self.decide(out, static_cast<const cf*>(b.ptr), (size_t)b.size); });
+                 return result;
+             })
+        .def("bits2symbols",
+             [](symbol_mapper& self, const barray bits) {
+                 py::buffer_info b = bits.request();
+                 const int bps = self.bits_per_symbol() > 0 ? self.bits_per_symbol() : 1;
+                 if (b.size % bps) throw std::runtime_error("number of bits MUST be a multiple of bits_per_symbol!");
+                 auto result = py::array_t<cf>(b.size / bps);
+                 self.bits2symbols(static_cast<cf*>(result.request().ptr), static_cast<const unsigned char*>(b.ptr),
+                                   (size_t)(b.size / bps));
+                 return result;
+             })
+        .def("symbols2bits",
+             [](symbol_mapper& self, const carray symbols) {
+                 py::buffer_info b = symbols.request();
+                 const int bps = self.bits_per_symbol() > 0 ? self.bits_per_symbol() : 1;
+                 auto result = py::array_t<unsigned char>(b.size * bps);
+                 self.symbols2bits(static_cast<unsigned char*>(result.request().ptr), static_cast<const cf*>(b.ptr),
+                                   (size_t)b.size);
+                 return result;
+             })
+        .def("modulate_chunks_batch",
+             [](symbol_mapper& self, modulator_kernel_cc& mod, const barray chunks) {
+                 py::buffer_info b = chunks.request();
+                 if (b.ndim != 2 || b.shape[1] != mod.block_size())
+                     throw std::runtime_error("Only TWO-dimensional arrays [n_frames][block_size] allowed!");
+                 auto result = out_2d(b.shape[0], mod.block_size());
+                 cf* out = static_cast<cf*>(result.request().ptr);
+                 nogil([&] { self.modulate_chunks(mod, out, static_cast<const unsigned char*>(b.ptr), (int)b.shape[0]); });
+                 return result;
+             })
+        .def("demodulate_decide_batch", [](symbol_mapper& self, receiver_kernel_cc& rx, const carray array) {
+            py::buffer_info b = array.request();
+            const py::ssize_t n = frames_2d(b, rx.block_size(), "Demodulator.block_size");
+            auto result = py::array_t<unsigned char>(std::vector<py::ssize_t>{ n, (py::ssize_t)rx.block_size() });
+            unsigned char* out = static_cast<unsigned char*>(result.request().ptr);
+            nogil([&] { self.demodulate_decide(rx, out, static_cast<const cf*>(b.ptr), nullptr, (int)n); });
+            return result;
+        });
+
+    py::class_<remove_prefix>(m, "Remove_prefix")
+        .def(py::init<int, int, int>(), py::arg("frame_len"), py::arg("block_len"), py::arg("offset"))
+        .def("work_batch", [](remove_prefix& self, const carray array) {
+            py::buffer_info b = array.request();
+            const py::ssize_t n = frames_2d(b, self.frame_len(), "Remove_prefix.frame_len");
+            auto result = out_2d(n, self.block_len());
+            cf* out = static_cast<cf*>(result.request().ptr);
+            nogil([&] { self.work_batch(out, static_cast<const cf*>(b.ptr), (int)n); });
+            return result;
+        });
+
+    py::class_<extract_burst>(m, "Extract_burst")
+        .def(py::init<int, int, bool>(), py::arg("burst_len"), py::arg("tag_backoff"),
+             py::arg("activate_cfo_correction") = false)
+        .def("activate_cfo_compensation", &extract_burst::activate_cfo_compensation)
+        .def("work",
+             [](extract_burst& self, const carray stream, std::vector<long long> burst_starts, std::vector<float> scale_factors,
+                std::vector<cf> phase_rotations) {
+                 py::buffer_info b = stream.request();
+                 const py::ssize_t mb = (py::ssize_t)burst_starts.size();
+                 auto bursts = out_2d(mb > 0 ? mb : 1, self.burst_len());
+                 extract_burst::result r = self.work(static_cast<cf*>(bursts.request().ptr), (int)mb,
+                                                     static_cast<const cf*>(b.ptr), (long long)b.size, burst_starts,
+                                                     scale_factors, phase_rotations);
+                 return py::make_tuple(bursts, r.n_produced, r.n_consumed);
+             },
+             py::arg("stream"), py::arg("burst_starts"), py::arg("scale_factors") = std::vector<float>(),
+             py::arg("phase_rotations") = std::vector<cf>());
 }

@@ -268,3 +268,43 @@ def test_advanced_receiver_binding(gp, port):
     ar.set_ic(1)
     oar.set_ic(1)
     assert_complex_close(ar.demodulate_batch(np.stack([x, x])), oar.demodulate_batch(np.stack([x, x])), what='adv batch')
+
+
+def test_pybind_new_rows_validate_before_device_use(gp):
+    with pytest.raises(ValueError, match='MUST NOT exceed frame_len'):
+        gp.Remove_prefix(100, 90, 11)
+    with pytest.raises(ValueError, match='burst_len MUST be positive'):
+        gp.Extract_burst(0, 0)
+    with pytest.raises(ValueError, match='QPSK sign rule needs exactly 4'):
+        gp.Symbol_mapper([1, -1], 1)
+
+
+@pytest.mark.gpu
+def test_pybind_rows_either_side_of_the_path(gp, port):
+    """Symbol_mapper / Remove_prefix / Extract_burst of the pybind11 module against the oracle (ctypes)."""
+    rng = np.random.default_rng(21)
+    pts = design.qam16_points().astype(np.complex64)
+    sm, so = gp.Symbol_mapper(pts, 0), capi.Symbol_mapper((pts, 0), lib=port)
+    assert sm.n_points() == 16 and sm.bits_per_symbol() == 4
+    chunks = rng.integers(0, 16, 999).astype(np.uint8)
+    sym = sm.map_chunks(chunks)
+    assert np.array_equal(sym, so.map_chunks(chunks))
+    noisy = sym + 0.2 * (rng.standard_normal(999) + 1j * rng.standard_normal(999)).astype(np.complex64)
+    assert np.array_equal(sm.decide(noisy), so.decide(noisy))
+    bits = rng.integers(0, 2, 4 * 64).astype(np.uint8)
+    assert np.array_equal(sm.bits2symbols(bits), so.bits2symbols(bits))
+    assert np.array_equal(sm.symbols2bits(noisy[:64]), so.symbols2bits(noisy[:64]))
+    M, K, L = 9, 64, 2
+    taps = design.get_frequency_domain_filter('rrc', .5, M, K, L)
+    mod, rx = gp.Modulator(M, K, L, taps), gp.Demodulator(M, K, L, np.conj(taps))
+    ch = rng.integers(0, 16, (5, M * K)).astype(np.uint8)
+    x = sm.modulate_chunks_batch(mod, ch)
+    assert np.array_equal(x, mod.modulate_batch(sm.map_chunks(ch.ravel()).reshape(5, -1)))
+    dec = sm.demodulate_decide_batch(rx, x)
+    assert np.array_equal(dec, sm.decide(rx.demodulate_batch(x).ravel()).reshape(5, -1))
+    frames = (rng.standard_normal((4, 100)) + 1j * rng.standard_normal((4, 100))).astype(np.complex64)
+    assert np.array_equal(gp.Remove_prefix(100, 80, 12).work_batch(frames), frames[:, 12:92])
+    stream = frames.ravel()
+    bursts, produced, consumed = gp.Extract_burst(32, 4).work(stream, [2, 100, 390], [2.0, 1.0, 0.5])
+    ob, oc = capi.Extract_burst(32, 4, lib=port).work(stream, [2, 100, 390], [2.0, 1.0, 0.5])
+    assert produced == ob.shape[0] == 2 and consumed == oc and np.array_equal(bursts[:produced], ob)
