@@ -32,6 +32,56 @@
 namespace gfdm {
 
 // ----------------------------------------------------------------------------------------
+// Loop-invariant table columns of a thread in tensor memory (see fused_dev.cuh): 4 sets of 2M 32-bit columns per
+// thread, T = 512 threads -> 4 thread groups per lane quarter -> 4 * 4 * 2M = 480 of the 512 columns.  The two-pass
+// kernels have no MMA and run one CTA per SM, so the whole tensor memory is theirs; the table reads leave L2 and the
+// long-scoreboard stalls they caused in the step loops go with them.
+template <class S>
+struct Tmem4 {
+    static constexpr int SET = 2 * S::M;
+    static constexpr int PER_THREAD = 4 * SET;
+    static constexpr int COLS = 512;
+    static_assert(((S::T / 32 + 3) / 4) * PER_THREAD <= COLS, "table columns do not fit in tensor memory");
+    // col(set, m) of this thread <- src(set, m); returns the allocation base and this thread's first column
+    template <class Src>
+    static __device__ __forceinline__ void setup(uint32_t* slot, int tid, uint32_t& base, uint32_t& mine, Src src)
+    {
+        if (tid < 32) tmem_alloc(slot, COLS);
+        tmem_fence_before_sync();
+        __syncthreads();
+        tmem_fence_after_sync();
+        base = *slot;
+        mine = base + ((uint32_t)(((tid >> 5) & 3) * 32) << 16) + (uint32_t)(tid >> 7) * PER_THREAD;
+#pragma unroll
+        for (int set = 0; set < 4; ++set) {
+            float tf[SET];
+#pragma unroll
+            for (int m = 0; m < S::M; ++m) {
+                const cpx c = src(set, m);
+                tf[2 * m] = c.x;
+                tf[2 * m + 1] = c.y;
+            }
+            tmem_st<SET>(mine + set * SET, tf);
+        }
+        tmem_wait_st();
+    }
+    static __device__ __forceinline__ void load(cpx (&tc)[S::M], uint32_t mine, int set)
+    {
+        float tf[SET];
+        tmem_ld<SET>(tf, mine + set * SET);
+        tmem_wait_ld();
+#pragma unroll
+        for (int m = 0; m < S::M; ++m) tc[m] = cmake(tf[2 * m], tf[2 * m + 1]);
+    }
+    static __device__ __forceinline__ void release(uint32_t base, int tid)
+    {
+        tmem_fence_before_sync();
+        __syncthreads();
+        if (tid < 32) tmem_dealloc(base, COLS);
+    }
+};
+
+// ----------------------------------------------------------------------------------------
 // modulator.  in/out: [n_frames][N], N = M*2*K1; tableP: [2][M][K1] = C_tx[m][2n'+p]; tw: row-FFT
 // twiddles of the K1-point transform; w2: W^{b'} = e^{+j2pi b'/K}, b' < K1.
 // Pieces of the staged frame (T*M elements each): LO0 = k < T, LO1 = T <= k < K1, HI0 = K1 <= k < K1+T,
@@ -66,6 +116,11 @@ __global__ void __launch_bounds__(S::T, 1) fused_mod2_kernel(cpx* __restrict__ o
         mbar_init(bar_l, 1);
     }
     const cpx wj0 = w2[tid], wj1 = w2[tid + T];
+    // table columns C_tx[m][2n'+p] of this thread's two items, both passes: set = 2*p + j
+    uint32_t tmem_base = 0, tmem_mine = 0;
+    Tmem4<S>::setup(reinterpret_cast<uint32_t*>(bars + 3), tid, tmem_base, tmem_mine, [&](int set, int m) {
+        return ldg_nc(tableP + ((size_t)(set >> 1) * M + m) * K1 + tid + (set & 1) * T);
+    });
     // the frame is read twice (pass 0 keeps it in L2, pass 1 releases it); the even samples of pass 0
     // wait in this CTA's L2-resident scratch so that pass 1 can write whole 16-byte sample pairs
     // (the policies are re-created where they are used: one instruction each, no live registers)
@@ -163,10 +218,8 @@ __global__ void __launch_bounds__(S::T, 1) fused_mod2_kernel(cpx* __restrict__ o
             row_fft<S, +1>(buf, tw_s, tid);
             STAGE_MARK(3) // row FFT
             __syncthreads();
-            const cpx* tbl = tableP + (size_t)p * M * K1;
             cpx tc[M];
-#pragma unroll
-            for (int m = 0; m < M; ++m) tc[m] = ldg_nc(tbl + m * K1 + tid);
+            Tmem4<S>::load(tc, tmem_mine, 2 * p);
             // ---- stage C: column n' of all rows -> registers
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
@@ -183,8 +236,7 @@ __global__ void __launch_bounds__(S::T, 1) fused_mod2_kernel(cpx* __restrict__ o
             cpx* sc = scratch + (size_t)blockIdx.x * (M * K1) + tid;
 #pragma unroll
             for (int m = 0; m < M; ++m) v[0][m] = cmul(v[0][m], tc[m]);
-#pragma unroll
-            for (int m = 0; m < M; ++m) tc[m] = ldg_nc(tbl + m * K1 + tid + T);
+            Tmem4<S>::load(tc, tmem_mine, 2 * p + 1);
             rf::FFTN<M, +1>::run(v[0]);
             if (p == 0) {
                 // even samples -> scratch [n2][n'] (whole lines, kept in L2 until pass 1 collects them)
@@ -219,11 +271,12 @@ __global__ void __launch_bounds__(S::T, 1) fused_mod2_kernel(cpx* __restrict__ o
             phase ^= 1;
         }
     }
+    Tmem4<S>::release(tmem_base, tid);
 }
 
 // ----------------------------------------------------------------------------------------
 // receiver.  in: [n_frames][N] time samples; out: [n_frames][N]; mode 0: soft symbols, mode 1: R.
-// tables: [2 (p)][2 (half)][M][K1] = Tlo^p, Thi^p.  A pass has four steps (item j, half h): the thread's
+// tables: [2 (half)][M][K1] = C_rx[m][n' + half*K1]; w2: W^{n'}.  A pass has four steps (item j, half h): the thread's
 // sample column n1 = tid + j*T + h*K1, i.e. M quarter rows of T samples, each moved by one bulk copy.
 // Homes of the quarter rows (n2 = sample row) -- chosen so that every copy is issued at least one compute
 // step before its data is needed, except step 1 of the next pass (issued when the output staging is done):
@@ -236,7 +289,8 @@ __global__ void __launch_bounds__(S::T, 1) fused_mod2_kernel(cpx* __restrict__ o
 template <class S>
 __global__ void __launch_bounds__(S::T, 1) fused_rx2_kernel(cpx* __restrict__ out, const cpx* __restrict__ in,
                                                            const cpx* __restrict__ tables,
-                                                           const cpx* __restrict__ tw, int mode, int n_frames)
+                                                           const cpx* __restrict__ tw, const cpx* __restrict__ w2,
+                                                           int mode, int n_frames)
 {
     constexpr int M = S::M, K1 = S::K, K = 2 * K1, N = M * K, T = S::T, RS = S::RS;
     static_assert(S::F == 1 && S::IPT == 2 && S::TWO_PASS, "two-pass kernels: one half-frame per CTA pass, two items per thread");
@@ -259,6 +313,13 @@ __global__ void __launch_bounds__(S::T, 1) fused_rx2_kernel(cpx* __restrict__ ou
     for (int i = tid; i < S::TW_ELEMS; i += T) tw_s[i] = tw[i];
     if (tid == 0)
         for (int s = 0; s < 4; ++s) mbar_init(bars + s, 1);
+    // With a = C_rx[m][n'] U_n'[m] and b = C_rx[m][n'+K1] U_{n'+K1}[m] the two passes need the same table columns:
+    // B^0 = a + b, B^1 = (a - b) W^{n'}.  They live in tensor memory: set = 2*j + h (item j, half h).
+    uint32_t tmem_base = 0, tmem_mine = 0;
+    Tmem4<S>::setup(reinterpret_cast<uint32_t*>(bars + 4), tid, tmem_base, tmem_mine, [&](int set, int m) {
+        return ldg_nc(tables + ((size_t)(set & 1) * M + m) * K1 + tid + (set >> 1) * T);
+    });
+    const cpx wj[2] = { w2[tid], w2[tid + T] };
     __syncthreads();
 
     // quarter row n2 of step s of frame gg -> its home; issued by lane 0 of warp n2
@@ -299,17 +360,11 @@ __global__ void __launch_bounds__(S::T, 1) fused_rx2_kernel(cpx* __restrict__ ou
         for (int p = 0; p < 2; ++p) {
             const int gn = p == 0 ? g : g + gridDim.x;
             const bool has_next = gn < n_frames;
-            const cpx* tbl = tables + (size_t)p * 2 * M * K1;
             cpx v[2][M];
 #pragma unroll
             for (int s = 0; s < 4; ++s) {
                 const int j = s >> 1, h = s & 1;
                 cpx tc[M], x[M];
-                {
-                    const cpx* tcol = tbl + (size_t)h * M * K1 + tid + j * T;
-#pragma unroll
-                    for (int m = 0; m < M; ++m) tc[m] = ldg_nc(tcol + m * K1);
-                }
                 mbar_wait(bars + s, phase);
 #pragma unroll
                 for (int n2 = 0; n2 < M; ++n2) x[n2] = home(s, n2)[tid];
@@ -325,12 +380,18 @@ __global__ void __launch_bounds__(S::T, 1) fused_rx2_kernel(cpx* __restrict__ ou
                     if (has_next) issue(gn, 0, 0, M, true, p == 1);
                 }
                 rf::FFTN<M, -1>::run(x);
+                Tmem4<S>::load(tc, tmem_mine, s);
                 if (h == 0) {
 #pragma unroll
                     for (int m = 0; m < M; ++m) v[j][m] = cmul(x[m], tc[m]);
                 } else {
+                    if (p == 0) {
 #pragma unroll
-                    for (int m = 0; m < M; ++m) v[j][m] = cfma(x[m], tc[m], v[j][m]);
+                        for (int m = 0; m < M; ++m) v[j][m] = cfma(x[m], tc[m], v[j][m]);
+                    } else {
+#pragma unroll
+                        for (int m = 0; m < M; ++m) v[j][m] = cmul(csub(v[j][m], cmul(x[m], tc[m])), wj[j]);
+                    }
                     cpx* dst = buf + S::swz(tid + j * T);
 #pragma unroll
                     for (int m = 0; m < M; ++m) dst[m * RS] = v[j][m];
@@ -386,6 +447,7 @@ __global__ void __launch_bounds__(S::T, 1) fused_rx2_kernel(cpx* __restrict__ ou
             phase ^= 1;
         }
     }
+    Tmem4<S>::release(tmem_base, tid);
 }
 
 // ----------------------------------------------------------------------------------------
@@ -460,18 +522,21 @@ TwoPass* twopass_create_rx(int M, int K, int L, const std::vector<std::complex<f
     t->name = "fused_rx2_kernel<M=15,K=2x32x32,T=512>";
     try {
         t->grid_cap = fused_grid_cap((const void*)&fused_rx2_kernel<S>, S::T, S::SMEM_BYTES);
-        // C_rx in double so that the extra twiddle does not cost a rounding
+        // C_rx[m][n'] and C_rx[m][n'+K1] as [h][m][n']; the pass-1 twiddle W^{n'} = e^{-j2pi n'/K} is applied in the kernel
         const std::vector<std::complex<double>> C = make_fold_table_d(M, K, L, taps, -1, true);
-        std::vector<cpx> P((size_t)4 * M * K1);
-        for (int p = 0; p < 2; ++p)
-            for (int h = 0; h < 2; ++h)
-                for (int m = 0; m < M; ++m)
-                    for (int n = 0; n < K1; ++n) {
-                        const std::complex<double> w = std::polar(1.0, -2.0 * M_PI * (double)(p * n) / (double)K);
-                        std::complex<double> c = C[(size_t)m * K + n + h * K1] * w;
-                        if (h && p) c = -c;
-                        P[(((size_t)p * 2 + h) * M + m) * K1 + n] = make_float2((float)c.real(), (float)c.imag());
-                    }
+        std::vector<cpx> P((size_t)2 * M * K1);
+        for (int h = 0; h < 2; ++h)
+            for (int m = 0; m < M; ++m)
+                for (int n = 0; n < K1; ++n) {
+                    const std::complex<double> c = C[(size_t)m * K + n + h * K1];
+                    P[((size_t)h * M + m) * K1 + n] = make_float2((float)c.real(), (float)c.imag());
+                }
+        std::vector<cpx> w((size_t)K1);
+        for (int n = 0; n < K1; ++n) {
+            const double ph = -2.0 * M_PI * (double)n / (double)K;
+            w[n] = make_float2((float)std::cos(ph), (float)std::sin(ph));
+        }
+        t->d_w2 = upload(w);
         t->d_table = upload(P);
         t->d_tw = upload(make_row_twiddles(S::R1, S::R2));
     } catch (...) {
@@ -504,7 +569,7 @@ int twopass_demodulate(TwoPass* t, cpx* out, const cpx* in, int mode, size_t fra
     for (size_t f0 = 0; f0 < frames; f0 += max_chunk) {
         const int nf = (int)std::min(max_chunk, frames - f0);
         const int grid = nf < t->grid_cap ? nf : t->grid_cap;
-        fused_rx2_kernel<S><<<grid, S::T, S::SMEM_BYTES, s>>>(out + f0 * N, in + f0 * N, t->d_table, t->d_tw, mode, nf);
+        fused_rx2_kernel<S><<<grid, S::T, S::SMEM_BYTES, s>>>(out + f0 * N, in + f0 * N, t->d_table, t->d_tw, t->d_w2, mode, nf);
         ++launches;
     }
     GFDM_CUDA_CHECK(cudaGetLastError());
