@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <cmath>
 #include <complex>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <sstream>
@@ -246,7 +247,13 @@ static void host_pipeline(HandleBase* h, size_t n, size_t chunk, const gfdm_comp
 // frames per pipeline chunk: 32 MB of host traffic per chunk keeps fill/drain below a millisecond
 static size_t pipe_chunk(size_t bytes_per_frame, size_t n)
 {
-    const size_t budget = (size_t)32 << 20;
+    // GFDM_PIPE_CHUNK_MB overrides the chunk size (tools/e2e_sweep.py measured 8..128 MB on B200)
+    static const size_t override_mb = [] {
+        const char* e = std::getenv("GFDM_PIPE_CHUNK_MB");
+        const long v = e ? std::atol(e) : 0;
+        return (size_t)(v > 0 && v <= 1024 ? v : 0);
+    }();
+    const size_t budget = (override_mb ? override_mb : (size_t)32) << 20;
     size_t c = budget / (bytes_per_frame ? bytes_per_frame : 1);
     if (c < 1) c = 1;
     return c < n ? c : n;

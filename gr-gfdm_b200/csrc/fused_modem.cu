@@ -183,12 +183,14 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_mod_kernel(cpx* __restric
                 int e = g_e0[j];
 #pragma unroll
                 for (int m = 0; m < M; ++m) {
-                    cpx val = cmake(0.f, 0.f);
-                    if (m < g_mv[j]) {
-                        if constexpr (CHK) val = lookup(pre_b[e]);
-                        else val = (e < PF) ? pre[e] : buf[e - PF];
-                    }
-                    v[j][m] = val;
+                    // branch-free: out-of-range timeslots read staged element 0 and are zeroed afterwards
+                    const bool ok = m < g_mv[j];
+                    const int ec = ok ? e : 0;
+                    cpx val;
+                    if constexpr (CHK) val = lookup(pre_b[ec]);
+                    else if constexpr (PF >= F * N) val = pre[ec]; // the whole staged group lives in P
+                    else val = *((ec < PF ? pre : buf - PF) + ec);
+                    v[j][m] = ok ? val : cmake(0.f, 0.f);
                     e += g_st;
                 }
             }
@@ -267,7 +269,7 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_mod_kernel(cpx* __restric
                         if ((unsigned)(i - lo) < (unsigned)(hi - lo)) stg_stream(o + i, v[j][n2]);
                         else tx_store_edge(o, i, v[j][n2], N, W, tx.ramp, tx.front, tx.back);
                         i += K;
-                        i = i >= N ? i - N : i;
+                        i = (int)min((unsigned)i, (unsigned)(i - N)); // wrap at N without a branch (i < 2N)
                     }
                 }
             }
@@ -277,9 +279,19 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_mod_kernel(cpx* __restric
             const int os = tx.P + N + tx.cp + tx.cs;
             for (int a = 0; a < tx.n_ant; ++a) {
                 const cpx* p = tx.preambles + (size_t)tx.pre_idx[a] * tx.P;
+                // 16-byte copies when every row start is 16-byte aligned (even P, even row length, aligned bases)
+                const bool vec = ((tx.P | os) & 1) == 0 && (tx.ant_stride & 1) == 0 &&
+                                 ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(p)) & 15) == 0;
                 for (int f = 0; f < fh; ++f) {
                     cpx* o = out + (size_t)a * tx.ant_stride + ((size_t)g * F + f) * os;
-                    for (int i = tid; i < tx.P; i += T) stg_stream(o + i, ldg_nc(p + i));
+                    if (vec) {
+                        for (int i = tid; i < tx.P / 2; i += T) {
+                            const float4 q = __ldg(reinterpret_cast<const float4*>(p) + i);
+                            stg_stream4(o + 2 * i, cmake(q.x, q.y), cmake(q.z, q.w));
+                        }
+                    } else {
+                        for (int i = tid; i < tx.P; i += T) stg_stream(o + i, ldg_nc(p + i));
+                    }
                 }
             }
         }
