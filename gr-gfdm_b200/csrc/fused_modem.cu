@@ -117,6 +117,10 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_mod_kernel(cpx* __restric
         const uint32_t bytes = (uint32_t)min(el, PF) * sizeof(cpx);
         mbar_expect_tx(bar_p, bytes);
         if (bytes) bulk_load(pre, in + (size_t)gg * F * EL, bytes, bar_p);
+        // the tail of the group can only be staged once the row buffer is free (after stage C's reads), which leaves it
+        // little time to arrive (stage profile: 922 of 15.3k cycles per frame waiting at the loop top): bring it into L2
+        // now so that the later bulk load is an L2 hit
+        if (el > PF) bulk_prefetch_l2(in + (size_t)gg * F * EL + PF, (uint32_t)(el - PF) * sizeof(cpx));
     };
     auto load_tail = [&](int gg) {
         if constexpr (CHK) return;
