@@ -200,7 +200,11 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_mod_kernel(cpx* __restric
             }
         }
         __syncthreads(); // staging fully consumed: P may be refilled, R may take the rows
-        if (tid == 0 && gn < n_groups) {
+        // Issuing the bulk copy costs its warp a few hundred cycles and every other warp waits for it at the next barrier.
+        // When the last warp has no row-FFT items (ROWS*R2 <= T-32, e.g. 480 of 512 threads at K = 1024) it issues the
+        // copy during that phase instead, off everybody's critical path; the data still has three phases to arrive.
+        constexpr bool IDLE_WARP = S::TWO_PASS && S::ROWS * S::R2 + 32 <= T;
+        if (!IDLE_WARP && tid == 0 && gn < n_groups) {
             fence_proxy_async();
             load_head(gn);
         }
@@ -217,6 +221,10 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_mod_kernel(cpx* __restric
         __syncthreads();
         STAGE_MARK(2) // stage A FFT + row writes
         // ---- stage B: K-point inverse FFT of every row (over the subcarrier index)
+        if (IDLE_WARP && tid == T - 32 && gn < n_groups) {
+            fence_proxy_async();
+            load_head(gn);
+        }
         row_fft<S, +1>(buf, tw_s, tid, tmem_mine + S::TMEM_TBL_COLS);
         STAGE_MARK(3) // row FFT (warp 0's own time)
         __syncthreads();
@@ -424,7 +432,9 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_rx_kernel(cpx* __restrict
             for (int n2 = 0; n2 < M; ++n2) v[j][n2] = n2 < PR ? src[n2 * K] : xr[j][n2 - PR < XR ? n2 - PR : 0];
         }
         __syncthreads(); // P consumed: refill it with the next group
-        if (tid == 0 && gn < n_groups) {
+        // (issued by the idle last warp during the row FFT where there is one, see the modulator)
+        constexpr bool IDLE_WARP = S::TWO_PASS && S::ROWS * S::R2 + 32 <= T;
+        if (!IDLE_WARP && tid == 0 && gn < n_groups) {
             fence_proxy_async();
             load_head(gn);
         }
@@ -460,6 +470,10 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_rx_kernel(cpx* __restrict
         __syncthreads();
         STAGE_MARK(19) // row writes
         // ---- stage B: K-point forward FFT of every row (over n1)
+        if (IDLE_WARP && tid == T - 32 && gn < n_groups) {
+            fence_proxy_async();
+            load_head(gn);
+        }
         row_fft<S, -1>(buf, tw_s, tid, tmem_mine + S::TMEM_TBL_COLS);
         STAGE_MARK(20) // row FFT
         if (gn < n_groups) load_rest(gn); // tail rows of the next group: in flight during stage C'
