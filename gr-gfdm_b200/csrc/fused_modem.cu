@@ -158,8 +158,11 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_mod_kernel(cpx* __restric
         const int fh = min(F, n_frames - g * F);
         const int gn = g + gridDim.x;
         mbar_wait(bar_p, phase);
-        if (!CHK && PF < F * N) mbar_wait(bar_r, phase);
-        phase ^= 1;
+        // the tail of the staged group (region R) is only read by the items whose records lie behind PF: the plain
+        // modulator waits for it right before the first of those (the transmitter's gather may touch it anywhere)
+        constexpr int J_TAIL = PF / (T * M); // first item with a record at or behind PF
+        constexpr bool LATE_TAIL = !TXF && !CHK && PF < F * N && J_TAIL >= 1 && J_TAIL < IPT;
+        if (!CHK && !LATE_TAIL && PF < F * N) mbar_wait(bar_r, phase);
         STAGE_MARK(0) // wait for the bulk loads
 
         cpx v[IPT][M];
@@ -174,6 +177,7 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_mod_kernel(cpx* __restric
         } else if constexpr (!TXF) {
 #pragma unroll
             for (int j = 0; j < IPT; ++j) {
+                if (LATE_TAIL && j == J_TAIL) mbar_wait(bar_r, phase);
                 const int e = (tid + j * T) * M; // (f*K + k)*M
                 const cpx* src = (e < PF) ? pre + e : buf + (e - PF);
 #pragma unroll
@@ -199,6 +203,7 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_mod_kernel(cpx* __restric
                 }
             }
         }
+        phase ^= 1;
         __syncthreads(); // staging fully consumed: P may be refilled, R may take the rows
         // Issuing the bulk copy costs its warp a few hundred cycles and every other warp waits for it at the next barrier.
         // When the last warp has no row-FFT items (ROWS*R2 <= T-32, e.g. 480 of 512 threads at K = 1024) it issues the
