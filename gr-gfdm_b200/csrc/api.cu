@@ -688,6 +688,7 @@ struct gfdm_advanced_receiver : gfdm_receiver {
     int* d_smap = nullptr;
     unsigned char* d_active = nullptr;
     cpx* d_points = nullptr;
+    DecideGrid grid; // O(1) nearest-point decisions when the constellation is a uniform rectangular grid
     DeviceBuf freq_block, ic_time, ic_freq;
 };
 
@@ -738,7 +739,7 @@ static void advanced_run(gfdm_advanced_receiver* h, cpx* out, const cpx* in, con
         cpx* nxt = (rest % 2 == 0) ? IT : out;
         if (j0 != 0 && cur != out) GFDM_CUDA_CHECK(cudaMemcpyAsync(cur, out, el * sizeof(cpx), cudaMemcpyDeviceToDevice, h->stream));
         for (int j = 0; j < rest; ++j) {
-            launch_sic_iter(nxt, cur, FB, h->d_ic, h->d_active, h->d_points, h->n_points, h->rule, h->M, h->K, frames, h->stream);
+            launch_sic_iter(nxt, cur, FB, h->d_ic, h->d_active, h->d_points, h->n_points, h->rule, h->grid, h->M, h->K, frames, h->stream);
             h->launches += 1;
             std::swap(cur, nxt);
         }
@@ -769,6 +770,11 @@ int gfdm_advanced_receiver_create(gfdm_advanced_receiver** out, int M, int K, in
     h->d_active = upload(active);
     h->d_smap = upload(h->smap);
     h->d_points = dev_upload(vec(c->points, c->n_points));
+    {
+        std::vector<cpx> p((size_t)c->n_points);
+        for (int i = 0; i < c->n_points; ++i) p[i] = make_float2(c->points[i].re, c->points[i].im);
+        h->grid = make_decide_grid(p);
+    }
     if (h->fused.available()) h->fused.init_sic(h->ic_taps, vec(c->points, c->n_points), h->rule, h->smap);
     *out = h.release();
     API_CATCH

@@ -31,7 +31,8 @@ void launch_ic_subtract(cpx* out, const cpx* fd, const cpx* F, const cpx* ic_tap
 // one whole cancellation iteration (decide neighbours, re-modulate, subtract, back to time domain): y_out != y_in
 bool sic_iter_supported(int M, int K, int n_points, size_t frames);
 void launch_sic_iter(cpx* y_out, const cpx* y_in, const cpx* fb, const cpx* ic_taps, const unsigned char* active,
-                     const cpx* points, int n_points, int rule, int M, int K, size_t frames, cudaStream_t s);
+                     const cpx* points, int n_points, int rule, const DecideGrid& grid, int M, int K, size_t frames,
+                     cudaStream_t s);
 void launch_decide(cpx* out, const cpx* in, const unsigned char* active, const cpx* points, int n_points, int rule,
                    int M, int K, size_t frames, cudaStream_t s);
 void launch_phase_rotate(cpx* R, const cpx* decided, const cpx* soft, const int* smap, int n_map, int M, int K,

@@ -334,6 +334,7 @@ struct SicArgs {
     const unsigned char* count;  // [K] multiplicity of subcarrier k in the subcarrier map (0 = inactive)
     int n_points, rule, ic_iter, phase_comp;
     float inv_map_total;         // 1 / (map.size() * M)
+    float qpsk_a;                // > 0: the constellation is gr::digital's QPSK (+-a +-ja in its index order): decisions by sign
     DecideGrid grid;             // hard-decision output (DEC): O(1) decisions on grid constellations
 };
 
@@ -364,13 +365,14 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_rx_kernel(cpx* __restrict
     for (int i = tid; i < L * M && i < S::IC_OFF; i += T) taps_s[i] = taps[i];
     if constexpr (SIC) {
         static_assert(IPT == 1, "the cancellation loop keeps one subcarrier per thread in registers");
-        for (int i = tid; i < M && i < 32; i += T) taps_s[S::IC_OFF + i] = sic.ic_taps[i];
+        for (int i = tid; i < M && i < 32; i += T) taps_s[S::IC_OFF + i] = cscale(sic.ic_taps[i], inv_m); // 1/M of the IFFT folded in
     }
     // constellation: interference cancellation and the hard-decision output (mode 2)
     if constexpr (SIC || DEC)
         for (int i = tid; i < sic.n_points && i < S::MAX_POINTS; i += T) taps_s[S::PTS_OFF + i] = sic.points[i];
-    unsigned char* lut_s = reinterpret_cast<unsigned char*>(taps_s + S::RED_OFF); // DEC only (no phase reduction there)
-    if constexpr (DEC)
+    // grid-constellation lookup table: behind the 16 floats the phase reduction of the SIC loop uses
+    unsigned char* lut_s = reinterpret_cast<unsigned char*>(taps_s + S::RED_OFF + 16);
+    if constexpr (SIC || DEC)
         if (tid < 64) lut_s[tid] = sic.grid.lut[tid];
     if (tid == 0) mbar_init(bar_p, 1);
     // table columns of this thread -> tensor memory (once per CTA)
@@ -557,11 +559,22 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_rx_kernel(cpx* __restrict
             rf::FFTN<M, +1>::run(y);
 #pragma unroll
             for (int m = 0; m < M; ++m) y[m] = cscale(y[m], inv_m);
+            // the 1/M of every later transform_subcarriers_to_td is folded into the kept block and the taps (ic_s), once
+#pragma unroll
+            for (int m = 0; m < M; ++m) v[0][m] = cscale(v[0][m], inv_m);
+            const float qa = cnt ? sic.qpsk_a : 0.f;
             for (int it = 0; it < sic.ic_iter; ++it) {
                 cpx d[M];
+                if (sic.qpsk_a > 0.f) {
+                    // gr::digital::constellation_qpsk: idx = 2*(im > 0) + (re > 0), point = (+-a, +-a): no table lookup
 #pragma unroll
-                for (int m = 0; m < M; ++m)
-                    d[m] = cnt ? pts_s[decide_symbol(y[m], pts_s, sic.n_points, sic.rule)] : cmake(0.f, 0.f);
+                    for (int m = 0; m < M; ++m) d[m] = cmake(y[m].x > 0.f ? qa : -qa, y[m].y > 0.f ? qa : -qa);
+                } else {
+#pragma unroll
+                    for (int m = 0; m < M; ++m)
+                        d[m] = cnt ? pts_s[decide_symbol_grid(y[m], pts_s, sic.n_points, sic.rule, sic.grid, lut_s)]
+                                   : cmake(0.f, 0.f);
+                }
                 if (sic.phase_comp > 0 && it == 0) {
                     // calculate_phase_offset (:78-91): mean over the map of arg(decided) - arg(soft); deterministic
                     // tree: lanes of a frame -> per-warp partial -> fixed-order sum
@@ -600,8 +613,6 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_rx_kernel(cpx* __restrict
 #pragma unroll
                 for (int m = 0; m < M; ++m) y[m] = csub(v[0][m], cmul(ic_s[m], d[m]));
                 rf::FFTN<M, +1>::run(y);
-#pragma unroll
-                for (int m = 0; m < M; ++m) y[m] = cscale(y[m], inv_m);
             }
 #pragma unroll
             for (int m = 0; m < M; ++m) v[0][m] = y[m];
@@ -1103,6 +1114,14 @@ bool FusedModem::init_sic(const std::vector<std::complex<float>>& ic_taps,
     impl_->sic.count = impl_->d_count;
     impl_->sic.n_points = (int)points.size();
     impl_->sic.rule = rule;
+    impl_->sic.grid = make_decide_grid(to_cpx(points)); // O(1) nearest-point decisions on grid constellations
+    impl_->sic.qpsk_a = 0.f;
+    if (rule == 1 && points.size() == 4) {
+        const float a = points[3].real();
+        const bool gr_qpsk = a > 0.f && points[3].imag() == a && points[0].real() == -a && points[0].imag() == -a &&
+                             points[1].real() == a && points[1].imag() == -a && points[2].real() == -a && points[2].imag() == a;
+        if (gr_qpsk) impl_->sic.qpsk_a = a;
+    }
     impl_->sic.inv_map_total = subcarrier_map.empty() ? 0.f : 1.0f / (float)(subcarrier_map.size() * (size_t)e->M);
     impl_->sic_name = std::string(e->rx_name) + "+sic";
     return true;

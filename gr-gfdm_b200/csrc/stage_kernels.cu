@@ -167,9 +167,12 @@ template <int M>
 __global__ void __launch_bounds__(SB) sic_iter_kernel(cpx* __restrict__ y_out, const cpx* __restrict__ y_in,
                                                       const cpx* __restrict__ fb, const cpx* __restrict__ ic_taps,
                                                       const unsigned char* __restrict__ active,
-                                                      const cpx* __restrict__ points, int n_points, int rule, int K)
+                                                      const cpx* __restrict__ points, int n_points, int rule, int K,
+                                                      const __grid_constant__ DecideGrid grid)
 {
     extern __shared__ __align__(16) unsigned char sic_smem[];
+    __shared__ unsigned char lut[64];
+    if (threadIdx.x < 64) lut[threadIdx.x] = grid.lut[threadIdx.x];
     cpx* ys = reinterpret_cast<cpx*>(sic_smem); // [SB + 2][M]: record 0 = subcarrier k0-1, record SB+1 = k0+SB
     cpx* rs = ys + (SB + 2) * M;                // [SB][M]: R in, y' out
     __shared__ cpx pts[64];
@@ -200,8 +203,8 @@ __global__ void __launch_bounds__(SB) sic_iter_kernel(cpx* __restrict__ y_out, c
         cpx d[M];
 #pragma unroll
         for (int m = 0; m < M; ++m) {
-            const cpx a = ap ? pts[decide_symbol(prev[m], pts, n_points, rule)] : cmake(0.f, 0.f);
-            const cpx b = an ? pts[decide_symbol(next[m], pts, n_points, rule)] : cmake(0.f, 0.f);
+            const cpx a = ap ? pts[decide_symbol_grid(prev[m], pts, n_points, rule, grid, lut)] : cmake(0.f, 0.f);
+            const cpx b = an ? pts[decide_symbol_grid(next[m], pts, n_points, rule, grid, lut)] : cmake(0.f, 0.f);
             d[m] = cadd(a, b);
         }
         rf::FFTN<M, -1>::run(d);
@@ -219,13 +222,14 @@ __global__ void __launch_bounds__(SB) sic_iter_kernel(cpx* __restrict__ y_out, c
 }
 template <int M>
 static void launch_sic_iter_m(cpx* y_out, const cpx* y_in, const cpx* fb, const cpx* ic_taps, const unsigned char* active,
-                              const cpx* points, int n_points, int rule, int K, size_t frames, cudaStream_t s)
+                              const cpx* points, int n_points, int rule, const DecideGrid& grid, int K, size_t frames,
+                              cudaStream_t s)
 {
     const size_t smem = sizeof(cpx) * (size_t)(2 * SB + 2) * M;
     if (smem > 48 * 1024)
         GFDM_CUDA_CHECK(cudaFuncSetAttribute(sic_iter_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const size_t blocks = frames * (size_t)((K + SB - 1) / SB);
-    sic_iter_kernel<M><<<(unsigned)blocks, SB, smem, s>>>(y_out, y_in, fb, ic_taps, active, points, n_points, rule, K);
+    sic_iter_kernel<M><<<(unsigned)blocks, SB, smem, s>>>(y_out, y_in, fb, ic_taps, active, points, n_points, rule, K, grid);
     GFDM_CUDA_CHECK(cudaGetLastError());
 }
 bool sic_iter_supported(int M, int K, int n_points, size_t frames)
@@ -237,11 +241,12 @@ bool sic_iter_supported(int M, int K, int n_points, size_t frames)
     return K >= 2 && n_points >= 1 && n_points <= 64 && frames * (size_t)((K + SB - 1) / SB) < ((size_t)1 << 31);
 }
 void launch_sic_iter(cpx* y_out, const cpx* y_in, const cpx* fb, const cpx* ic_taps, const unsigned char* active,
-                     const cpx* points, int n_points, int rule, int M, int K, size_t frames, cudaStream_t s)
+                     const cpx* points, int n_points, int rule, const DecideGrid& grid, int M, int K, size_t frames,
+                     cudaStream_t s)
 {
     if (!frames) return;
 #define GFDM_SIC_CASE(MM) \
-    case MM: launch_sic_iter_m<MM>(y_out, y_in, fb, ic_taps, active, points, n_points, rule, K, frames, s); break;
+    case MM: launch_sic_iter_m<MM>(y_out, y_in, fb, ic_taps, active, points, n_points, rule, grid, K, frames, s); break;
     switch (M) {
         GFDM_SIC_CASE(2) GFDM_SIC_CASE(3) GFDM_SIC_CASE(4) GFDM_SIC_CASE(5) GFDM_SIC_CASE(7) GFDM_SIC_CASE(8)
         GFDM_SIC_CASE(9) GFDM_SIC_CASE(15) GFDM_SIC_CASE(16) GFDM_SIC_CASE(21) GFDM_SIC_CASE(25)

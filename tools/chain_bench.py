@@ -101,6 +101,25 @@ def rx_rows(M, K, A, frames, ic_iter=4):
         ms = timed(lambda: adv.demodulate_ptr(d_y.data_ptr(), d_x.data_ptr(), d_h.data_ptr(), frames))
         report('advanced_receiver_kernel_cc::generic_work_equalize, %d SIC iterations' % it, shape, frames, ms, 24 * N,
                adv.last_kernel())
+    # 16-QAM with nearest-point decisions needs a realistic signal (the decision cost depends on where the soft symbols
+    # fall): mapped 16-QAM symbols through the modulator, channel = the equaliser's input, a little noise
+    pts16 = design.qam16_points().astype(np.complex64)
+    mp = capi.Resource_mapper(M, K, A, smap, True, lib=lib)
+    mod = capi.Modulator(M, K, 2, taps, lib=lib)
+    d_s = torch.from_numpy(pts16[rng.integers(0, 16, (frames, M * A))]).cuda()
+    d_g = torch.empty_like(d_x)
+    d_x16 = torch.empty_like(d_x)
+    mp.map_ptr(d_g.data_ptr(), d_s.data_ptr(), M * A, frames)
+    mp.sync()
+    mod.modulate_ptr(d_x16.data_ptr(), d_g.data_ptr(), frames)
+    mod.sync()
+    d_x16 = torch.fft.ifft(torch.fft.fft(d_x16, dim=1) * d_h, dim=1)
+    d_x16 = (d_x16 + 0.01 * torch.randn_like(d_x16)).to(torch.complex64).contiguous()
+    adv = capi.Advanced_receiver(M, K, 2, np.conj(taps), smap, ic_iter, (pts16, capi.DECISION_NEAREST), 0, lib=lib)
+    adv.set_stream(stream.cuda_stream)
+    ms = timed(lambda: adv.demodulate_ptr(d_y.data_ptr(), d_x16.data_ptr(), d_h.data_ptr(), frames))
+    report('advanced_receiver_kernel_cc::generic_work_equalize, %d SIC iterations, 16-QAM nearest-point decisions' % ic_iter, shape,
+           frames, ms, 24 * N, adv.last_kernel())
     preamble = crand(rng, 2 * K)
     est = capi.Preamble_channel_estimator(M, K, A, True, 0, preamble, lib=lib)
     est.set_stream(stream.cuda_stream)
