@@ -676,12 +676,14 @@ __device__ __forceinline__ void stg_stream_cpx(cpx* p, cpx v)
 __global__ void __launch_bounds__(TH) est_fused_kernel(cpx* __restrict__ frame, const cpx* __restrict__ rx,
                                                        const cpx* __restrict__ tw, const cpx* __restrict__ inv0,
                                                        const cpx* __restrict__ inv1, const float* __restrict__ g, int M,
-                                                       int K, int A, int off, size_t frames)
+                                                       int K, int A, int off, int fpc, size_t frames)
 {
+    // fpc = frames per CTA pass: short transforms are batched so that every pass keeps all TH threads busy
     extern __shared__ __align__(16) unsigned char est_smem[];
-    cpx* xa = reinterpret_cast<cpx*>(est_smem); // [2][K] ping
-    cpx* xb = xa + 2 * K;                       // [2][K] pong; later H [K] and filt [A+off]
-    cpx* tws = xb + 2 * K;                      // [K] twiddles W_K^e
+    const int HH = 2 * fpc;                     // preamble halves in flight
+    cpx* xa = reinterpret_cast<cpx*>(est_smem); // [HH][K] ping
+    cpx* xb = xa + HH * K;                      // [HH][K] pong; later H [fpc][K] and the filtered estimates
+    cpx* tws = xb + HH * K;                     // [K] twiddles W_K^e
     const int tid = threadIdx.x;
     const int N = M * K, n_est = A + off, half = n_est / 2;
     const int center = N / 2, dead_half = M * (K - A) / 2;
@@ -690,22 +692,22 @@ __global__ void __launch_bounds__(TH) est_fused_kernel(cpx* __restrict__ frame, 
     for (int t = 0; t < 9; ++t) gt[t] = g[t];
     const int so0 = tid / M, j0 = tid - so0 * M, qTH = (int)TH / M, rTH = (int)TH - qTH * M; // walk of the interpolation loops
     for (int i = tid; i < K; i += TH) tws[i] = tw[i];
-    for (size_t f = blockIdx.x; f < frames; f += gridDim.x) {
-        const cpx* in = rx + f * 2 * (size_t)K;
-        for (int i = tid; i < 2 * K; i += TH) xa[i] = in[i];
+    const int Q = K / 4, lq = 31 - __clz(Q), lk2 = lq + 1; // K is a power of two
+    for (size_t f0 = (size_t)blockIdx.x * fpc; f0 < frames; f0 += (size_t)gridDim.x * fpc) {
+        const int nf = (int)(frames - f0 < (size_t)fpc ? frames - f0 : (size_t)fpc);
+        const cpx* in = rx + f0 * 2 * (size_t)K;
+        for (int i = tid; i < nf * 2 * K; i += TH) xa[i] = in[i];
         __syncthreads();
-        // both transforms at once (half h = which preamble half).  Radix-4 Stockham passes while they fit, one radix-2
-        // pass at the end for K = 2 * 4^n; twiddles W_K^e from the shared-memory copy of the double-precision table
+        // all transforms at once (h = which preamble half of which frame).  Radix-4 Stockham passes while they keep every
+        // thread busy, radix-2 passes for the rest (one for K = 2 * 4^n); twiddles W_K^e from the shared-memory copy of
+        // the double-precision table.  Measured on B200: K = 1024 radix 4: 0.194 -> 0.159 ms; K = 256 needs fpc = 2 for it.
         cpx* src = xa;
         cpx* dst = xb;
         int Ns = 1;
-        const int Q = K / 4;
-        // radix 4 pays when a pass keeps every thread busy (2*K/4 >= TH butterflies); measured on B200: K = 1024
-        // 0.194 -> 0.175 ms, but K = 256 0.208 -> 0.272 ms, so short transforms stay on radix 2
-        for (; K >= 2 * (int)TH && Ns * 4 <= K; Ns <<= 2) {
+        for (; HH * Q >= (int)TH && Ns * 4 <= K; Ns <<= 2) {
             const int sh = K / (4 * Ns);
-            for (int w = tid; w < 2 * Q; w += TH) {
-                const int h = w >= Q, j = w - h * Q;
+            for (int w = tid; w < HH * Q; w += TH) {
+                const int h = w >> lq, j = w & (Q - 1);
                 const int k = j & (Ns - 1);
                 const cpx* x = src + h * K + j;
                 const cpx v0 = x[0];
@@ -727,67 +729,69 @@ __global__ void __launch_bounds__(TH) est_fused_kernel(cpx* __restrict__ frame, 
             dst = t2;
         }
         for (; Ns < K; Ns <<= 1) {
-            for (int w = tid; w < K; w += TH) {
-                const int h = w >= K / 2, j = w - h * (K / 2);
+            for (int w = tid; w < HH * (K / 2); w += TH) {
+                const int h = w >> lk2, j = w & (K / 2 - 1);
                 const int k = j & (Ns - 1);
                 const cpx a = src[h * K + j];
                 const cpx b = cmul(src[h * K + j + K / 2], tws[k * (K / (2 * Ns))]);
-                const int j0 = ((j - k) << 1) + k;
-                dst[h * K + j0] = cadd(a, b);
-                dst[h * K + j0 + Ns] = csub(a, b);
+                const int j0b = ((j - k) << 1) + k;
+                dst[h * K + j0b] = cadd(a, b);
+                dst[h * K + j0b + Ns] = csub(a, b);
             }
             __syncthreads();
             cpx* t2 = src;
             src = dst;
             dst = t2;
         }
-        // H = F0 * inv0 + F1 * inv1 (:121-143) -> dst[0..K)
-        for (int q = tid; q < K; q += TH) {
-            const cpx a = cmul_rn(src[q], inv0[q]);
-            const cpx b = cmul_rn(src[K + q], inv1[q]);
-            dst[q] = cmake(__fadd_rn(b.x, a.x), __fadd_rn(b.y, a.y));
+        // H = F0 * inv0 + F1 * inv1 (:121-143) -> dst[fi][0..K)
+        for (int q = tid; q < fpc * K; q += TH) {
+            const int fi = q >> (lk2 + 1), qq = q & (K - 1);
+            const cpx a = cmul_rn(src[(2 * fi) * K + qq], inv0[qq]);
+            const cpx b = cmul_rn(src[(2 * fi + 1) * K + qq], inv1[qq]);
+            dst[fi * K + qq] = cmake(__fadd_rn(b.x, a.x), __fadd_rn(b.y, a.y));
         }
         __syncthreads();
-        // reorder + edge replicate + 9-tap correlation (:145-185) -> src[0..n_est)
-        for (int i = tid; i < n_est; i += TH) {
+        // reorder + edge replicate + 9-tap correlation (:145-185) -> src[fi][0..n_est)
+        for (int i = tid; i < fpc * n_est; i += TH) {
+            const int fi = i / n_est, ii = i - fi * n_est;
             float re = 0.f, im = 0.f;
 #pragma unroll
             for (int t = 0; t < 9; ++t) {
-                const cpx v = est_padded(dst, i + t, K, A, off);
+                const cpx v = est_padded(dst + fi * K, ii + t, K, A, off);
                 re = __fadd_rn(re, __fmul_rn(v.x, gt[t]));
                 im = __fadd_rn(im, __fmul_rn(v.y, gt[t]));
             }
-            src[i] = cmake(re, im);
+            src[fi * K + ii] = cmake(re, im);
         }
         __syncthreads();
         // piecewise-linear interpolation to N bins (:238-274): the cases of est_interp_kernel as four division-free
         // loops (thread t walks bins t, t+TH, ...: segment and offset advance by TH/M and TH%M); the reference's
         // running sum e[i] + inc + ... + inc (j times) is evaluated as fma(j, inc, e[i]) -- at most j ulps apart
-        const cpx* e = src;
-        cpx* o = frame + f * (size_t)N;
         const float step = 1.0f / (float)M;
-        auto ramp = [&](int lo, int n_bins, int seg0) {
-            int seg = seg0 + so0, j = j0;
-            for (int r = tid; r < n_bins; r += TH) {
-                const cpx e0 = e[seg], d = csub(e[seg + 1], e0);
-                const float fj = (float)j;
-                stg_stream_cpx(o + lo + r, cmake(fmaf(fj, d.x * step, e0.x), fmaf(fj, d.y * step, e0.y)));
-                j += rTH;
-                seg += qTH;
-                if (j >= M) {
-                    j -= M;
-                    ++seg;
+        for (int fi = 0; fi < nf; ++fi) {
+            const cpx* e = src + fi * K;
+            cpx* o = frame + (f0 + fi) * (size_t)N;
+            auto ramp = [&](int lo, int n_bins, int seg0) {
+                int seg = seg0 + so0, j = j0;
+                for (int r = tid; r < n_bins; r += TH) {
+                    const cpx e0 = e[seg], d = csub(e[seg + 1], e0);
+                    const float fj = (float)j;
+                    stg_stream_cpx(o + lo + r, cmake(fmaf(fj, d.x * step, e0.x), fmaf(fj, d.y * step, e0.y)));
+                    j += rTH;
+                    seg += qTH;
+                    if (j >= M) {
+                        j -= M;
+                        ++seg;
+                    }
                 }
-            }
-        };
-        ramp(0, (n_est - 1 - half) * M, half);          // last loop of the reference: i in [half, n_est-1)
-        ramp(center + dead_half, half * M, 0);          // i in [0, half)
-        {
+            };
+            ramp(0, (n_est - 1 - half) * M, half);          // last loop of the reference: i in [half, n_est-1)
+            ramp(center + dead_half, half * M, 0);          // i in [0, half)
             const cpx hi = e[n_est - 1], lo = e[0];
             for (int b2 = M * A / 2 + tid; b2 < center; b2 += TH) stg_stream_cpx(o + b2, hi);
             for (int b2 = center + tid; b2 < center + dead_half; b2 += TH) stg_stream_cpx(o + b2, lo);
         }
-        __syncthreads(); // src/dst are reused by the next frame
+        __syncthreads(); // src/dst are reused by the next pass
     }
 }
 bool est_fused_supported(int K, int A, int dc_free)
@@ -799,7 +803,9 @@ void launch_est_fused(cpx* frame, const cpx* rx, const cpx* tw, const cpx* inv0,
                       int K, int A, int dc_free, size_t frames, cudaStream_t s)
 {
     if (!frames) return;
-    const size_t smem = sizeof(cpx) * 5 * (size_t)K;
+    int fpc = (2 * (int)TH) / K; // short transforms: batch frames until a radix-4 pass has TH butterflies
+    fpc = fpc < 1 ? 1 : (fpc > 8 ? 8 : fpc);
+    const size_t smem = sizeof(cpx) * (size_t)(4 * fpc + 1) * (size_t)K;
     static int sms = 0;
     if (!sms) {
         int dev = 0;
@@ -811,8 +817,9 @@ void launch_est_fused(cpx* frame, const cpx* rx, const cpx* tw, const cpx* inv0,
     int per_sm = 1;
     GFDM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, est_fused_kernel, (int)TH, smem));
     const size_t cap = (size_t)sms * (per_sm > 0 ? per_sm : 1);
-    est_fused_kernel<<<(unsigned)(frames < cap ? frames : cap), TH, smem, s>>>(frame, rx, tw, inv0, inv1, g, M, K, A,
-                                                                                dc_free ? 1 : 0, frames);
+    const size_t passes = (frames + fpc - 1) / fpc;
+    est_fused_kernel<<<(unsigned)(passes < cap ? passes : cap), TH, smem, s>>>(frame, rx, tw, inv0, inv1, g, M, K, A,
+                                                                                dc_free ? 1 : 0, fpc, frames);
     GFDM_CUDA_CHECK(cudaGetLastError());
 }
 
