@@ -10,7 +10,10 @@
 #include "engine.h"
 #include "fused.h"
 
+#include <nvtx3/nvToolsExt.h> // header-only NVTX v3: ranges cost a predicted branch unless a profiler is attached
+
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <complex>
 #include <cstdlib>
@@ -22,7 +25,11 @@ using namespace gfdm;
 typedef std::complex<float> cf;
 
 static thread_local std::string g_err;
-static int g_device = 0;
+// Device selection is PER HOST THREAD (one thread per GPU may create and drive its own handles concurrently);
+// a thread that never called gfdm_set_device inherits the last selection made anywhere in the process.
+static thread_local int t_device = -1;
+static std::atomic<int> g_default_device{ 0 };
+static int current_device_choice() { return t_device >= 0 ? t_device : g_default_device.load(std::memory_order_relaxed); }
 
 static int fail(int code, const std::string& msg)
 {
@@ -30,7 +37,15 @@ static int fail(int code, const std::string& msg)
     return code;
 }
 
-#define API_TRY try {
+// one NVTX range per C-ABI entry (tracing hooks), named after the entry point
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+
+#define API_TRY                  \
+    NvtxRange nvtx_range_(__func__); \
+    try {
 #define API_CATCH                                                                     \
     }                                                                                 \
     catch (const std::invalid_argument& e) { return fail(GFDM_ERR_INVALID_ARGUMENT, e.what()); } \
@@ -46,6 +61,7 @@ struct HandleBase {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    bool opened = false; // open() ran: device resources may exist (the *_destroy functions select the device only then)
     long long launches = 0;
     const char* last_kernel = "none";
     DeviceBuf stage_in, stage_in2, stage_out; // HOST-pointer staging
@@ -62,8 +78,10 @@ struct HandleBase {
         if (e != cudaSuccess || n <= 0)
             throw CudaError(std::string("gfdm_b200: no usable CUDA device (") + cudaGetErrorString(e) +
                             "); this library has no CPU fallback");
-        device = g_device;
+        device = current_device_choice();
+        if (device >= n) throw CudaError("gfdm_b200: the selected device does not exist");
         GFDM_CUDA_CHECK(cudaSetDevice(device));
+        opened = true;
         GFDM_CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         own_stream = true;
     }
@@ -277,7 +295,8 @@ int gfdm_set_device(int device)
     int n = 0;
     GFDM_CUDA_CHECK(cudaGetDeviceCount(&n));
     if (device < 0 || device >= n) throw std::invalid_argument("device index out of range");
-    g_device = device;
+    t_device = device;
+    g_default_device.store(device, std::memory_order_relaxed);
     API_CATCH
 }
 static HandleBase* base(void* handle)
@@ -344,7 +363,7 @@ int gfdm_fft_create(gfdm_fft** out, int fft_size, int forward)
 {
     API_TRY
     if (fft_size < 1) throw std::invalid_argument("fft_size MUST be positive");
-    std::unique_ptr<gfdm_fft> h(new gfdm_fft);
+    std::unique_ptr<gfdm_fft, void (*)(gfdm_fft*)> h(new gfdm_fft, gfdm_fft_destroy); // a throwing step releases stream + device memory
     h->open();
     h->plan.init(fft_size);
     h->forward = forward != 0;
@@ -354,7 +373,7 @@ int gfdm_fft_create(gfdm_fft** out, int fft_size, int forward)
 void gfdm_fft_destroy(gfdm_fft* h)
 {
     if (!h) return;
-    cudaSetDevice(h->device);
+    if (h->opened) cudaSetDevice(h->device);
     h->plan.destroy();
     h->close();
     delete h;
@@ -411,7 +430,7 @@ int gfdm_modulator_create(gfdm_modulator** out, int M, int K, int L, const gfdm_
     API_TRY
     check_taps((size_t)(n_taps > 0 ? n_taps : 0), M, L);
     if (M < 1 || K < 1 || L < 1) throw std::invalid_argument("timeslots, subcarriers and overlap MUST be positive");
-    std::unique_ptr<gfdm_modulator> h(new gfdm_modulator);
+    std::unique_ptr<gfdm_modulator, void (*)(gfdm_modulator*)> h(new gfdm_modulator, gfdm_modulator_destroy); // a throwing step releases stream + device memory
     h->M = M; h->K = K; h->L = L; h->N = M * K;
     h->taps = normalize_taps(vec(taps, n_taps), M);
     h->open();
@@ -423,7 +442,7 @@ int gfdm_modulator_create(gfdm_modulator** out, int M, int K, int L, const gfdm_
 void gfdm_modulator_destroy(gfdm_modulator* h)
 {
     if (!h) return;
-    cudaSetDevice(h->device);
+    if (h->opened) cudaSetDevice(h->device);
     if (h->d_taps) cudaFree(h->d_taps);
     h->fft_m.destroy();
     h->fft_n.destroy();
@@ -486,7 +505,7 @@ static void receiver_init(gfdm_receiver* h, int M, int K, int L, const std::vect
 }
 static void receiver_free(gfdm_receiver* h)
 {
-    cudaSetDevice(h->device);
+    if (h->opened) cudaSetDevice(h->device);
     if (h->d_taps) cudaFree(h->d_taps);
     if (h->d_ic) cudaFree(h->d_ic);
     h->fft_m.destroy();
@@ -577,7 +596,7 @@ static void receiver_cancel(gfdm_receiver* h, cpx* out, const cpx* td, const cpx
 int gfdm_receiver_create(gfdm_receiver** out, int M, int K, int L, const gfdm_complex* taps, int n_taps)
 {
     API_TRY
-    std::unique_ptr<gfdm_receiver> h(new gfdm_receiver);
+    std::unique_ptr<gfdm_receiver, void (*)(gfdm_receiver*)> h(new gfdm_receiver, gfdm_receiver_destroy); // a throwing step releases stream + device memory
     receiver_init(h.get(), M, K, L, vec(taps, n_taps));
     *out = h.release();
     API_CATCH
@@ -696,7 +715,8 @@ struct gfdm_advanced_receiver : gfdm_receiver {
 static void advanced_run(gfdm_advanced_receiver* h, cpx* out, const cpx* in, const cpx* eq, size_t frames)
 {
     if (!frames) return;
-    if (h->fused.sic_available() && h->ic_iter >= 0 && aligned16(out) && aligned16(in) && aligned16(eq)) {
+    if (h->fused.sic_available() && (!eq || h->fused.supports_eq()) && h->ic_iter >= 0 && aligned16(out) && aligned16(in) &&
+        aligned16(eq)) {
         h->launches += h->fused.demodulate_sic(out, in, eq, frames, h->ic_iter, h->phase_comp, h->stream);
         h->last_kernel = h->fused.sic_name();
         return;
@@ -755,10 +775,15 @@ int gfdm_advanced_receiver_create(gfdm_advanced_receiver** out, int M, int K, in
 {
     API_TRY
     if (!c || c->n_points < 1 || !c->points) throw std::invalid_argument("constellation MUST hold at least one point");
+    // same rules as gfdm_symbol_mapper_create: the sign rule indexes points[0..3]
+    if (c->decision_rule != GFDM_DECISION_NEAREST && c->decision_rule != GFDM_DECISION_QPSK_SIGN)
+        throw std::invalid_argument("unknown constellation decision rule!");
+    if (c->decision_rule == GFDM_DECISION_QPSK_SIGN && c->n_points != 4)
+        throw std::invalid_argument("the QPSK sign rule needs exactly 4 constellation points!");
     if (n_map < 0) throw std::invalid_argument("subcarrier_map size MUST NOT be negative");
     for (int i = 0; i < n_map; ++i)
         if (smap[i] < 0 || smap[i] >= K) throw std::invalid_argument("subcarrier_map entries MUST lie in [0, subcarriers)");
-    std::unique_ptr<gfdm_advanced_receiver> h(new gfdm_advanced_receiver);
+    std::unique_ptr<gfdm_advanced_receiver, void (*)(gfdm_advanced_receiver*)> h(new gfdm_advanced_receiver, gfdm_advanced_receiver_destroy); // a throwing step releases stream + device memory
     h->smap.assign(smap, smap + n_map);
     h->ic_iter = ic_iter;
     h->phase_comp = do_phase_compensation;
@@ -782,7 +807,7 @@ int gfdm_advanced_receiver_create(gfdm_advanced_receiver** out, int M, int K, in
 void gfdm_advanced_receiver_destroy(gfdm_advanced_receiver* h)
 {
     if (!h) return;
-    cudaSetDevice(h->device);
+    if (h->opened) cudaSetDevice(h->device);
     if (h->d_smap) cudaFree(h->d_smap);
     if (h->d_active) cudaFree(h->d_active);
     if (h->d_points) cudaFree(h->d_points);
@@ -889,7 +914,7 @@ int gfdm_resource_mapper_create(gfdm_resource_mapper** out, int M, int K, int A,
                                 int per_timeslot, int is_mapper)
 {
     API_TRY
-    std::unique_ptr<gfdm_resource_mapper> h(new gfdm_resource_mapper);
+    std::unique_ptr<gfdm_resource_mapper, void (*)(gfdm_resource_mapper*)> h(new gfdm_resource_mapper, gfdm_resource_mapper_destroy); // a throwing step releases stream + device memory
     h->c.validate(M, K, A, smap, n_map, per_timeslot != 0, is_mapper != 0);
     h->open();
     h->c.to_device();
@@ -899,7 +924,7 @@ int gfdm_resource_mapper_create(gfdm_resource_mapper** out, int M, int K, int A,
 void gfdm_resource_mapper_destroy(gfdm_resource_mapper* h)
 {
     if (!h) return;
-    cudaSetDevice(h->device);
+    if (h->opened) cudaSetDevice(h->device);
     h->c.destroy();
     h->close();
     delete h;
@@ -1008,7 +1033,7 @@ int gfdm_cyclic_prefixer_create(gfdm_cyclic_prefixer** out, int block_len, int c
                                 const gfdm_complex* w, int n_w, int cyclic_shift)
 {
     API_TRY
-    std::unique_ptr<gfdm_cyclic_prefixer> h(new gfdm_cyclic_prefixer);
+    std::unique_ptr<gfdm_cyclic_prefixer, void (*)(gfdm_cyclic_prefixer*)> h(new gfdm_cyclic_prefixer, gfdm_cyclic_prefixer_destroy); // a throwing step releases stream + device memory
     h->c.validate(block_len, cp_len, cs_len, ramp_len, vec(w, n_w), cyclic_shift);
     h->open();
     h->c.to_device();
@@ -1018,7 +1043,7 @@ int gfdm_cyclic_prefixer_create(gfdm_cyclic_prefixer** out, int block_len, int c
 void gfdm_cyclic_prefixer_destroy(gfdm_cyclic_prefixer* h)
 {
     if (!h) return;
-    cudaSetDevice(h->device);
+    if (h->opened) cudaSetDevice(h->device);
     h->c.destroy();
     h->close();
     delete h;
@@ -1100,9 +1125,12 @@ int gfdm_channel_estimator_create(gfdm_channel_estimator** out, int M, int K, in
     if (M < 1 || K < 2 || A < 2 || A > K)
         throw std::invalid_argument("timeslots MUST be positive and 2 <= active_subcarriers <= fft_len");
     if (n_preamble < 2 * K) throw std::invalid_argument("preamble MUST hold at least 2 * fft_len samples");
+    // odd A: the reference's interpolate_frame (:238-274) writes up to index N + M/2 - 1 of the N-long frame when dc free,
+    // filter_preamble_estimate correlates against an unfilled entry and estimate_snr leaves cnrs[A-1] unset
+    if (A % 2) throw std::invalid_argument("active_subcarriers MUST be even (the reference writes past its frame buffer for odd values)");
     if (A + (is_dc_free ? 1 : 0) > K)
         throw std::invalid_argument("active_subcarriers (+1 if dc free) MUST NOT exceed fft_len");
-    std::unique_ptr<gfdm_channel_estimator> h(new gfdm_channel_estimator);
+    std::unique_ptr<gfdm_channel_estimator, void (*)(gfdm_channel_estimator*)> h(new gfdm_channel_estimator, gfdm_channel_estimator_destroy); // a throwing step releases stream + device memory
     h->M = M; h->K = K; h->A = A; h->dc_free = is_dc_free ? 1 : 0; h->which = which;
     // initialize_gaussian_filter(sigma_sq = 1, 9 taps), lib/preamble_channel_estimator_cc.cc:86-100
     float s = 0.0f;
@@ -1135,7 +1163,7 @@ int gfdm_channel_estimator_create(gfdm_channel_estimator** out, int M, int K, in
 void gfdm_channel_estimator_destroy(gfdm_channel_estimator* h)
 {
     if (!h) return;
-    cudaSetDevice(h->device);
+    if (h->opened) cudaSetDevice(h->device);
     h->fft_k.destroy(); h->fft_2k.destroy();
     if (h->d_inv0) cudaFree(h->d_inv0);
     if (h->d_inv1) cudaFree(h->d_inv1);
@@ -1360,7 +1388,7 @@ int gfdm_transmitter_create(gfdm_transmitter** out, int M, int K, int A, int cp,
 {
     API_TRY
     if (n_preambles < 1) throw std::invalid_argument("at least one preamble is required");
-    std::unique_ptr<gfdm_transmitter> h(new gfdm_transmitter);
+    std::unique_ptr<gfdm_transmitter, void (*)(gfdm_transmitter*)> h(new gfdm_transmitter, gfdm_transmitter_destroy); // a throwing step releases stream + device memory
     // member construction order of the reference: mapper, modulator, prefixer (transmitter_kernel.cc:47-52)
     h->map.validate(M, K, A, smap, n_map, per_timeslot != 0, true);
     check_taps((size_t)(n_taps > 0 ? n_taps : 0), M, L);
@@ -1391,7 +1419,7 @@ int gfdm_transmitter_create(gfdm_transmitter** out, int M, int K, int A, int cp,
 void gfdm_transmitter_destroy(gfdm_transmitter* h)
 {
     if (!h) return;
-    cudaSetDevice(h->device);
+    if (h->opened) cudaSetDevice(h->device);
     h->map.destroy();
     h->pre.destroy();
     if (h->d_taps) cudaFree(h->d_taps);
@@ -1525,7 +1553,7 @@ int gfdm_remove_prefix_create(gfdm_remove_prefix** out, int frame_len, int block
     // the block does not validate (:44-61) and would read past the frame; the ABI rejects it
     if (frame_len < 1 || block_len < 1 || offset < 0 || offset + block_len > frame_len)
         throw std::invalid_argument("remove_prefix: offset + block_len MUST NOT exceed frame_len!");
-    std::unique_ptr<gfdm_remove_prefix> h(new gfdm_remove_prefix);
+    std::unique_ptr<gfdm_remove_prefix, void (*)(gfdm_remove_prefix*)> h(new gfdm_remove_prefix, gfdm_remove_prefix_destroy); // a throwing step releases stream + device memory
     h->frame_len = frame_len; h->block_len = block_len; h->offset = offset;
     h->open();
     *out = h.release();
@@ -1534,7 +1562,7 @@ int gfdm_remove_prefix_create(gfdm_remove_prefix** out, int frame_len, int block
 void gfdm_remove_prefix_destroy(gfdm_remove_prefix* h)
 {
     if (!h) return;
-    cudaSetDevice(h->device);
+    if (h->opened) cudaSetDevice(h->device);
     h->close();
     delete h;
 }
@@ -1575,7 +1603,10 @@ int gfdm_extract_burst_create(gfdm_extract_burst** out, int burst_len, int tag_b
 {
     API_TRY
     if (burst_len < 1) throw std::invalid_argument("extract_burst: burst_len MUST be positive!");
-    std::unique_ptr<gfdm_extract_burst> h(new gfdm_extract_burst);
+    // A negative back-off moves the burst BEHIND its tag; the block's admission test (:152) looks at the tag only and the
+    // reference then reads past its input window.  The ABI rejects the configuration (deliberate deviation).
+    if (tag_backoff < 0) throw std::invalid_argument("extract_burst: tag_backoff MUST NOT be negative!");
+    std::unique_ptr<gfdm_extract_burst, void (*)(gfdm_extract_burst*)> h(new gfdm_extract_burst, gfdm_extract_burst_destroy); // a throwing step releases stream + device memory
     h->burst_len = burst_len; h->tag_backoff = tag_backoff; h->cfo = activate_cfo_correction != 0;
     h->open();
     *out = h.release();
@@ -1584,7 +1615,7 @@ int gfdm_extract_burst_create(gfdm_extract_burst** out, int burst_len, int tag_b
 void gfdm_extract_burst_destroy(gfdm_extract_burst* h)
 {
     if (!h) return;
-    cudaSetDevice(h->device);
+    if (h->opened) cudaSetDevice(h->device);
     for (int i = 0; i < 2; ++i) {
         h->d_desc[i].release();
         if (h->h_desc[i]) cudaFreeHost(h->h_desc[i]);
@@ -1649,7 +1680,7 @@ int gfdm_extract_burst_work(gfdm_extract_burst* h, gfdm_complex* out, int max_bu
         GFDM_CUDA_CHECK(cudaEventRecord(h->ev_copied[sl], h->stream));
         const cpx* di = st.in(in, (size_t)n_in, h->stage_in);
         cpx* dout = st.out(out, (size_t)nb * BL, h->stage_out);
-        h->launches += launch_extract_burst(dout, di, h->d_desc[sl].as<BurstDesc>(), h->burst_len, h->cfo, nb, h->stream);
+        h->launches += launch_extract_burst(dout, di, h->d_desc[sl].as<BurstDesc>(), h->burst_len, h->cfo, nb, n_in, h->stream);
         h->last_kernel = "extract_burst_kernel";
         st.finish(out, (size_t)nb * BL, h->stage_out);
     }
@@ -1670,9 +1701,11 @@ int gfdm_symbol_mapper_create(gfdm_symbol_mapper** out, const gfdm_constellation
     API_TRY
     if (!c || !c->points || c->n_points < 1 || c->n_points > 256)
         throw std::invalid_argument("constellation MUST have between 1 and 256 points!");
+    if (c->decision_rule != GFDM_DECISION_NEAREST && c->decision_rule != GFDM_DECISION_QPSK_SIGN)
+        throw std::invalid_argument("unknown constellation decision rule!");
     if (c->decision_rule == GFDM_DECISION_QPSK_SIGN && c->n_points != 4)
         throw std::invalid_argument("the QPSK sign rule needs exactly 4 constellation points!");
-    std::unique_ptr<gfdm_symbol_mapper> h(new gfdm_symbol_mapper);
+    std::unique_ptr<gfdm_symbol_mapper, void (*)(gfdm_symbol_mapper*)> h(new gfdm_symbol_mapper, gfdm_symbol_mapper_destroy); // a throwing step releases stream + device memory
     h->points = vec(c->points, c->n_points);
     h->rule = c->decision_rule;
     for (int b = 0; b <= 8; ++b)
@@ -1690,7 +1723,7 @@ int gfdm_symbol_mapper_create(gfdm_symbol_mapper** out, const gfdm_constellation
 void gfdm_symbol_mapper_destroy(gfdm_symbol_mapper* h)
 {
     if (!h) return;
-    cudaSetDevice(h->device);
+    if (h->opened) cudaSetDevice(h->device);
     if (h->d_points) cudaFree(h->d_points);
     h->close();
     delete h;

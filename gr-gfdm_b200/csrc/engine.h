@@ -68,7 +68,8 @@ struct BurstDesc {
 };
 // desc: start, scale and phase_rotation set by the host; with cfo the rotation constants are derived on the device
 // first (one more launch).  Returns the number of launches.
-int launch_extract_burst(cpx* out, const cpx* in, BurstDesc* desc, int burst_len, bool cfo, int n_bursts, cudaStream_t s);
+int launch_extract_burst(cpx* out, const cpx* in, BurstDesc* desc, int burst_len, bool cfo, int n_bursts, long long n_in,
+                         cudaStream_t s);
 // symbol mapping (python/pygfdm/symbolmapping.py:27-47): chunk = constellation point index, one byte per symbol
 void launch_map_chunks(cpx* out, const unsigned char* chunks, const cpx* points, int n_points, size_t n, cudaStream_t s);
 void launch_decide_chunks(unsigned char* chunks, const cpx* in, const cpx* points, int n_points, int rule,

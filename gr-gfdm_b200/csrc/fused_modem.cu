@@ -794,6 +794,7 @@ struct FusedImpl {
     const ShapeEntry* e = nullptr; // single-pass shape, or
     TwoPass* tp = nullptr;         // two-pass kernels (frame larger than shared memory)
     int M = 0, K = 0, L = 0;
+    bool eq_ok = false;        // rx: the equalising variant is available (single-pass shape, L*M <= 64)
     cpx* d_table = nullptr;    // tx: C_tx ; rx: C_rx (taps folded)
     cpx* d_table_eq = nullptr; // rx only: plain twiddle
     cpx* d_tw = nullptr;
@@ -844,6 +845,9 @@ std::vector<std::complex<double>> make_fold_table_d(int M, int K, int L, const s
     const int N = M * K, h = L / 2;
     const int part_len = (M * L / 2 < M) ? M * L / 2 : M;
     std::vector<std::complex<double>> t((size_t)N);
+    // roots of unity once: a full-width receiver (L = K) sums K taps per table entry
+    std::vector<std::complex<double>> wk((size_t)K);
+    for (int e = 0; e < K; ++e) wk[e] = std::polar(1.0, sign * 2.0 * M_PI * (double)e / (double)K);
     for (int m = 0; m < M; ++m)
         for (int n1 = 0; n1 < K; ++n1) {
             std::complex<double> G(1.0, 0.0);
@@ -853,7 +857,7 @@ std::vector<std::complex<double>> make_fold_table_d(int M, int K, int L, const s
                     const std::complex<double> tp(taps[((i + h) % L) * M + m].real(), taps[((i + h) % L) * M + m].imag());
                     long e = ((long)(i - h) * n1) % K;
                     if (e < 0) e += K;
-                    G += tp * std::polar(1.0, sign * 2.0 * M_PI * (double)e / (double)K);
+                    G += tp * wk[e];
                 }
                 if (sign > 0 && m >= part_len) G = 0.0;
             }
@@ -918,9 +922,13 @@ void FusedModem::init_rx(int M, int K, int L, const std::vector<std::complex<flo
         impl_->tp = tp; impl_->M = M; impl_->K = K; impl_->L = L;
         return;
     }
-    if (!e || L < 2 || L * M > 64) return; // the kernel keeps at most 64 receive taps in shared memory
+    if (!e || L < 2) return;
     FusedImpl* p = new FusedImpl;
     p->e = e; p->M = M; p->K = K; p->L = L;
+    // Without equalisation any overlap (up to the full-width L = K of a zero-forcing receiver) costs nothing at run time:
+    // the taps live in the folded table.  The equalising variant combines the L neighbouring blocks explicitly with the
+    // taps held in shared memory (at most 64 of them).
+    p->eq_ok = L * M <= 64;
     try {
         p->rx_grid_cap = fused_grid_cap(e->rx_fn, e->T, e->smem);
         p->d_table = upload(make_fold_table(M, K, L, taps, -1, true));
@@ -935,7 +943,7 @@ void FusedModem::init_rx(int M, int K, int L, const std::vector<std::complex<flo
     impl_ = p;
 }
 
-bool FusedModem::supports_eq() const { return impl_ && impl_->e != nullptr; }
+bool FusedModem::supports_eq() const { return impl_ && impl_->e != nullptr && impl_->eq_ok; }
 
 int FusedModem::modulate(cpx* out, const cpx* in, size_t frames, cudaStream_t s)
 {

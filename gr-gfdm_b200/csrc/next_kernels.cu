@@ -33,7 +33,7 @@ static unsigned grid_for(size_t items, unsigned threads)
 // access is a full 256-byte line), computes one sincos in double at its first sample and steps by inc^32 in double.
 __global__ void __launch_bounds__(TH) extract_burst_kernel(cpx* __restrict__ out, const cpx* __restrict__ in,
                                                            const BurstDesc* __restrict__ desc, int burst_len, int cfo,
-                                                           int n_bursts)
+                                                           int n_bursts, long long n_in)
 {
     const int tiles = (burst_len + 127) / 128; // warp tiles per burst
     const size_t total = (size_t)n_bursts * tiles;
@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(TH) extract_burst_kernel(cpx* __restrict__ out
         for (int j = 0; j < 4; ++j) {
             const int i = i0 + 32 * j;
             const long long src = d.start + i;
-            x[j] = (i < burst_len && src >= 0) ? ldg_stream_cpx(in + src) : cmake(0.f, 0.f);
+            x[j] = (i < burst_len && src >= 0 && src < n_in) ? ldg_stream_cpx(in + src) : cmake(0.f, 0.f); // never outside the window
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -83,12 +83,13 @@ __global__ void __launch_bounds__(TH) burst_prepare_kernel(BurstDesc* __restrict
     desc[b].angle = angle;
     sincos(32.0 * angle, &desc[b].inc32_im, &desc[b].inc32_re);
 }
-int launch_extract_burst(cpx* out, const cpx* in, BurstDesc* desc, int burst_len, bool cfo, int n_bursts, cudaStream_t s)
+int launch_extract_burst(cpx* out, const cpx* in, BurstDesc* desc, int burst_len, bool cfo, int n_bursts, long long n_in,
+                         cudaStream_t s)
 {
     if (n_bursts <= 0) return 0;
     if (cfo) burst_prepare_kernel<<<blocks_for((size_t)n_bursts, TH), TH, 0, s>>>(desc, n_bursts);
     const size_t total = (size_t)n_bursts * ((burst_len + 127) / 128) * 32; // threads
-    extract_burst_kernel<<<grid_for(total, TH), TH, 0, s>>>(out, in, desc, burst_len, cfo ? 1 : 0, n_bursts);
+    extract_burst_kernel<<<grid_for(total, TH), TH, 0, s>>>(out, in, desc, burst_len, cfo ? 1 : 0, n_bursts, n_in);
     GFDM_CUDA_CHECK(cudaGetLastError());
     return cfo ? 2 : 1;
 }

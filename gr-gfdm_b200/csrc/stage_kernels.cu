@@ -439,7 +439,8 @@ void launch_demap(cpx* out, const cpx* in, const int* smap, int M, int K, int A,
     const size_t total = frames * n_out;
     if (!total) return;
     const size_t tiled_blocks = frames * (size_t)((A + TS - 1) / TS);
-    if (per_timeslot && K >= 512 && M <= 96 && A > 0 && tiled_blocks < ((size_t)1 << 31)) {
+    // static `sub[TS]` + the dynamic tile must stay inside the 48 KB that need no opt-in
+    if (per_timeslot && K >= 512 && sizeof(cpx) * TS * M + sizeof(int) * TS <= 48 * 1024 && A > 0 && tiled_blocks < ((size_t)1 << 31)) {
         demap_tiled_kernel<<<(unsigned)tiled_blocks, TH, sizeof(cpx) * TS * M, s>>>(out, in, smap, M, K, A, n_out, out_stride);
         GFDM_CUDA_CHECK(cudaGetLastError());
         return;

@@ -73,7 +73,9 @@ def gfdm_freq_taps(h):
 
 
 def gfdm_freq_taps_sparse(H, M, L):
-    return np.concatenate((H[0:(M * L) // 2], H[-((M * L) // 2):]))
+    # `H[-(M * L) // 2:]` as the reference writes it (python/pygfdm/filters.py:43): floor(-(M*L)/2), i.e. for odd M*L
+    # the negative half is one tap longer than the positive half and the result has M*L entries
+    return np.concatenate((H[0:(M * L) // 2], H[-(M * L) // 2:]))
 
 
 def get_frequency_domain_filter(filtertype, alpha, M, K, L):
@@ -95,7 +97,10 @@ def get_zero_forcing_taps(filtertype, alpha, M, K, L=2):
     time by K/L, i.e. its spectrum folded onto the L*M sparse taps, conjugated for
     the correlation receiver and renormalised like every tap set (the receiver
     kernel renormalises again, so only the shape matters).  With L = 2 the fold
-    makes this an approximation of the full-width ZF receiver.
+    ALIASES the dual's wide spectrum onto two blocks: measured through the reference
+    kernels this is a worse receiver than the matched filter (tests/test_design.py),
+    it is kept because SURVEY 8d prescribes it for the benchmark taps.  Use
+    get_zero_forcing_taps_full for a receiver that zero-forces.
     """
     if K % L:
         raise ValueError('subcarriers MUST be a multiple of overlap')
@@ -106,6 +111,75 @@ def get_zero_forcing_taps(filtertype, alpha, M, K, L=2):
     gamma = np.fft.ifft(Zd, axis=0).reshape(N)  # dual window
     G = np.conjugate(np.fft.fft(gamma[::K // L]))
     return G / np.sqrt(np.sum(np.abs(G) ** 2) / M)
+
+
+def pulse_spectrum_from_sparse_taps(taps, M, K, L):
+    """N-bin spectrum (FFT order) of the pulse the kernels implement with L*M sparse taps: the modulator scatters
+    taps[((i+h)%L)*M + m] onto bin ((k+i-h) mod K)*M + m (lib/modulator_kernel_cc.cc:113-135), h = L/2, so subcarrier 0's
+    pulse has G[((i-h) mod K)*M + m] = taps[((i+h)%L)*M + m]; every other bin is zero.  Taps are renormalised like the
+    kernels do (sum |T|^2 = M)."""
+    taps = np.asarray(taps, dtype=complex)
+    taps = taps / np.sqrt(np.sum(np.abs(taps) ** 2) / M)
+    G = np.zeros(M * K, dtype=complex)
+    h = L // 2
+    for i in range(L):
+        b = (i - h) % K
+        G[b * M:(b + 1) * M] += taps[((i + h) % L) * M:((i + h) % L) * M + M]
+    return G
+
+
+def sparse_taps_from_pulse_spectrum(G, M, K, L):
+    """Inverse of pulse_spectrum_from_sparse_taps: the L*M taps (kernel tap order) that keep the L blocks of M bins
+    around DC of an N-bin spectrum; L = K keeps everything."""
+    G = np.asarray(G)
+    h = L // 2
+    T = np.zeros(L * M, dtype=complex)
+    for i in range(L):
+        b = (i - h) % K
+        T[((i + h) % L) * M:((i + h) % L) * M + M] = G[b * M:(b + 1) * M]
+    return T
+
+
+def _zak(g, M, K):
+    return np.fft.fft(np.reshape(g, (M, K)), axis=0)  # [m, k] <- sum_l g[k + l K] e^{-j 2 pi m l / M}
+
+
+def get_zero_forcing_taps_full(tx_taps, M, K, L, rx_overlap=None):
+    """Receive taps that ZERO-FORCE the modulator built from `tx_taps` (L*M sparse taps): the canonical dual window of
+    the transmit pulse on the critically sampled (K, M) Gabor lattice, Z(gamma) = 1 / conj(Z(g)) in the Zak domain
+    (python/gfdmlib/gfdm/detail/gfdmutil.py:107-113, gabor.py:41-72), expressed as receive taps of
+    receiver_kernel_cc with overlap = K (the whole spectrum, FFT order; default) -- noiseless demodulation then returns
+    the transmitted symbols times a real gain (the receiver renormalises its taps).  With rx_overlap < K the dual's
+    spectrum is truncated to the rx_overlap blocks around DC: an approximation whose residual interference falls
+    slowly for wide pulses (RRC 0.5, M = 15: EVM 0.36 / 0.07 / 0.013 at overlap 2 / 16 / 32).  Requires an invertible
+    transmit matrix (odd M for the usual symmetric pulses)."""
+    G = pulse_spectrum_from_sparse_taps(tx_taps, M, K, L)
+    g = np.fft.ifft(G)                       # x[n] = sum_{k,t} d[k,t] g[n - tK] e^{j 2 pi k n / K}
+    Zg = _zak(g, M, K)
+    if np.min(np.abs(Zg)) < 1e-9 * np.max(np.abs(Zg)):
+        raise ValueError('the transmit matrix is singular (zero of the Zak transform): no zero-forcing receiver exists')
+    gamma = np.fft.ifft(1.0 / np.conjugate(Zg), axis=0).reshape(M * K)
+    Gam = np.conjugate(np.fft.fft(gamma))
+    Lr = K if rx_overlap is None else int(rx_overlap)
+    T = sparse_taps_from_pulse_spectrum(Gam, M, K, Lr)
+    return T / np.sqrt(np.sum(np.abs(T) ** 2) / M)
+
+
+def get_mmse_taps_full(tx_taps, M, K, L, snr_db=20.0, rx_overlap=None):
+    """Linear MMSE receive taps for the modulator built from `tx_taps`: B = (A^H A + sigma^2 I)^-1 A^H is diagonal in
+    the Zak domain on the critical lattice (eigenvalues of A^H A are K |Z(g)|^2), so
+    Z(gamma) = Z(g) / (|Z(g)|^2 + sigma^2 / K) (gfdmlib's MMSE pulse, gfdmutil.py:115-131, written without its masking
+    of small values).  sigma^2 = mean transmit sample power / 10^(snr_db/10) for unit-energy symbols.  snr -> inf is
+    get_zero_forcing_taps_full, snr -> -inf the matched filter."""
+    G = pulse_spectrum_from_sparse_taps(tx_taps, M, K, L)
+    g = np.fft.ifft(G)
+    sigma2 = np.sum(np.abs(g) ** 2) * 10.0 ** (-snr_db / 10.0)
+    Zg = _zak(g, M, K)
+    gamma = np.fft.ifft(Zg / (np.abs(Zg) ** 2 + sigma2 / K), axis=0).reshape(M * K)
+    Gam = np.conjugate(np.fft.fft(gamma))
+    Lr = K if rx_overlap is None else int(rx_overlap)
+    T = sparse_taps_from_pulse_spectrum(Gam, M, K, Lr)
+    return T / np.sqrt(np.sum(np.abs(T) ** 2) / M)
 
 
 def get_mmse_taps(filtertype, alpha, M, K, L=2, snr_db=20.0):

@@ -459,6 +459,11 @@ int gfdm_advanced_receiver_create(gfdm_advanced_receiver** out, int M, int K, in
 {
     if (!c || c->n_points < 1 || !c->points)
         return fail(GFDM_ERR_INVALID_ARGUMENT, "constellation MUST hold at least one point");
+    /* ABI rules shared with gfdm_symbol_mapper_create: the sign rule indexes points[0..3] */
+    if (c->decision_rule != GFDM_DECISION_NEAREST && c->decision_rule != GFDM_DECISION_QPSK_SIGN)
+        return fail(GFDM_ERR_INVALID_ARGUMENT, "unknown constellation decision rule!");
+    if (c->decision_rule == GFDM_DECISION_QPSK_SIGN && c->n_points != 4)
+        return fail(GFDM_ERR_INVALID_ARGUMENT, "the QPSK sign rule needs exactly 4 constellation points!");
     for (int i = 0; i < n_map; ++i)
         if (smap[i] < 0 || smap[i] >= K)
             return fail(GFDM_ERR_INVALID_ARGUMENT, "subcarrier_map entries MUST lie in [0, subcarriers)");
@@ -830,6 +835,9 @@ int gfdm_channel_estimator_create(gfdm_channel_estimator** out, int M, int K, in
     if (M < 1 || K < 2 || A < 2 || A > K)
         return fail(GFDM_ERR_INVALID_ARGUMENT, "timeslots MUST be positive and 2 <= active_subcarriers <= fft_len");
     if (n_preamble < 2 * K) return fail(GFDM_ERR_INVALID_ARGUMENT, "preamble MUST hold at least 2 * fft_len samples");
+    /* odd A: interpolate_frame (:238-274) writes up to index N + M/2 - 1 of an N-long frame when dc free, and
+       filter_preamble_estimate / estimate_snr read unfilled entries; the ABI rejects it on every backend */
+    if (A % 2) return fail(GFDM_ERR_INVALID_ARGUMENT, "active_subcarriers MUST be even (the reference writes past its frame buffer for odd values)");
     if (A + (is_dc_free ? 1 : 0) > K)
         return fail(GFDM_ERR_INVALID_ARGUMENT, "active_subcarriers (+1 if dc free) MUST NOT exceed fft_len");
     gfdm_channel_estimator* h = (gfdm_channel_estimator*)calloc(1, sizeof(*h));

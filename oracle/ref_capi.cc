@@ -286,6 +286,11 @@ int gfdm_advanced_receiver_create(gfdm_advanced_receiver** out, int M, int K, in
     REF_TRY
     if (!c || c->n_points < 1 || !c->points)
         throw std::invalid_argument("constellation MUST hold at least one point");
+    // ABI rules shared with gfdm_symbol_mapper_create: the sign rule indexes points[0..3]
+    if (c->decision_rule != GFDM_DECISION_NEAREST && c->decision_rule != GFDM_DECISION_QPSK_SIGN)
+        throw std::invalid_argument("unknown constellation decision rule!");
+    if (c->decision_rule == GFDM_DECISION_QPSK_SIGN && c->n_points != 4)
+        throw std::invalid_argument("the QPSK sign rule needs exactly 4 constellation points!");
     auto cst = std::make_shared<gr::digital::constellation>(vec(c->points, c->n_points),
                                                              c->decision_rule);
     auto h = new gfdm_advanced_receiver;
@@ -463,6 +468,8 @@ int gfdm_channel_estimator_create(gfdm_channel_estimator** out, int M, int K, in
     REF_TRY
     if (n_preamble < 2 * K)
         throw std::invalid_argument("preamble MUST hold at least 2 * fft_len samples");
+    // odd A overflows the reference's own frame buffer in interpolate_frame (:238-274): rejected by the ABI
+    if (A % 2) throw std::invalid_argument("active_subcarriers MUST be even (the reference writes past its frame buffer for odd values)");
     auto h = new gfdm_channel_estimator;
     try {
         h->k.reset(new preamble_channel_estimator_cc(M, K, A, is_dc_free != 0, which,

@@ -50,6 +50,13 @@ def ref():
     return capi.load(REF_SO)
 
 
+@pytest.fixture(scope='session', params=['port', 'ref'])
+def oracle(request):
+    """Both checkers in turn: the plain-C restatement and the unmodified reference sources (+ shims).  The GPU parity
+    tests take this fixture, so every CUDA result is compared with the REFERENCE's own code as well."""
+    return request.getfixturevalue(request.param)
+
+
 @pytest.fixture(scope='session')
 def cuda():
     """The product library; gpu tests fail (not skip) when it cannot be loaded."""

@@ -336,3 +336,22 @@ def test_signal_energy_and_fft(port, ref):
             assert rel_l2(capi.FFT(n, True, lib=lib).execute(x), np.fft.fft(x.astype(np.complex128), axis=1)) < 1e-6
             assert rel_l2(capi.FFT(n, False, lib=lib).execute(x), np.fft.ifft(x.astype(np.complex128), axis=1) * n) < 1e-6
             assert abs(lib.calculate_signal_energy(x[0]) - np.sum(np.abs(x[0]) ** 2)) < 1e-3 * n
+
+
+def test_estimator_rejects_odd_active_subcarriers(lib):
+    """ADVICE r1 / deliberate deviation: for odd active_subcarriers the reference's interpolate_frame writes up to
+    index N + M/2 - 1 of its N-long frame (dc free), filter_preamble_estimate correlates against an unfilled entry and
+    estimate_snr leaves cnrs[A-1] unset.  Every backend of the ABI refuses the configuration at create."""
+    core = np.ones(64, np.complex64)
+    with pytest.raises(ValueError, match='active_subcarriers MUST be even'):
+        capi.Preamble_channel_estimator(5, 32, 21, True, 1, core, lib=lib)
+
+
+def test_advanced_receiver_rejects_inconsistent_constellations(lib):
+    """the sign rule indexes points[0..3]; an unknown rule value is refused as well."""
+    taps = design.get_frequency_domain_filter('rrc', .5, 5, 16, 2)
+    pts = np.array([1, -1], np.complex64)
+    with pytest.raises(ValueError, match='exactly 4 constellation points'):
+        capi.Advanced_receiver(5, 16, 2, taps, np.arange(16), 1, (pts, capi.DECISION_QPSK_SIGN), 0, lib=lib)
+    with pytest.raises(ValueError, match='unknown constellation decision rule'):
+        capi.Advanced_receiver(5, 16, 2, taps, np.arange(16), 1, (pts, 7), 0, lib=lib)
