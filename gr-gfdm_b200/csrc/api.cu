@@ -66,6 +66,7 @@ struct HandleBase {
     const char* last_kernel = "none";
     DeviceBuf stage_in, stage_in2, stage_out; // HOST-pointer staging
     DeviceBuf work_a, work_b, work_c;         // pipeline scratch
+    DeviceBuf work_fmt;                       // complex64 side of an sc16 batch
     // pipelined HOST batches (host_pipeline below): two chunk slots, copy engines on their own streams
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
     cudaEvent_t ev_in[2] = { nullptr, nullptr }, ev_run[2] = { nullptr, nullptr }, ev_out[2] = { nullptr, nullptr };
@@ -88,7 +89,7 @@ struct HandleBase {
     void close()
     {
         stage_in.release(); stage_in2.release(); stage_out.release();
-        work_a.release(); work_b.release(); work_c.release();
+        work_a.release(); work_b.release(); work_c.release(); work_fmt.release();
         for (int i = 0; i < 2; ++i) {
             slot_in0[i].release(); slot_in1[i].release(); slot_out[i].release();
             if (ev_in[i]) cudaEventDestroy(ev_in[i]);
@@ -103,7 +104,11 @@ struct HandleBase {
         stream = nullptr;
     }
     void use() { GFDM_CUDA_CHECK(cudaSetDevice(device)); }
-    void sync() { GFDM_CUDA_CHECK(cudaStreamSynchronize(stream)); }
+    void sync()
+    {
+        if (s_d2h) GFDM_CUDA_CHECK(cudaStreamSynchronize(s_d2h)); // device->host copies of a GFDM_MEM_HOST_ASYNC batch
+        GFDM_CUDA_CHECK(cudaStreamSynchronize(stream));
+    }
 };
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -147,9 +152,16 @@ static void check_taps(size_t n_taps, int M, int L)
 struct Staging {
     HandleBase* h;
     int mem;
-    explicit Staging(HandleBase* hb, int m) : h(hb), mem(m)
+    bool async = false; // GFDM_MEM_HOST_ASYNC: the host pipeline returns without waiting (gfdm_sync completes it)
+    explicit Staging(HandleBase* hb, int m, bool allow_async = false) : h(hb), mem(m)
     {
-        if (m != GFDM_MEM_HOST && m != GFDM_MEM_DEVICE) throw std::invalid_argument("mem MUST be GFDM_MEM_HOST or GFDM_MEM_DEVICE");
+        if (m == GFDM_MEM_HOST_ASYNC) {
+            if (!allow_async) throw std::invalid_argument("GFDM_MEM_HOST_ASYNC is accepted by the pipelined batch entries only");
+            mem = GFDM_MEM_HOST;
+            async = true;
+        } else if (m != GFDM_MEM_HOST && m != GFDM_MEM_DEVICE) {
+            throw std::invalid_argument("mem MUST be GFDM_MEM_HOST, GFDM_MEM_DEVICE or GFDM_MEM_HOST_ASYNC");
+        }
     }
     const cpx* in(const gfdm_complex* p, size_t elems, DeviceBuf& buf)
     {
@@ -185,12 +197,14 @@ static size_t chunk_frames(size_t bytes_per_frame, size_t n)
 // Pipelined HOST batch: the batch is cut into chunks of `chunk` frames; the host->device copy of chunk
 // i+1 (stream s_h2d), the kernels of chunk i (the handle's stream) and the device->host copy of chunk
 // i-1 (stream s_d2h) run concurrently, so both PCIe directions stay busy.  run(dout, d0, d1, f0, nf)
-// enqueues the kernels of one chunk on h->stream.  Synchronous for the caller, like generic_work.
+// enqueues the kernels of one chunk on h->stream.  Synchronous for the caller, like generic_work -- unless `async`
+// (GFDM_MEM_HOST_ASYNC): then the call returns with everything enqueued and gfdm_sync() completes it; a following
+// call on the same handle is ordered behind it by the slot events.
 // seed_out: the staged output starts as the caller's data (kernels that leave elements untouched).
 // Sizes are BYTES per frame (the symbol side of a frame may be one byte per symbol, see the chunk entries).
 template <class Run>
 static void host_pipeline_bytes(HandleBase* h, size_t n, size_t chunk, const void* in0v, size_t in0_sz, const void* in1v,
-                                size_t in1_sz, void* outv, size_t out_sz, bool seed_out, Run run)
+                                size_t in1_sz, void* outv, size_t out_sz, bool seed_out, bool async, Run run)
 {
     if (!n) return;
     if (chunk < 1) chunk = 1;
@@ -222,7 +236,7 @@ static void host_pipeline_bytes(HandleBase* h, size_t n, size_t chunk, const voi
         void* d0 = nullptr;
         void* d1 = nullptr;
         void* dout = h->slot_out[sl].p;
-        // inputs of this slot are free once the kernels of chunk idx-2 have run
+        // inputs of this slot are free once the kernels of chunk idx-2 have run (chunks of an earlier call: ev_run[0] above)
         if (idx >= 2) GFDM_CUDA_CHECK(cudaStreamWaitEvent(h->s_h2d, h->ev_run[sl], 0));
         if (in0 && in0_sz) {
             d0 = h->slot_in0[sl].p;
@@ -233,13 +247,14 @@ static void host_pipeline_bytes(HandleBase* h, size_t n, size_t chunk, const voi
             GFDM_CUDA_CHECK(cudaMemcpyAsync(d1, in1 + f0 * in1_sz, nf * in1_sz, cudaMemcpyHostToDevice, h->s_h2d));
         }
         if (seed_out) {
-            // the output slot is free once chunk idx-2 has been copied back
-            if (idx >= 2) GFDM_CUDA_CHECK(cudaStreamWaitEvent(h->s_h2d, h->ev_out[sl], 0));
+            // the output slot is free once chunk idx-2 (or the last chunk of an earlier asynchronous call that used this
+            // slot) has been copied back; waiting on a never-recorded event is a no-op
+            GFDM_CUDA_CHECK(cudaStreamWaitEvent(h->s_h2d, h->ev_out[sl], 0));
             GFDM_CUDA_CHECK(cudaMemcpyAsync(dout, out + f0 * out_sz, nf * out_sz, cudaMemcpyHostToDevice, h->s_h2d));
         }
         GFDM_CUDA_CHECK(cudaEventRecord(h->ev_in[sl], h->s_h2d));
         GFDM_CUDA_CHECK(cudaStreamWaitEvent(h->stream, h->ev_in[sl], 0));
-        if (idx >= 2) GFDM_CUDA_CHECK(cudaStreamWaitEvent(h->stream, h->ev_out[sl], 0));
+        GFDM_CUDA_CHECK(cudaStreamWaitEvent(h->stream, h->ev_out[sl], 0));
         run(dout, d0, d1, f0, nf);
         GFDM_CUDA_CHECK(cudaEventRecord(h->ev_run[sl], h->stream));
         GFDM_CUDA_CHECK(cudaStreamWaitEvent(h->s_d2h, h->ev_run[sl], 0));
@@ -247,6 +262,7 @@ static void host_pipeline_bytes(HandleBase* h, size_t n, size_t chunk, const voi
             GFDM_CUDA_CHECK(cudaMemcpyAsync(out + f0 * out_sz, dout, nf * out_sz, cudaMemcpyDeviceToHost, h->s_d2h));
         GFDM_CUDA_CHECK(cudaEventRecord(h->ev_out[sl], h->s_d2h));
     }
+    if (async) return;
     GFDM_CUDA_CHECK(cudaStreamSynchronize(h->s_d2h));
     GFDM_CUDA_CHECK(cudaStreamSynchronize(h->stream));
 }
@@ -254,9 +270,9 @@ static void host_pipeline_bytes(HandleBase* h, size_t n, size_t chunk, const voi
 template <class Run>
 static void host_pipeline(HandleBase* h, size_t n, size_t chunk, const gfdm_complex* in0, size_t in0_sz,
                           const gfdm_complex* in1, size_t in1_sz, gfdm_complex* out, size_t out_sz, bool seed_out,
-                          Run run)
+                          bool async, Run run)
 {
-    host_pipeline_bytes(h, n, chunk, in0, in0_sz * sizeof(cpx), in1, in1_sz * sizeof(cpx), out, out_sz * sizeof(cpx), seed_out,
+    host_pipeline_bytes(h, n, chunk, in0, in0_sz * sizeof(cpx), in1, in1_sz * sizeof(cpx), out, out_sz * sizeof(cpx), seed_out, async,
                         [&](void* dout, const void* d0, const void* d1, size_t f0, size_t nf) {
                             run(static_cast<cpx*>(dout), static_cast<const cpx*>(d0), static_cast<const cpx*>(d1), f0, nf);
                         });
@@ -461,12 +477,12 @@ int gfdm_modulator_work_batch(gfdm_modulator* h, gfdm_complex* out, const gfdm_c
     API_TRY
     h->use();
     if (n < 0) throw std::invalid_argument("n_frames MUST NOT be negative");
-    Staging st(h, mem);
+    Staging st(h, mem, true);
     if (mem == GFDM_MEM_DEVICE) {
         modulator_run(h, reinterpret_cast<cpx*>(out), reinterpret_cast<const cpx*>(in), (size_t)n);
     } else {
         host_pipeline(h, (size_t)n, pipe_chunk(2 * sizeof(cpx) * h->N, (size_t)n), in, h->N, nullptr, 0, out, h->N, false,
-                      [&](cpx* dout, const cpx* d0, const cpx*, size_t, size_t nf) { modulator_run(h, dout, d0, nf); });
+                      st.async, [&](cpx* dout, const cpx* d0, const cpx*, size_t, size_t nf) { modulator_run(h, dout, d0, nf); });
     }
     API_CATCH
 }
@@ -630,7 +646,7 @@ static int receiver_batch(gfdm_receiver* h, RxOp op, gfdm_complex* out, const gf
     h->use();
     if (n < 0) throw std::invalid_argument("n_frames MUST NOT be negative");
     if (op == RX_CANCEL && !in1) throw std::invalid_argument("fd_in MUST NOT be NULL");
-    Staging st(h, mem);
+    Staging st(h, mem, true);
     const size_t N = h->N;
     auto run = [&](cpx* dout, const cpx* d0, const cpx* d1, size_t, size_t nf) {
         switch (op) {
@@ -646,7 +662,7 @@ static int receiver_batch(gfdm_receiver* h, RxOp op, gfdm_complex* out, const gf
     if (mem == GFDM_MEM_DEVICE)
         run(reinterpret_cast<cpx*>(out), reinterpret_cast<const cpx*>(in0), reinterpret_cast<const cpx*>(in1), 0, (size_t)n);
     else
-        host_pipeline(h, (size_t)n, pipe_chunk((in1 ? 3 : 2) * sizeof(cpx) * N, (size_t)n), in0, N, in1, N, out, N, false, run);
+        host_pipeline(h, (size_t)n, pipe_chunk((in1 ? 3 : 2) * sizeof(cpx) * N, (size_t)n), in0, N, in1, N, out, N, false, st.async, run);
     API_CATCH
 }
 int gfdm_receiver_work_batch(gfdm_receiver* h, gfdm_complex* out, const gfdm_complex* in, const gfdm_complex* eq,
@@ -826,13 +842,13 @@ int gfdm_advanced_receiver_work_batch(gfdm_advanced_receiver* h, gfdm_complex* o
     API_TRY
     h->use();
     if (n < 0) throw std::invalid_argument("n_frames MUST NOT be negative");
-    Staging st(h, mem);
+    Staging st(h, mem, true);
     const size_t N = h->N;
     auto run = [&](cpx* dout, const cpx* d0, const cpx* d1, size_t, size_t nf) { advanced_run(h, dout, d0, d1, nf); };
     if (mem == GFDM_MEM_DEVICE)
         run(reinterpret_cast<cpx*>(out), reinterpret_cast<const cpx*>(in), reinterpret_cast<const cpx*>(eq), 0, (size_t)n);
     else
-        host_pipeline(h, (size_t)n, pipe_chunk((eq ? 3 : 2) * sizeof(cpx) * N, (size_t)n), in, N, eq, N, out, N, false, run);
+        host_pipeline(h, (size_t)n, pipe_chunk((eq ? 3 : 2) * sizeof(cpx) * N, (size_t)n), in, N, eq, N, out, N, false, st.async, run);
     API_CATCH
 }
 int gfdm_advanced_receiver_work(gfdm_advanced_receiver* h, gfdm_complex* out, const gfdm_complex* in)
@@ -1571,7 +1587,7 @@ int gfdm_remove_prefix_work_batch(gfdm_remove_prefix* h, gfdm_complex* out, cons
     API_TRY
     h->use();
     if (n < 0) throw std::invalid_argument("n_frames MUST NOT be negative");
-    Staging st(h, mem);
+    Staging st(h, mem, true);
     // the strided copy of remove_cyclic_prefix with cp = offset, cs = whatever follows the block
     const int cs = h->frame_len - h->block_len - h->offset;
     auto run = [&](cpx* dout, const cpx* d0, const cpx*, size_t, size_t nf) {
@@ -1583,7 +1599,7 @@ int gfdm_remove_prefix_work_batch(gfdm_remove_prefix* h, gfdm_complex* out, cons
         run(reinterpret_cast<cpx*>(out), reinterpret_cast<const cpx*>(in), nullptr, 0, (size_t)n);
     else
         host_pipeline(h, (size_t)n, pipe_chunk(sizeof(cpx) * ((size_t)h->frame_len + h->block_len), (size_t)n), in,
-                      (size_t)h->frame_len, nullptr, 0, out, (size_t)h->block_len, false, run);
+                      (size_t)h->frame_len, nullptr, 0, out, (size_t)h->block_len, false, st.async, run);
     API_CATCH
 }
 
@@ -1848,12 +1864,12 @@ int gfdm_modulator_work_chunks_batch(gfdm_modulator* h, const gfdm_symbol_mapper
     h->use();
     if (n < 0) throw std::invalid_argument("n_frames MUST NOT be negative");
     check_same_device(h, sm);
-    Staging st(h, mem);
+    Staging st(h, mem, true);
     if (mem == GFDM_MEM_DEVICE) {
         modulator_run_chunks(h, sm, reinterpret_cast<cpx*>(out), chunks, (size_t)n);
     } else {
         host_pipeline_bytes(h, (size_t)n, pipe_chunk((sizeof(cpx) + 1) * h->N, (size_t)n), chunks, (size_t)h->N, nullptr, 0, out,
-                            sizeof(cpx) * h->N, false, [&](void* dout, const void* d0, const void*, size_t, size_t nf) {
+                            sizeof(cpx) * h->N, false, st.async, [&](void* dout, const void* d0, const void*, size_t, size_t nf) {
                                 modulator_run_chunks(h, sm, static_cast<cpx*>(dout), static_cast<const unsigned char*>(d0), nf);
                             });
     }
@@ -1884,13 +1900,13 @@ int gfdm_receiver_work_decide_batch(gfdm_receiver* h, const gfdm_symbol_mapper* 
     h->use();
     if (n < 0) throw std::invalid_argument("n_frames MUST NOT be negative");
     check_same_device(h, sm);
-    Staging st(h, mem);
+    Staging st(h, mem, true);
     const size_t N = h->N;
     if (mem == GFDM_MEM_DEVICE) {
         receiver_run_decide(h, sm, chunks_out, reinterpret_cast<const cpx*>(in), reinterpret_cast<const cpx*>(eq), (size_t)n);
     } else {
         host_pipeline_bytes(h, (size_t)n, pipe_chunk(((eq ? 2 : 1) * sizeof(cpx) + 1) * N, (size_t)n), in, sizeof(cpx) * N, eq,
-                            sizeof(cpx) * N, chunks_out, N, false,
+                            sizeof(cpx) * N, chunks_out, N, false, st.async,
                             [&](void* dout, const void* d0, const void* d1, size_t, size_t nf) {
                                 receiver_run_decide(h, sm, static_cast<unsigned char*>(dout), static_cast<const cpx*>(d0),
                                                     static_cast<const cpx*>(d1), nf);
@@ -1909,7 +1925,7 @@ int gfdm_transmitter_work_chunks_batch(gfdm_transmitter* h, const gfdm_symbol_ma
     h->map.check_map_size((size_t)nin);
     check_same_device(h, sm);
     for (int s : h->shifts) h->pre.check_shift(s);
-    Staging st(h, mem);
+    Staging st(h, mem, true);
     const size_t os = h->out_size(), N = h->N;
     const int np = (int)sm->points.size();
     auto run = [&](cpx* dout, const unsigned char* dch, size_t nf) {
@@ -1948,7 +1964,7 @@ int gfdm_transmitter_work_chunks_batch(gfdm_transmitter* h, const gfdm_symbol_ma
         run(reinterpret_cast<cpx*>(out), chunks, (size_t)n);
     } else {
         host_pipeline_bytes(h, (size_t)n, pipe_chunk(sizeof(cpx) * os + (size_t)nin, (size_t)n), chunks, (size_t)nin, nullptr, 0,
-                            out, sizeof(cpx) * os, false, [&](void* dout, const void* d0, const void*, size_t, size_t nf) {
+                            out, sizeof(cpx) * os, false, st.async, [&](void* dout, const void* d0, const void*, size_t, size_t nf) {
                                 run(static_cast<cpx*>(dout), static_cast<const unsigned char*>(d0), nf);
                             });
     }
@@ -1963,7 +1979,7 @@ int gfdm_resource_mapper_demap_chunks_batch(gfdm_resource_mapper* h, unsigned ch
     h->c.check_demap_size(sz);
     if (n < 0) throw std::invalid_argument("n_frames MUST NOT be negative");
     if (sz == 0) return GFDM_OK;
-    Staging st(h, mem);
+    Staging st(h, mem, true);
     const size_t fs = h->c.frame_size;
     auto run = [&](void* dout, const void* d0, const void*, size_t, size_t nf) {
         launch_demap_chunks(static_cast<unsigned char*>(dout), static_cast<const unsigned char*>(d0), h->c.d_smap, h->c.M,
@@ -1974,7 +1990,112 @@ int gfdm_resource_mapper_demap_chunks_batch(gfdm_resource_mapper* h, unsigned ch
     if (mem == GFDM_MEM_DEVICE)
         run(out, in, nullptr, 0, (size_t)n);
     else
-        host_pipeline_bytes(h, (size_t)n, pipe_chunk(fs + sz, (size_t)n), in, fs, nullptr, 0, out, sz, false, run);
+        host_pipeline_bytes(h, (size_t)n, pipe_chunk(fs + sz, (size_t)n), in, fs, nullptr, 0, out, sz, false, st.async, run);
+    API_CATCH
+}
+
+/* ---- sc16 sample format on the host side of a batch (include/gfdm_b200.h) ---- */
+static void check_sc16(float scale, const void* iq, int n)
+{
+    if (n < 0) throw std::invalid_argument("n_frames MUST NOT be negative");
+    if (!(scale > 0.f) || !std::isfinite(scale)) throw std::invalid_argument("sc16 scale MUST be positive and finite");
+    if (reinterpret_cast<uintptr_t>(iq) & 3u) throw std::invalid_argument("sc16 arrays MUST be aligned to a whole I/Q pair");
+}
+// device-pointer form: the 16-byte / 8-byte vector accesses of the conversion kernels
+static void check_sc16_device(const void* iq)
+{
+    if (reinterpret_cast<uintptr_t>(iq) & 7u) throw std::invalid_argument("sc16 device arrays MUST be 8-byte aligned");
+}
+int gfdm_modulator_work_batch_sc16(gfdm_modulator* h, short* out, const gfdm_complex* in, float scale, int n, int mem)
+{
+    API_TRY
+    h->use();
+    check_sc16(scale, out, n);
+    Staging st(h, mem, true);
+    const size_t N = h->N;
+    auto run = [&](void* dout, const void* d0, const void*, size_t, size_t nf) {
+        h->work_fmt.ensure(nf * N * sizeof(cpx));
+        modulator_run(h, h->work_fmt.as<cpx>(), static_cast<const cpx*>(d0), nf);
+        launch_cf32_to_sc16(static_cast<short*>(dout), h->work_fmt.as<cpx>(), scale, nf * N, h->stream);
+        h->launches += nf ? 1 : 0;
+    };
+    if (mem == GFDM_MEM_DEVICE) {
+        check_sc16_device(out);
+        run(out, in, nullptr, 0, (size_t)n);
+    } else {
+        host_pipeline_bytes(h, (size_t)n, pipe_chunk((sizeof(cpx) + 4) * N, (size_t)n), in, sizeof(cpx) * N, nullptr, 0, out, 4 * N,
+                            false, st.async, run);
+    }
+    API_CATCH
+}
+int gfdm_modulator_work_chunks_batch_sc16(gfdm_modulator* h, const gfdm_symbol_mapper* sm, short* out, const unsigned char* chunks,
+                                          float scale, int n, int mem)
+{
+    API_TRY
+    h->use();
+    check_sc16(scale, out, n);
+    check_same_device(h, sm);
+    Staging st(h, mem, true);
+    const size_t N = h->N;
+    auto run = [&](void* dout, const void* d0, const void*, size_t, size_t nf) {
+        h->work_fmt.ensure(nf * N * sizeof(cpx));
+        modulator_run_chunks(h, sm, h->work_fmt.as<cpx>(), static_cast<const unsigned char*>(d0), nf);
+        launch_cf32_to_sc16(static_cast<short*>(dout), h->work_fmt.as<cpx>(), scale, nf * N, h->stream);
+        h->launches += nf ? 1 : 0;
+    };
+    if (mem == GFDM_MEM_DEVICE) {
+        check_sc16_device(out);
+        run(out, chunks, nullptr, 0, (size_t)n);
+    } else {
+        host_pipeline_bytes(h, (size_t)n, pipe_chunk(5 * N, (size_t)n), chunks, N, nullptr, 0, out, 4 * N, false, st.async, run);
+    }
+    API_CATCH
+}
+int gfdm_receiver_work_batch_sc16(gfdm_receiver* h, gfdm_complex* out, const short* in, const gfdm_complex* eq, float scale, int n,
+                                  int mem)
+{
+    API_TRY
+    h->use();
+    check_sc16(scale, in, n);
+    Staging st(h, mem, true);
+    const size_t N = h->N;
+    auto run = [&](void* dout, const void* d0, const void* d1, size_t, size_t nf) {
+        h->work_fmt.ensure(nf * N * sizeof(cpx));
+        launch_sc16_to_cf32(h->work_fmt.as<cpx>(), static_cast<const short*>(d0), scale, nf * N, h->stream);
+        h->launches += nf ? 1 : 0;
+        receiver_run(h, static_cast<cpx*>(dout), h->work_fmt.as<cpx>(), static_cast<const cpx*>(d1), nf);
+    };
+    if (mem == GFDM_MEM_DEVICE) {
+        check_sc16_device(in);
+        run(out, in, eq, 0, (size_t)n);
+    } else {
+        host_pipeline_bytes(h, (size_t)n, pipe_chunk(((eq ? 2 : 1) * sizeof(cpx) + 4) * N, (size_t)n), in, 4 * N, eq, sizeof(cpx) * N,
+                            out, sizeof(cpx) * N, false, st.async, run);
+    }
+    API_CATCH
+}
+int gfdm_receiver_work_decide_batch_sc16(gfdm_receiver* h, const gfdm_symbol_mapper* sm, unsigned char* chunks_out, const short* in,
+                                         const gfdm_complex* eq, float scale, int n, int mem)
+{
+    API_TRY
+    h->use();
+    check_sc16(scale, in, n);
+    check_same_device(h, sm);
+    Staging st(h, mem, true);
+    const size_t N = h->N;
+    auto run = [&](void* dout, const void* d0, const void* d1, size_t, size_t nf) {
+        h->work_fmt.ensure(nf * N * sizeof(cpx));
+        launch_sc16_to_cf32(h->work_fmt.as<cpx>(), static_cast<const short*>(d0), scale, nf * N, h->stream);
+        h->launches += nf ? 1 : 0;
+        receiver_run_decide(h, sm, static_cast<unsigned char*>(dout), h->work_fmt.as<cpx>(), static_cast<const cpx*>(d1), nf);
+    };
+    if (mem == GFDM_MEM_DEVICE) {
+        check_sc16_device(in);
+        run(chunks_out, in, eq, 0, (size_t)n);
+    } else {
+        host_pipeline_bytes(h, (size_t)n, pipe_chunk(((eq ? sizeof(cpx) : 0) + 5) * N, (size_t)n), in, 4 * N, eq, sizeof(cpx) * N,
+                            chunks_out, N, false, st.async, run);
+    }
     API_CATCH
 }
 

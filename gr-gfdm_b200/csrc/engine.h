@@ -78,6 +78,9 @@ void launch_bits2symbols(cpx* out, const unsigned char* bits, const cpx* points,
                          cudaStream_t s);
 void launch_symbols2bits(unsigned char* bits, const cpx* in, const cpx* points, int n_points, int rule, int bps,
                          const DecideGrid& grid, size_t n, cudaStream_t s);
+// sc16 host sample format: complex64 <-> interleaved int16 I/Q (n complex samples; aligned arrays, see next_kernels.cu)
+void launch_cf32_to_sc16(short* out, const cpx* in, float scale, size_t n, cudaStream_t s);
+void launch_sc16_to_cf32(cpx* out, const short* in, float scale, size_t n, cudaStream_t s);
 void launch_demap_chunks(unsigned char* out, const unsigned char* in, const int* smap, int M, int K, int A, bool per_timeslot,
                          size_t n_out, size_t frames, cudaStream_t s);
 

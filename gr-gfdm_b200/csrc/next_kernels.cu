@@ -245,4 +245,57 @@ void launch_demap_chunks(unsigned char* out, const unsigned char* in, const int*
     GFDM_CUDA_CHECK(cudaGetLastError());
 }
 
+// ---------------------------------------------------------------------------------------------
+// sc16 host sample format (include/gfdm_b200.h, "sc16 sample format"): complex64 <-> interleaved int16 I/Q.
+// Two samples (16 bytes of complex64, 8 bytes of sc16) per thread and step; HBM-bound streaming passes that run behind
+// / in front of the path kernels of a HOST batch, where the PCIe leg is 100x slower than they are.
+__device__ __forceinline__ short quant_sc16(float v, float scale)
+{
+    const int q = __float2int_rn(v * scale); // round to nearest even; NaN -> 0, +-inf saturate in the conversion
+    return (short)max(-32768, min(32767, q));
+}
+__global__ void __launch_bounds__(TH) cf32_to_sc16_kernel(short2* __restrict__ out, const cpx* __restrict__ in, float scale, size_t n)
+{
+    const size_t pairs = n / 2, stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < pairs; p += stride) {
+        float4 v;
+        asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(in + 2 * p));
+        short4 q;
+        q.x = quant_sc16(v.x, scale); q.y = quant_sc16(v.y, scale); q.z = quant_sc16(v.z, scale); q.w = quant_sc16(v.w, scale);
+        reinterpret_cast<short4*>(out)[p] = q;
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        const cpx v = in[n - 1];
+        out[n - 1] = make_short2(quant_sc16(v.x, scale), quant_sc16(v.y, scale));
+    }
+}
+__global__ void __launch_bounds__(TH) sc16_to_cf32_kernel(cpx* __restrict__ out, const short2* __restrict__ in, float inv_scale, size_t n)
+{
+    const size_t pairs = n / 2, stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < pairs; p += stride) {
+        const short4 q = __ldg(reinterpret_cast<const short4*>(in) + p);
+        reinterpret_cast<float4*>(out)[p] =
+            make_float4((float)q.x * inv_scale, (float)q.y * inv_scale, (float)q.z * inv_scale, (float)q.w * inv_scale);
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        const short2 q = in[n - 1];
+        out[n - 1] = cmake((float)q.x * inv_scale, (float)q.y * inv_scale);
+    }
+}
+// both need 16-byte aligned complex64 and 8-byte aligned sc16 arrays (the library's own staging buffers, or frames of
+// an even number of samples behind an aligned base)
+void launch_cf32_to_sc16(short* out, const cpx* in, float scale, size_t n, cudaStream_t s)
+{
+    if (!n) return;
+    cf32_to_sc16_kernel<<<grid_for((n + 1) / 2, TH), TH, 0, s>>>(reinterpret_cast<short2*>(out), in, scale, n);
+    GFDM_CUDA_CHECK(cudaGetLastError());
+}
+void launch_sc16_to_cf32(cpx* out, const short* in, float scale, size_t n, cudaStream_t s)
+{
+    if (!n) return;
+    sc16_to_cf32_kernel<<<grid_for((n + 1) / 2, TH), TH, 0, s>>>(out, reinterpret_cast<const short2*>(in), 1.0f / scale, n);
+    GFDM_CUDA_CHECK(cudaGetLastError());
+}
+
 } // namespace gfdm

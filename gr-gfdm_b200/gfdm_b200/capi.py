@@ -19,7 +19,7 @@ from ctypes import POINTER, byref, c_char_p, c_float, c_int, c_longlong, c_size_
 import numpy as np
 
 GFDM_OK, GFDM_ERR_INVALID_ARGUMENT, GFDM_ERR_RUNTIME, GFDM_ERR_CUDA, GFDM_ERR_UNSUPPORTED = range(5)
-MEM_HOST, MEM_DEVICE = 0, 1
+MEM_HOST, MEM_DEVICE, MEM_HOST_ASYNC = 0, 1, 2
 DECISION_NEAREST, DECISION_QPSK_SIGN = 0, 1
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
@@ -172,6 +172,11 @@ class Library(object):
         'gfdm_transmitter_work_chunks_batch': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int]),
         'gfdm_receiver_work_decide_batch': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int]),
         'gfdm_resource_mapper_demap_chunks_batch': (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int]),
+        # sc16 sample format on the host side of a batch
+        'gfdm_modulator_work_batch_sc16': (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_int, c_int]),
+        'gfdm_modulator_work_chunks_batch_sc16': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_int]),
+        'gfdm_receiver_work_batch_sc16': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_int]),
+        'gfdm_receiver_work_decide_batch_sc16': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_int]),
     }
 
     def __init__(self, path):
@@ -334,9 +339,33 @@ class Modulator(_Handle):
         self._ck(self._dll.gfdm_modulator_work_batch(self._h, _ptr(out), _ptr(a), a.shape[0], MEM_HOST))
         return out
 
-    def modulate_batch_host_ptr(self, out_ptr, in_ptr, n_frames):
+    def modulate_batch_host_ptr(self, out_ptr, in_ptr, n_frames, mem=MEM_HOST):
+        """HOST pointers; mem=MEM_HOST_ASYNC returns with the batch enqueued (pinned buffers; finish with sync())."""
         self._ck(self._dll.gfdm_modulator_work_batch(self._h, c_void_p(out_ptr), c_void_p(in_ptr),
-                                                     n_frames, MEM_HOST))
+                                                     n_frames, mem))
+
+    def modulate_batch_sc16(self, array, scale):
+        """[n_frames, block_size] symbols -> int16 I/Q samples [n_frames, block_size, 2] = round(x * scale), saturated."""
+        a = _c64(array)
+        self._two_dim(a, self.block_size())
+        out = np.empty(a.shape + (2,), np.int16)
+        self._ck(self._dll.gfdm_modulator_work_batch_sc16(self._h, _ptr(out), _ptr(a), scale, a.shape[0], MEM_HOST))
+        return out
+
+    def modulate_sc16_ptr(self, out_ptr, in_ptr, scale, n_frames, mem=MEM_DEVICE):
+        self._ck(self._dll.gfdm_modulator_work_batch_sc16(self._h, c_void_p(out_ptr), c_void_p(in_ptr), scale, n_frames, mem))
+
+    def modulate_chunks_batch_sc16(self, symbol_mapper, chunks, scale):
+        c = _u8(chunks)
+        self._two_dim(c, self.block_size())
+        out = np.empty(c.shape + (2,), np.int16)
+        self._ck(self._dll.gfdm_modulator_work_chunks_batch_sc16(self._h, symbol_mapper._h, _ptr(out), _ptr(c), scale,
+                                                                 c.shape[0], MEM_HOST))
+        return out
+
+    def modulate_chunks_sc16_ptr(self, symbol_mapper, out_ptr, chunks_ptr, scale, n_frames, mem=MEM_DEVICE):
+        self._ck(self._dll.gfdm_modulator_work_chunks_batch_sc16(self._h, symbol_mapper._h, c_void_p(out_ptr),
+                                                                 c_void_p(chunks_ptr), scale, n_frames, mem))
 
     def modulate_ptr(self, out_ptr, in_ptr, n_frames):
         self._ck(self._dll.gfdm_modulator_work_batch(self._h, c_void_p(out_ptr), c_void_p(in_ptr),
@@ -351,9 +380,9 @@ class Modulator(_Handle):
                                                             c.shape[0], MEM_HOST))
         return out
 
-    def modulate_chunks_batch_host_ptr(self, symbol_mapper, out_ptr, chunks_ptr, n_frames):
+    def modulate_chunks_batch_host_ptr(self, symbol_mapper, out_ptr, chunks_ptr, n_frames, mem=MEM_HOST):
         self._ck(self._dll.gfdm_modulator_work_chunks_batch(self._h, symbol_mapper._h, c_void_p(out_ptr),
-                                                            c_void_p(chunks_ptr), n_frames, MEM_HOST))
+                                                            c_void_p(chunks_ptr), n_frames, mem))
 
     def modulate_chunks_ptr(self, symbol_mapper, out_ptr, chunks_ptr, n_frames):
         self._ck(self._dll.gfdm_modulator_work_chunks_batch(self._h, symbol_mapper._h, c_void_p(out_ptr),
@@ -471,10 +500,50 @@ class Demodulator(_Handle):
             self._h, _ptr(out), _ptr(a), _ptr(e), a.shape[0], MEM_HOST))
         return out
 
-    def demodulate_batch_host_ptr(self, out_ptr, in_ptr, eq_ptr, n_frames):
+    def demodulate_batch_host_ptr(self, out_ptr, in_ptr, eq_ptr, n_frames, mem=MEM_HOST):
+        """HOST pointers; mem=MEM_HOST_ASYNC returns with the batch enqueued (pinned buffers; finish with sync())."""
         self._ck(self._dll.gfdm_receiver_work_batch(self._h, c_void_p(out_ptr), c_void_p(in_ptr),
                                                     c_void_p(eq_ptr) if eq_ptr else None,
-                                                    n_frames, MEM_HOST))
+                                                    n_frames, mem))
+
+    @staticmethod
+    def _iq(array, size):
+        a = np.ascontiguousarray(array, dtype=np.int16)
+        if a.ndim != 3 or a.shape[1] != size or a.shape[2] != 2:
+            raise RuntimeError('sc16 batches MUST have shape [n_frames, %d, 2], got %s' % (size, a.shape))
+        return a
+
+    def demodulate_batch_sc16(self, iq, scale, eq_arr=None):
+        """int16 I/Q samples [n_frames, block_size, 2] (value = sample * scale) -> soft symbols."""
+        a = self._iq(iq, self.block_size())
+        eq = None
+        if eq_arr is not None:
+            eq = _c64(eq_arr)
+            self._two_dim(eq, self.block_size())
+        out = np.empty(a.shape[:2], np.complex64)
+        self._ck(self._dll.gfdm_receiver_work_batch_sc16(self._h, _ptr(out), _ptr(a), _ptr(eq) if eq is not None else None,
+                                                         scale, a.shape[0], MEM_HOST))
+        return out
+
+    def demodulate_sc16_ptr(self, out_ptr, in_ptr, eq_ptr, scale, n_frames, mem=MEM_DEVICE):
+        self._ck(self._dll.gfdm_receiver_work_batch_sc16(self._h, c_void_p(out_ptr), c_void_p(in_ptr),
+                                                         c_void_p(eq_ptr) if eq_ptr else None, scale, n_frames, mem))
+
+    def demodulate_decide_batch_sc16(self, symbol_mapper, iq, scale, eq_arr=None):
+        a = self._iq(iq, self.block_size())
+        eq = None
+        if eq_arr is not None:
+            eq = _c64(eq_arr)
+            self._two_dim(eq, self.block_size())
+        out = np.empty(a.shape[:2], np.uint8)
+        self._ck(self._dll.gfdm_receiver_work_decide_batch_sc16(self._h, symbol_mapper._h, _ptr(out), _ptr(a),
+                                                                _ptr(eq) if eq is not None else None, scale, a.shape[0],
+                                                                MEM_HOST))
+        return out
+
+    def demodulate_decide_sc16_ptr(self, symbol_mapper, out_ptr, in_ptr, eq_ptr, scale, n_frames, mem=MEM_DEVICE):
+        self._ck(self._dll.gfdm_receiver_work_decide_batch_sc16(self._h, symbol_mapper._h, c_void_p(out_ptr), c_void_p(in_ptr),
+                                                                c_void_p(eq_ptr) if eq_ptr else None, scale, n_frames, mem))
 
     def demodulate_decide_batch(self, symbol_mapper, array, eq_arr=None):
         """time samples [n_frames, block_size] -> hard decisions (uint8 point indices) on the full grid."""
@@ -490,20 +559,20 @@ class Demodulator(_Handle):
                                                            a.shape[0], MEM_HOST))
         return out
 
-    def demodulate_decide_batch_host_ptr(self, symbol_mapper, out_ptr, in_ptr, eq_ptr, n_frames):
+    def demodulate_decide_batch_host_ptr(self, symbol_mapper, out_ptr, in_ptr, eq_ptr, n_frames, mem=MEM_HOST):
         self._ck(self._dll.gfdm_receiver_work_decide_batch(self._h, symbol_mapper._h, c_void_p(out_ptr),
                                                            c_void_p(in_ptr), c_void_p(eq_ptr) if eq_ptr else None,
-                                                           n_frames, MEM_HOST))
+                                                           n_frames, mem))
 
     def demodulate_decide_ptr(self, symbol_mapper, out_ptr, in_ptr, eq_ptr, n_frames):
         self._ck(self._dll.gfdm_receiver_work_decide_batch(self._h, symbol_mapper._h, c_void_p(out_ptr),
                                                            c_void_p(in_ptr), c_void_p(eq_ptr) if eq_ptr else None,
                                                            n_frames, MEM_DEVICE))
 
-    def demodulate_ptr(self, out_ptr, in_ptr, eq_ptr, n_frames):
+    def demodulate_ptr(self, out_ptr, in_ptr, eq_ptr, n_frames, mem=MEM_DEVICE):
         self._ck(self._dll.gfdm_receiver_work_batch(self._h, c_void_p(out_ptr), c_void_p(in_ptr),
                                                     c_void_p(eq_ptr) if eq_ptr else None,
-                                                    n_frames, MEM_DEVICE))
+                                                    n_frames, mem))
 
 
 def qpsk_constellation():
@@ -574,10 +643,10 @@ class Advanced_receiver(_Handle):
             self._h, _ptr(out), _ptr(a), _ptr(e) if e is not None else None, a.shape[0], MEM_HOST))
         return out
 
-    def demodulate_ptr(self, out_ptr, in_ptr, eq_ptr, n_frames):
+    def demodulate_ptr(self, out_ptr, in_ptr, eq_ptr, n_frames, mem=MEM_DEVICE):
         self._ck(self._dll.gfdm_advanced_receiver_work_batch(
             self._h, c_void_p(out_ptr), c_void_p(in_ptr), c_void_p(eq_ptr) if eq_ptr else None,
-            n_frames, MEM_DEVICE))
+            n_frames, mem))
 
 
 class Resource_mapper(_Handle):
@@ -848,9 +917,9 @@ class Preamble_channel_estimator(_Handle):
             self._h, _ptr(snr), _ptr(cnrs), _ptr(a), a.shape[0], MEM_HOST))
         return snr, cnrs
 
-    def estimate_frame_ptr(self, out_ptr, in_ptr, n_frames):
+    def estimate_frame_ptr(self, out_ptr, in_ptr, n_frames, mem=MEM_DEVICE):
         self._ck(self._dll.gfdm_channel_estimator_estimate_frame_batch(
-            self._h, c_void_p(out_ptr), c_void_p(in_ptr), n_frames, MEM_DEVICE))
+            self._h, c_void_p(out_ptr), c_void_p(in_ptr), n_frames, mem))
 
 
 class Transmitter(_Handle):
@@ -944,9 +1013,9 @@ class Transmitter(_Handle):
         self._ck(self._dll.gfdm_transmitter_work_chunks_batch(self._h, symbol_mapper._h, c_void_p(out_ptr),
                                                               c_void_p(chunks_ptr), ninput_size, n_frames, MEM_DEVICE))
 
-    def work_ptr(self, out_ptr, in_ptr, ninput_size, n_frames, all_antennas=False):
+    def work_ptr(self, out_ptr, in_ptr, ninput_size, n_frames, all_antennas=False, mem=MEM_DEVICE):
         fn = self._dll.gfdm_transmitter_work_all_batch if all_antennas else self._dll.gfdm_transmitter_work_batch
-        self._ck(fn(self._h, c_void_p(out_ptr), c_void_p(in_ptr), ninput_size, n_frames, MEM_DEVICE))
+        self._ck(fn(self._h, c_void_p(out_ptr), c_void_p(in_ptr), ninput_size, n_frames, mem))
 
 
 class Remove_prefix(_Handle):
@@ -965,9 +1034,8 @@ class Remove_prefix(_Handle):
         self._ck(self._dll.gfdm_remove_prefix_work_batch(self._h, _ptr(out), _ptr(a), a.shape[0], MEM_HOST))
         return out
 
-    def work_ptr(self, out_ptr, in_ptr, n_frames):
-        self._ck(self._dll.gfdm_remove_prefix_work_batch(self._h, c_void_p(out_ptr), c_void_p(in_ptr), n_frames,
-                                                         MEM_DEVICE))
+    def work_ptr(self, out_ptr, in_ptr, n_frames, mem=MEM_DEVICE):
+        self._ck(self._dll.gfdm_remove_prefix_work_batch(self._h, c_void_p(out_ptr), c_void_p(in_ptr), n_frames, mem))
 
 
 class Extract_burst(_Handle):

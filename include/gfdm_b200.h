@@ -56,7 +56,16 @@ typedef enum gfdm_status {
 
 typedef enum gfdm_mem {
     GFDM_MEM_HOST = 0,
-    GFDM_MEM_DEVICE = 1
+    GFDM_MEM_DEVICE = 1,
+    /* HOST pointers, asynchronous: the call returns once the chunked copies and kernels of the batch are enqueued
+     * (host->device on one copy stream, kernels on the handle's stream, device->host on a second copy stream); the
+     * output is valid -- and the input may be reused -- after gfdm_sync(handle).  Buffers MUST be page-locked
+     * (cudaHostAlloc / cudaHostRegister), otherwise the copies degrade to synchronous ones.  Lets a caller overlap the
+     * device->host leg of one handle (a modulator) with the host->device leg of another (a receiver), i.e. use both
+     * PCIe directions at once.  Accepted by the pipelined batch entries only: gfdm_modulator_work[_chunks]_batch[_sc16],
+     * gfdm_receiver_*_batch[_sc16], gfdm_receiver_work_decide_batch[_sc16], gfdm_advanced_receiver_work_batch,
+     * gfdm_transmitter_work_chunks_batch, gfdm_remove_prefix_work_batch, gfdm_resource_mapper_demap_chunks_batch. */
+    GFDM_MEM_HOST_ASYNC = 2
 } gfdm_mem;
 
 /* ---- library-wide ------------------------------------------------------- */
@@ -392,6 +401,25 @@ GFDM_B200_API int gfdm_receiver_work_decide_batch(gfdm_receiver* h, const gfdm_s
 GFDM_B200_API int gfdm_resource_mapper_demap_chunks_batch(gfdm_resource_mapper* h, unsigned char* out,
                                                           const unsigned char* in, size_t size_per_frame,
                                                           int n_frames, int mem);
+
+/* ---- sc16 sample format on the host side of a batch ------------------------------------------------------
+ * Time-domain samples cross the host<->device link as interleaved int16 I/Q ("sc16", the wire format of the SDR front
+ * ends the reference's flowgraphs feed, e.g. UHD's sc16) instead of complex64: 4 instead of 8 bytes per sample on the
+ * PCIe leg that bounds every HOST batch.  Arithmetic stays fp32 on the device:
+ *   modulator: out_sc16[i] = saturate_int16(round_to_nearest_even(generic_work(in)[i] * scale))   (re, im separately)
+ *   receiver : generic_work[_equalize] runs on in[i] = (float)in_sc16[i] * (1.0f / scale)
+ * `mem` as for the complex64 entries (HOST, DEVICE, HOST_ASYNC).  The quantisation is part of the FORMAT, not of the
+ * kernels: the complex64 entries remain the parity path (north_star tolerance); tests hold these entries to
+ * +-1 LSB of the quantised oracle output (modulator) and to the usual tolerance on identical int16 input (receiver). */
+GFDM_B200_API int gfdm_modulator_work_batch_sc16(gfdm_modulator* h, short* out_iq, const gfdm_complex* in, float scale,
+                                                 int n_frames, int mem);
+GFDM_B200_API int gfdm_modulator_work_chunks_batch_sc16(gfdm_modulator* h, const gfdm_symbol_mapper* sm, short* out_iq,
+                                                        const unsigned char* chunks, float scale, int n_frames, int mem);
+GFDM_B200_API int gfdm_receiver_work_batch_sc16(gfdm_receiver* h, gfdm_complex* out, const short* in_iq,
+                                                const gfdm_complex* f_eq_in, float scale, int n_frames, int mem);
+GFDM_B200_API int gfdm_receiver_work_decide_batch_sc16(gfdm_receiver* h, const gfdm_symbol_mapper* sm,
+                                                       unsigned char* chunks_out, const short* in_iq,
+                                                       const gfdm_complex* f_eq_in, float scale, int n_frames, int mem);
 
 #ifdef __cplusplus
 }

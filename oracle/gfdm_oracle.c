@@ -38,7 +38,7 @@ static int fail(int code, const char* msg)
 }
 
 #define REQUIRE_HOST(mem)    \
-    if ((mem) != GFDM_MEM_HOST) \
+    if ((mem) != GFDM_MEM_HOST && (mem) != GFDM_MEM_HOST_ASYNC) /* a CPU library is trivially 'complete at return' */ \
         return fail(GFDM_ERR_UNSUPPORTED, "oracle-port is CPU only: GFDM_MEM_DEVICE is not supported");
 
 static inline cf cf_make(float re, float im) { cf r = { re, im }; return r; }

@@ -54,7 +54,7 @@ static int fail(int code, const std::string& msg)
     return GFDM_OK;
 
 #define REQUIRE_HOST(mem)                                                                 \
-    if ((mem) != GFDM_MEM_HOST)                                                           \
+    if ((mem) != GFDM_MEM_HOST && (mem) != GFDM_MEM_HOST_ASYNC) /* a CPU library is trivially 'complete at return' */                                                           \
         return fail(GFDM_ERR_UNSUPPORTED, "oracle-ref is CPU only: GFDM_MEM_DEVICE is not supported");
 
 static inline cf* C(gfdm_complex* p) { return reinterpret_cast<cf*>(p); }
