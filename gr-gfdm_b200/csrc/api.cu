@@ -290,7 +290,10 @@ static size_t pipe_chunk(size_t bytes_per_frame, size_t n)
     const size_t budget = (override_mb ? override_mb : (size_t)32) << 20;
     size_t c = budget / (bytes_per_frame ? bytes_per_frame : 1);
     if (c < 1) c = 1;
-    return c < n ? c : n;
+    if (c >= n) return n;
+    // equal chunks: a short last chunk would leave one copy engine idle for most of a pipeline step
+    const size_t k = (n + c - 1) / c;
+    return (n + k - 1) / k;
 }
 
 /* ======================================================================== */
@@ -1397,6 +1400,56 @@ static void tx_add_frame(gfdm_transmitter* h, cpx* out, const cpx* blk, int shif
     h->launches += 2;
 }
 
+// Shaper parameters as the kernels see them (gfdm_burst_shaper below owns them)
+struct ShaperArgs {
+    int pre = 0, post = 0;
+    cpx scale = make_float2(1.f, 0.f);
+};
+
+// transmitter_kernel::generic_work for nf frames on DEVICE pointers, n_ant antennas (cyclic shifts): antenna a at
+// out + a*ant_stride, one row per frame.  One kernel for the whole chain when the shape has a shared-memory resident
+// modulator, separate kernels otherwise.  sh != nullptr: every row passes through the short_burst_shaper as well
+// (row = pre + out_size + post) -- inside the same kernel on the fused path.
+static void tx_chain_device(gfdm_transmitter* h, cpx* out, size_t ant_stride, const cpx* di, size_t in_sz, size_t nf, size_t n_ant,
+                            const ShaperArgs* sh)
+{
+    if (!nf) return;
+    const size_t N = h->N, os = h->out_size();
+    TxArgs ta;
+    ta.inv_map = h->map.d_inv; ta.front = h->pre.d_front; ta.back = h->pre.d_back; ta.preambles = h->d_preambles;
+    ta.A = h->map.A; ta.per_timeslot = h->map.per_timeslot ? 1 : 0; ta.n_in = (int)in_sz;
+    ta.cp = h->pre.cp_len; ta.cs = h->pre.cs_len; ta.ramp = h->pre.ramp_len; ta.P = h->preamble_size;
+    ta.n_ant = (int)n_ant;
+    ta.ant_stride = ant_stride;
+    for (size_t a = 0; a < n_ant && a < (size_t)GFDM_TX_MAX_ANT; ++a) {
+        ta.shift[a] = h->shifts[a];
+        ta.pre_idx[a] = h->shift_index(h->shifts[a]);
+    }
+    if (sh) {
+        ta.shaped = 1; ta.pre_pad = sh->pre; ta.post_pad = sh->post; ta.sc_re = sh->scale.x; ta.sc_im = sh->scale.y;
+    }
+    if (!h->force_staged && h->fused.available() && h->fused.supports_tx_chain(ta) && aligned16(di)) {
+        h->launches += h->fused.transmit(out, di, ta, nf, h->stream);
+        h->last_kernel = h->fused.tx_name();
+        return;
+    }
+    h->frame.ensure(nf * N * sizeof(cpx));
+    tx_modulate(h, h->frame.as<cpx>(), di, in_sz, nf);
+    for (size_t a = 0; a < n_ant; ++a) {
+        cpx* o = out + a * ant_stride;
+        if (!sh) {
+            tx_add_frame(h, o, h->frame.as<cpx>(), h->shifts[a], nf);
+        } else {
+            h->work_c.ensure(nf * os * sizeof(cpx));
+            tx_add_frame(h, h->work_c.as<cpx>(), h->frame.as<cpx>(), h->shifts[a], nf);
+            launch_burst_shape(o, h->work_c.as<cpx>(), (int)os, sh->pre, sh->post, sh->scale, nf, h->stream);
+            h->launches += 1;
+        }
+    }
+    h->last_kernel = h->fused.available() ? (sh ? "map+fused_mod+copy_rows+add_cp+burst_shape" : "map+fused_mod+copy_rows+add_cp")
+                                          : "generic:transmitter";
+}
+
 int gfdm_transmitter_create(gfdm_transmitter** out, int M, int K, int A, int cp, int cs, int ramp, const int* smap,
                             int n_map, int per_timeslot, int L, const gfdm_complex* taps, int n_taps,
                             const gfdm_complex* w, int n_w, const int* shifts, int n_shifts,
@@ -1498,32 +1551,10 @@ static int transmitter_batch(gfdm_transmitter* h, TxOp op, gfdm_complex* out, co
             h->last_kernel = "copy_rows+add_cp_kernel";
             break;
         case TX_WORK:
-        case TX_WORK_ALL: {
-            // one kernel for the whole chain when the shape has a shared-memory resident modulator
-            TxArgs ta;
-            ta.inv_map = h->map.d_inv; ta.front = h->pre.d_front; ta.back = h->pre.d_back; ta.preambles = h->d_preambles;
-            ta.A = h->map.A; ta.per_timeslot = h->map.per_timeslot ? 1 : 0; ta.n_in = (int)in_sz;
-            ta.cp = h->pre.cp_len; ta.cs = h->pre.cs_len; ta.ramp = h->pre.ramp_len; ta.P = h->preamble_size;
-            ta.n_ant = (int)n_ant;
-            ta.ant_stride = (mem == GFDM_MEM_DEVICE ? (size_t)n : nf) * os;
-            for (size_t a = 0; a < n_ant && a < (size_t)GFDM_TX_MAX_ANT; ++a) {
-                ta.shift[a] = h->shifts[a];
-                ta.pre_idx[a] = h->shift_index(h->shifts[a]);
-            }
-            if (!h->force_staged && h->fused.available() && h->fused.supports_tx_chain(ta) && aligned16(di)) {
-                h->launches += h->fused.transmit(mem == GFDM_MEM_DEVICE ? dout + f0 * os : dout, di, ta, nf, h->stream);
-                h->last_kernel = h->fused.tx_name();
-                break;
-            }
-            h->frame.ensure(nf * N * sizeof(cpx));
-            tx_modulate(h, h->frame.as<cpx>(), di, in_sz, nf);
-            for (size_t a = 0; a < n_ant; ++a) {
-                cpx* o = mem == GFDM_MEM_DEVICE ? dout + (a * (size_t)n + f0) * os : dout + a * nf * os;
-                tx_add_frame(h, o, h->frame.as<cpx>(), h->shifts[a], nf);
-            }
-            h->last_kernel = h->fused.available() ? "map+fused_mod+copy_rows+add_cp" : "generic:transmitter";
+        case TX_WORK_ALL:
+            tx_chain_device(h, mem == GFDM_MEM_DEVICE ? dout + f0 * os : dout, (mem == GFDM_MEM_DEVICE ? (size_t)n : nf) * os, di,
+                            in_sz, nf, n_ant, nullptr);
             break;
-        }
         }
         if (mem == GFDM_MEM_HOST) {
             for (size_t a = 0; a < n_ant; ++a)
@@ -1991,6 +2022,79 @@ int gfdm_resource_mapper_demap_chunks_batch(gfdm_resource_mapper* h, unsigned ch
         run(out, in, nullptr, 0, (size_t)n);
     else
         host_pipeline_bytes(h, (size_t)n, pipe_chunk(fs + sz, (size_t)n), in, fs, nullptr, 0, out, sz, false, st.async, run);
+    API_CATCH
+}
+
+/* ---- short_burst_shaper: lib/short_burst_shaper_impl.cc:57-84, 161-182 ------ */
+struct gfdm_burst_shaper : HandleBase {
+    ShaperArgs a;
+};
+int gfdm_burst_shaper_create(gfdm_burst_shaper** out, int pre_padding, int post_padding, float scale_re, float scale_im)
+{
+    API_TRY
+    if (pre_padding < 0) throw std::invalid_argument("Pre-padding length MUST be >= 0!");   // :77-79
+    if (post_padding < 0) throw std::invalid_argument("Post-padding length MUST be >= 0!"); // :80-82
+    std::unique_ptr<gfdm_burst_shaper, void (*)(gfdm_burst_shaper*)> h(new gfdm_burst_shaper, gfdm_burst_shaper_destroy);
+    h->a.pre = pre_padding; h->a.post = post_padding; h->a.scale = make_float2(scale_re, scale_im);
+    h->open();
+    *out = h.release();
+    API_CATCH
+}
+void gfdm_burst_shaper_destroy(gfdm_burst_shaper* h)
+{
+    if (!h) return;
+    if (h->opened) cudaSetDevice(h->device);
+    h->close();
+    delete h;
+}
+int gfdm_burst_shaper_pre_padding(const gfdm_burst_shaper* h) { return h->a.pre; }
+int gfdm_burst_shaper_post_padding(const gfdm_burst_shaper* h) { return h->a.post; }
+int gfdm_burst_shaper_work_batch(gfdm_burst_shaper* h, gfdm_complex* out, const gfdm_complex* in, int burst_len, int n, int mem)
+{
+    API_TRY
+    h->use();
+    if (n < 0 || burst_len < 0) throw std::invalid_argument("burst_len and n_bursts MUST NOT be negative");
+    Staging st(h, mem, true);
+    const size_t row = (size_t)h->a.pre + burst_len + h->a.post;
+    auto run = [&](cpx* dout, const cpx* d0, const cpx*, size_t, size_t nf) {
+        launch_burst_shape(dout, d0, burst_len, h->a.pre, h->a.post, h->a.scale, nf, h->stream);
+        h->launches += 1;
+        h->last_kernel = "burst_shape_kernel";
+    };
+    if (mem == GFDM_MEM_DEVICE)
+        run(reinterpret_cast<cpx*>(out), reinterpret_cast<const cpx*>(in), nullptr, 0, (size_t)n);
+    else
+        host_pipeline(h, (size_t)n, pipe_chunk(sizeof(cpx) * (row + burst_len), (size_t)n), in, (size_t)burst_len, nullptr, 0, out, row,
+                      false, st.async, run);
+    API_CATCH
+}
+int gfdm_transmitter_work_shaped_batch(gfdm_transmitter* h, const gfdm_burst_shaper* sh, gfdm_complex* out, const gfdm_complex* in,
+                                       int nin, int n, int all_antennas, int mem)
+{
+    API_TRY
+    h->use();
+    if (!sh || sh->magic != HANDLE_MAGIC) throw std::invalid_argument("burst shaper MUST NOT be NULL");
+    if (sh->device != h->device) throw std::invalid_argument("the burst shaper lives on another device");
+    if (n < 0) throw std::invalid_argument("n_frames MUST NOT be negative");
+    if (nin < 0) throw std::invalid_argument("ninput_size MUST NOT be negative");
+    h->map.check_map_size((size_t)nin);
+    for (int s : h->shifts) h->pre.check_shift(s);
+    Staging st(h, mem);
+    const size_t row = (size_t)sh->a.pre + h->out_size() + sh->a.post, n_ant = all_antennas ? h->shifts.size() : 1;
+    const size_t c = mem == GFDM_MEM_DEVICE ? (size_t)n : chunk_frames(sizeof(cpx) * ((size_t)nin + row * n_ant + 4 * (size_t)h->N), (size_t)n);
+    for (size_t f0 = 0; f0 < (size_t)n; f0 += c) {
+        const size_t nf = std::min(c, (size_t)n - f0);
+        const cpx* di = nin ? st.in(in + f0 * (size_t)nin, nf * (size_t)nin, h->stage_in) : nullptr;
+        cpx* dout = mem == GFDM_MEM_DEVICE ? reinterpret_cast<cpx*>(out) : st.out(out, nf * row * n_ant, h->stage_out);
+        tx_chain_device(h, mem == GFDM_MEM_DEVICE ? dout + f0 * row : dout, (mem == GFDM_MEM_DEVICE ? (size_t)n : nf) * row, di,
+                        (size_t)nin, nf, n_ant, &sh->a);
+        if (mem == GFDM_MEM_HOST) {
+            for (size_t a = 0; a < n_ant; ++a)
+                GFDM_CUDA_CHECK(cudaMemcpyAsync(out + (a * (size_t)n + f0) * row, dout + a * nf * row, nf * row * sizeof(cpx),
+                                                cudaMemcpyDeviceToHost, h->stream));
+            h->sync();
+        }
+    }
     API_CATCH
 }
 

@@ -81,6 +81,8 @@ void launch_symbols2bits(unsigned char* bits, const cpx* in, const cpx* points, 
 // sc16 host sample format: complex64 <-> interleaved int16 I/Q (n complex samples; aligned arrays, see next_kernels.cu)
 void launch_cf32_to_sc16(short* out, const cpx* in, float scale, size_t n, cudaStream_t s);
 void launch_sc16_to_cf32(cpx* out, const short* in, float scale, size_t n, cudaStream_t s);
+// short_burst_shaper (lib/short_burst_shaper_impl.cc:161-182): [pre zeros | in * scale | post zeros] per burst of `len`
+void launch_burst_shape(cpx* out, const cpx* in, int len, int pre, int post, cpx scale, size_t n_bursts, cudaStream_t s);
 void launch_demap_chunks(unsigned char* out, const unsigned char* in, const int* smap, int M, int K, int A, bool per_timeslot,
                          size_t n_out, size_t frames, cudaStream_t s);
 

@@ -27,6 +27,10 @@ struct TxArgs {
     // chunk input (one byte per symbol): constellation points, device pointer
     const cpx* points = nullptr;
     int n_points = 0;
+    // short_burst_shaper epilogue (lib/short_burst_shaper_impl.cc:161-182): every output row becomes
+    // [pre_pad zeros | scale * (preamble | frame) | post_pad zeros]
+    int shaped = 0, pre_pad = 0, post_pad = 0;
+    float sc_re = 1.f, sc_im = 0.f;
 };
 constexpr int GFDM_FUSED_MAX_POINTS = 64; // constellation size the fused kernels keep in shared memory
 

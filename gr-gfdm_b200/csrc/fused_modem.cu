@@ -38,12 +38,13 @@ namespace gfdm {
 // transmitter chain, stage C: the few output positions that carry a window ramp and/or are written twice (cyclic
 // prefix / suffix).  Out of line so that the unrolled common case stays one compare and one store.
 static __device__ __noinline__ void tx_store_edge(cpx* o, int i, cpx v, int N, int W, int ramp, const cpx* front,
-                                                  const cpx* back)
+                                                  const cpx* back, bool shaped, cpx scale)
 {
     for (; i < W; i += N) {
         cpx val = v;
         if (i < ramp) val = cmul_rn(val, __ldg(front + i));
         if (i >= W - ramp) val = cmul_rn(val, __ldg(back + (i - (W - ramp))));
+        if (shaped) val = cmul_rn(val, scale); // short_burst_shaper: after the window, as the block chain orders them
         stg_stream(o + i, val);
     }
 }
@@ -276,15 +277,17 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_mod_kernel(cpx* __restric
                 // add_cyclic_prefix: o[i] = x[(i + N - cp - s) mod N], i < W = N + cp + cs  <=>  sample n goes to
                 // i = (n + cp + s) mod N and again to i + N while that is < W; ramps on the first / last samples.
                 // Positions lo <= i < hi are neither ramped nor duplicated: one compare, one store.
-                const int W = N + tx.cp + tx.cs, os = tx.P + W, dup = tx.cp + tx.cs;
+                const int W = N + tx.cp + tx.cs, os = tx.pre_pad + tx.P + W + tx.post_pad, dup = tx.cp + tx.cs;
                 const int lo = max(tx.ramp, dup), hi = max(lo, min(N, W - tx.ramp));
+                const bool shaped = tx.shaped != 0;
+                const cpx scale = cmake(tx.sc_re, tx.sc_im);
                 for (int a = 0; a < tx.n_ant; ++a) {
-                    cpx* o = out + (size_t)a * tx.ant_stride + ((size_t)g * F + f) * os + tx.P;
+                    cpx* o = out + (size_t)a * tx.ant_stride + ((size_t)g * F + f) * os + tx.pre_pad + tx.P;
                     int i = (n1 + tx.cp + tx.shift[a]) % N;
 #pragma unroll
                     for (int n2 = 0; n2 < M; ++n2) {
-                        if ((unsigned)(i - lo) < (unsigned)(hi - lo)) stg_stream(o + i, v[j][n2]);
-                        else tx_store_edge(o, i, v[j][n2], N, W, tx.ramp, tx.front, tx.back);
+                        if ((unsigned)(i - lo) < (unsigned)(hi - lo)) stg_stream(o + i, shaped ? cmul_rn(v[j][n2], scale) : v[j][n2]);
+                        else tx_store_edge(o, i, v[j][n2], N, W, tx.ramp, tx.front, tx.back, shaped, scale);
                         i += K;
                         i = (int)min((unsigned)i, (unsigned)(i - N)); // wrap at N without a branch (i < 2N)
                     }
@@ -293,15 +296,22 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_mod_kernel(cpx* __restric
         }
         if constexpr (TXF) {
             // insert_preamble (lib/transmitter_kernel.cc:86-90): the shift's preamble in front of every frame
-            const int os = tx.P + N + tx.cp + tx.cs;
+            const int W = N + tx.cp + tx.cs, os = tx.pre_pad + tx.P + W + tx.post_pad;
+            const bool shaped = tx.shaped != 0;
+            const cpx scale = cmake(tx.sc_re, tx.sc_im);
             for (int a = 0; a < tx.n_ant; ++a) {
                 const cpx* p = tx.preambles + (size_t)tx.pre_idx[a] * tx.P;
                 // 16-byte copies when every row start is 16-byte aligned (even P, even row length, aligned bases)
-                const bool vec = ((tx.P | os) & 1) == 0 && (tx.ant_stride & 1) == 0 &&
+                const bool vec = !shaped && ((tx.P | os) & 1) == 0 && (tx.ant_stride & 1) == 0 &&
                                  ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(p)) & 15) == 0;
                 for (int f = 0; f < fh; ++f) {
-                    cpx* o = out + (size_t)a * tx.ant_stride + ((size_t)g * F + f) * os;
-                    if (vec) {
+                    cpx* o = out + (size_t)a * tx.ant_stride + ((size_t)g * F + f) * os + tx.pre_pad;
+                    if (shaped) {
+                        // short_burst_shaper: zero padding either side of the burst, preamble scaled like the frame
+                        for (int i = tid; i < tx.pre_pad; i += T) stg_stream(o - tx.pre_pad + i, cmake(0.f, 0.f));
+                        for (int i = tid; i < tx.post_pad; i += T) stg_stream(o + tx.P + W + i, cmake(0.f, 0.f));
+                        for (int i = tid; i < tx.P; i += T) stg_stream(o + i, cmul_rn(ldg_nc(p + i), scale));
+                    } else if (vec) {
                         for (int i = tid; i < tx.P / 2; i += T) {
                             const float4 q = __ldg(reinterpret_cast<const float4*>(p) + i);
                             stg_stream4(o + 2 * i, cmake(q.x, q.y), cmake(q.z, q.w));
@@ -973,7 +983,7 @@ int FusedModem::transmit(cpx* out, const cpx* in, const TxArgs& tx, size_t frame
     const ShapeEntry* e = impl_->e;
     if (!impl_->tx_grid_cap) impl_->tx_grid_cap = fused_grid_cap(e->tx_fn, e->T, e->smem);
     int launches = 0;
-    const size_t os = (size_t)tx.P + (size_t)e->M * e->K + tx.cp + tx.cs;
+    const size_t os = (size_t)tx.pre_pad + tx.P + (size_t)e->M * e->K + tx.cp + tx.cs + tx.post_pad;
     const size_t max_chunk = (size_t)1 << 20; // keep frame counts in int range
     for (size_t f0 = 0; f0 < frames; f0 += max_chunk) {
         const int nf = (int)std::min(max_chunk, frames - f0);
@@ -1031,7 +1041,7 @@ int FusedModem::transmit_chunks(cpx* out, const unsigned char* chunks, const TxA
     const ShapeEntry* e = impl_->e;
     if (!impl_->txc_grid_cap) impl_->txc_grid_cap = fused_grid_cap(e->txc_fn, e->T, e->smem);
     int launches = 0;
-    const size_t os = (size_t)tx.P + (size_t)e->M * e->K + tx.cp + tx.cs;
+    const size_t os = (size_t)tx.pre_pad + tx.P + (size_t)e->M * e->K + tx.cp + tx.cs + tx.post_pad;
     const size_t max_chunk = (size_t)1 << 20;
     for (size_t f0 = 0; f0 < frames; f0 += max_chunk) {
         const int nf = (int)std::min(max_chunk, frames - f0);

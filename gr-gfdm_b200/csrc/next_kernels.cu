@@ -298,4 +298,27 @@ void launch_sc16_to_cf32(cpx* out, const short* in, float scale, size_t n, cudaS
     GFDM_CUDA_CHECK(cudaGetLastError());
 }
 
+// ---------------------------------------------------------------------------------------------
+// short_burst_shaper (lib/short_burst_shaper_impl.cc:161-182): out = [pre zeros | in * scale | post zeros] per burst;
+// the multiply is volk_32fc_s32fc_multiply_32fc's plain complex product (unfused, reference operand order).
+__global__ void __launch_bounds__(TH) burst_shape_kernel(cpx* __restrict__ out, const cpx* __restrict__ in, int len, int pre,
+                                                         int post, cpx scale, size_t total)
+{
+    const size_t row = (size_t)pre + len + post;
+    for (size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x; gid < total; gid += (size_t)gridDim.x * blockDim.x) {
+        const size_t b = gid / row;
+        const int i = (int)(gid - b * row) - pre;
+        cpx v = cmake(0.f, 0.f);
+        if (i >= 0 && i < len) v = cmul_rn(ldg_stream_cpx(in + b * (size_t)len + i), scale);
+        out[gid] = v;
+    }
+}
+void launch_burst_shape(cpx* out, const cpx* in, int len, int pre, int post, cpx scale, size_t n_bursts, cudaStream_t s)
+{
+    const size_t total = n_bursts * ((size_t)pre + len + post);
+    if (!total) return;
+    burst_shape_kernel<<<grid_for(total, TH), TH, 0, s>>>(out, in, len, pre, post, scale, total);
+    GFDM_CUDA_CHECK(cudaGetLastError());
+}
+
 } // namespace gfdm

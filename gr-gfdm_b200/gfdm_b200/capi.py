@@ -172,6 +172,12 @@ class Library(object):
         'gfdm_transmitter_work_chunks_batch': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int]),
         'gfdm_receiver_work_decide_batch': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int]),
         'gfdm_resource_mapper_demap_chunks_batch': (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int]),
+        'gfdm_burst_shaper_create': (c_int, [POINTER(c_void_p), c_int, c_int, c_float, c_float]),
+        'gfdm_burst_shaper_destroy': (None, [c_void_p]),
+        'gfdm_burst_shaper_pre_padding': (c_int, [c_void_p]),
+        'gfdm_burst_shaper_post_padding': (c_int, [c_void_p]),
+        'gfdm_burst_shaper_work_batch': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int]),
+        'gfdm_transmitter_work_shaped_batch': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int]),
         # sc16 sample format on the host side of a batch
         'gfdm_modulator_work_batch_sc16': (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_int, c_int]),
         'gfdm_modulator_work_chunks_batch_sc16': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_int]),
@@ -1009,6 +1015,22 @@ class Transmitter(_Handle):
                                                               c.shape[1], c.shape[0], MEM_HOST))
         return out
 
+    def work_shaped_batch(self, shaper, array, all_antennas=False):
+        """transmitter chain + short_burst_shaper epilogue: [n_frames, pre + output_vector_size + post] (per antenna)."""
+        a = _c64(array)
+        if a.ndim != 2:
+            raise RuntimeError('batch arrays MUST have shape [n_frames, ninput_size]')
+        n_ant = len(self.cyclic_shifts()) if all_antennas else 1
+        row = shaper.pre_padding + self.output_vector_size() + shaper.post_padding
+        out = np.empty((n_ant, a.shape[0], row), np.complex64)
+        self._ck(self._dll.gfdm_transmitter_work_shaped_batch(self._h, shaper._h, _ptr(out), _ptr(a), a.shape[1], a.shape[0],
+                                                              int(bool(all_antennas)), MEM_HOST))
+        return out if all_antennas else out[0]
+
+    def work_shaped_ptr(self, shaper, out_ptr, in_ptr, ninput_size, n_frames, all_antennas=False, mem=MEM_DEVICE):
+        self._ck(self._dll.gfdm_transmitter_work_shaped_batch(self._h, shaper._h, c_void_p(out_ptr), c_void_p(in_ptr), ninput_size,
+                                                              n_frames, int(bool(all_antennas)), mem))
+
     def work_chunks_ptr(self, symbol_mapper, out_ptr, chunks_ptr, ninput_size, n_frames):
         self._ck(self._dll.gfdm_transmitter_work_chunks_batch(self._h, symbol_mapper._h, c_void_p(out_ptr),
                                                               c_void_p(chunks_ptr), ninput_size, n_frames, MEM_DEVICE))
@@ -1016,6 +1038,28 @@ class Transmitter(_Handle):
     def work_ptr(self, out_ptr, in_ptr, ninput_size, n_frames, all_antennas=False, mem=MEM_DEVICE):
         fn = self._dll.gfdm_transmitter_work_all_batch if all_antennas else self._dll.gfdm_transmitter_work_batch
         self._ck(fn(self._h, c_void_p(out_ptr), c_void_p(in_ptr), ninput_size, n_frames, mem))
+
+
+class Burst_shaper(_Handle):
+    """short_burst_shaper's sample path (lib/short_burst_shaper_impl.cc:161-182): [pre zeros | in * scale | post zeros]."""
+    _destroy = 'gfdm_burst_shaper_destroy'
+
+    def __init__(self, pre_padding, post_padding, scale=1.0, lib=None):
+        _Handle.__init__(self, lib)
+        sc = complex(scale)
+        self.pre_padding, self.post_padding, self.scale = pre_padding, post_padding, np.complex64(sc)
+        self._ck(self._dll.gfdm_burst_shaper_create(byref(self._h), pre_padding, post_padding, sc.real, sc.imag))
+
+    def work_batch(self, array):
+        a = _c64(array)
+        if a.ndim != 2:
+            raise RuntimeError('batch arrays MUST have shape [n_bursts, burst_len]')
+        out = np.empty((a.shape[0], self.pre_padding + a.shape[1] + self.post_padding), np.complex64)
+        self._ck(self._dll.gfdm_burst_shaper_work_batch(self._h, _ptr(out), _ptr(a), a.shape[1], a.shape[0], MEM_HOST))
+        return out
+
+    def work_ptr(self, out_ptr, in_ptr, burst_len, n_bursts, mem=MEM_DEVICE):
+        self._ck(self._dll.gfdm_burst_shaper_work_batch(self._h, c_void_p(out_ptr), c_void_p(in_ptr), burst_len, n_bursts, mem))
 
 
 class Remove_prefix(_Handle):

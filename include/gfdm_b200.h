@@ -402,6 +402,25 @@ GFDM_B200_API int gfdm_resource_mapper_demap_chunks_batch(gfdm_resource_mapper* 
                                                           const unsigned char* in, size_t size_per_frame,
                                                           int n_frames, int mem);
 
+/* ---- short_burst_shaper: lib/short_burst_shaper_impl.cc:57-84 (ctor checks), :161-182 (work) ---------------------
+ * The sample path of the block that follows the transmitter in the reference's flowgraphs: every burst becomes
+ *   [pre_padding zeros | in * scale | post_padding zeros]      (volk_32fc_s32fc_multiply_32fc: plain complex product).
+ * The block's timed-command / message handling (:185-230) is radio control, not sample processing, and is out of scope.
+ * gfdm_transmitter_work_shaped_batch runs the transmitter chain with this step as the EPILOGUE of the same kernel
+ * (single-pass shapes; composition of the two elsewhere):
+ *   out [n_ant][n_frames][pre + output_vector_size + post], n_ant = all_antennas ? n_cyclic_shifts : 1. */
+typedef struct gfdm_burst_shaper gfdm_burst_shaper;
+GFDM_B200_API int gfdm_burst_shaper_create(gfdm_burst_shaper** out, int pre_padding, int post_padding, float scale_re,
+                                           float scale_im);
+GFDM_B200_API void gfdm_burst_shaper_destroy(gfdm_burst_shaper* h);
+GFDM_B200_API int gfdm_burst_shaper_pre_padding(const gfdm_burst_shaper* h);
+GFDM_B200_API int gfdm_burst_shaper_post_padding(const gfdm_burst_shaper* h);
+GFDM_B200_API int gfdm_burst_shaper_work_batch(gfdm_burst_shaper* h, gfdm_complex* out, const gfdm_complex* in,
+                                               int burst_len, int n_bursts, int mem);
+GFDM_B200_API int gfdm_transmitter_work_shaped_batch(gfdm_transmitter* h, const gfdm_burst_shaper* shaper,
+                                                     gfdm_complex* out, const gfdm_complex* in, int ninput_size,
+                                                     int n_frames, int all_antennas, int mem);
+
 /* ---- sc16 sample format on the host side of a batch ------------------------------------------------------
  * Time-domain samples cross the host<->device link as interleaved int16 I/Q ("sc16", the wire format of the SDR front
  * ends the reference's flowgraphs feed, e.g. UHD's sc16) instead of complex64: 4 instead of 8 bytes per sample on the

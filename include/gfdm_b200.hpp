@@ -29,9 +29,15 @@
 #include "gfdm_b200.h"
 
 #include <complex>
+#include <condition_variable>
 #include <cstddef>
+#include <exception>
+#include <functional>
+#include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -493,6 +499,29 @@ private:
 };
 
 // ---------------------------------------------------------------------------
+// lib/short_burst_shaper_impl.cc:57-84 (ctor checks), :161-182 (sample path): [pre zeros | in * scale | post zeros]
+class burst_shaper : public stream_control<burst_shaper>
+{
+public:
+    typedef std::complex<float> gfdm_complex;
+    burst_shaper(int pre_padding, int post_padding, gfdm_complex scale)
+    {
+        detail::check(gfdm_burst_shaper_create(d_h.out(), pre_padding, post_padding, scale.real(), scale.imag()));
+    }
+    int pre_padding() const { return gfdm_burst_shaper_pre_padding(d_h.get()); }
+    int post_padding() const { return gfdm_burst_shaper_post_padding(d_h.get()); }
+    // out[n_bursts][pre + burst_len + post]
+    void work_batch(gfdm_complex* p_out, const gfdm_complex* p_in, int burst_len, int n_bursts, int mem = GFDM_MEM_HOST)
+    {
+        detail::check(gfdm_burst_shaper_work_batch(d_h.get(), detail::c(p_out), detail::c(p_in), burst_len, n_bursts, mem));
+    }
+    gfdm_burst_shaper* raw() const { return d_h.get(); }
+
+private:
+    detail::handle<gfdm_burst_shaper, gfdm_burst_shaper_destroy> d_h;
+};
+
+// ---------------------------------------------------------------------------
 // lib/transmitter_kernel.cc:34-107
 class transmitter_kernel : public stream_control<transmitter_kernel>
 {
@@ -543,6 +572,13 @@ public:
     {
         detail::check(
             gfdm_transmitter_work_all_batch(d_h.get(), detail::c(p_out), detail::c(p_in), ninput_size, n_frames, mem));
+    }
+    // the chain with the short_burst_shaper as the kernel's epilogue: out[n_ant][n_frames][pre + output_vector_size() + post]
+    void generic_work_shaped_batch(const burst_shaper& shaper, gfdm_complex* p_out, const gfdm_complex* p_in, int ninput_size,
+                                   int n_frames, bool all_antennas = false, int mem = GFDM_MEM_HOST)
+    {
+        detail::check(gfdm_transmitter_work_shaped_batch(d_h.get(), shaper.raw(), detail::c(p_out), detail::c(p_in), ninput_size,
+                                                         n_frames, all_antennas ? 1 : 0, mem));
     }
     const std::vector<int>& cyclic_shifts() const { return d_cyclic_shifts; }
     void* raw() const { return d_h.get(); }
@@ -674,6 +710,124 @@ public:
 
 private:
     detail::handle<gfdm_symbol_mapper, gfdm_symbol_mapper_destroy> d_h;
+};
+
+// ---------------------------------------------------------------------------
+// Single-process multi-GPU driver ("one host thread + one or two CUDA streams per GPU").
+// Frames are independent (lib/simple_modulator_cc_impl.cc:72-76), so a batch is split contiguously over the devices and
+// nothing is exchanged between them.  One persistent worker thread per device: device selection is per host thread
+// (gfdm_set_device), every worker creates its OWN kernel object through `make` after selecting its device, and
+// for_each_shard(n, fn) runs fn(kernel, first_frame, n_frames) for the worker's shard on that thread; it returns when
+// every shard is done and rethrows the first exception a worker raised.
+template <class Kernel>
+class multi_gpu
+{
+public:
+    template <class Factory>
+    multi_gpu(const std::vector<int>& devices, Factory make) : d_workers(devices.size())
+    {
+        for (size_t i = 0; i < devices.size(); ++i) {
+            worker& w = d_workers[i];
+            w.device = devices[i];
+            w.thread = std::thread([this, &w, make]() {
+                try {
+                    detail::check(gfdm_set_device(w.device));
+                    w.kernel = make();
+                } catch (...) {
+                    w.error = std::current_exception();
+                }
+                signal_done(w);
+                for (;;) {
+                    std::unique_lock<std::mutex> lk(d_mutex);
+                    d_cv.wait(lk, [&w]() { return w.has_job || w.stop; });
+                    if (w.stop) break;
+                    std::function<void(Kernel&)> job = w.job;
+                    lk.unlock();
+                    try {
+                        if (w.kernel) job(*w.kernel);
+                    } catch (...) {
+                        w.error = std::current_exception();
+                    }
+                    signal_done(w);
+                }
+                w.kernel.reset(); // handles are destroyed on the thread that owns their device selection
+            });
+        }
+        wait_all(); // construction errors (no such device, invalid kernel parameters) surface here
+    }
+    ~multi_gpu()
+    {
+        {
+            std::lock_guard<std::mutex> lk(d_mutex);
+            for (worker& w : d_workers) w.stop = true;
+        }
+        d_cv.notify_all();
+        for (worker& w : d_workers)
+            if (w.thread.joinable()) w.thread.join();
+    }
+    multi_gpu(const multi_gpu&) = delete;
+    multi_gpu& operator=(const multi_gpu&) = delete;
+    size_t n_devices() const { return d_workers.size(); }
+    // contiguous split, remainder spread over the first shards: [lo, hi) of shard `rank`
+    static std::pair<size_t, size_t> shard_bounds(size_t n, size_t world, size_t rank)
+    {
+        const size_t base = n / world, rem = n % world;
+        const size_t lo = rank * base + (rank < rem ? rank : rem);
+        return { lo, lo + base + (rank < rem ? 1 : 0) };
+    }
+    template <class Fn>
+    void for_each_shard(size_t n_frames, Fn fn)
+    {
+        {
+            std::lock_guard<std::mutex> lk(d_mutex);
+            for (size_t i = 0; i < d_workers.size(); ++i) {
+                const std::pair<size_t, size_t> b = shard_bounds(n_frames, d_workers.size(), i);
+                d_workers[i].job = [fn, b](Kernel& k) { fn(k, b.first, b.second - b.first); };
+                d_workers[i].has_job = true;
+                d_workers[i].done = false;
+            }
+        }
+        d_cv.notify_all();
+        wait_all();
+    }
+
+private:
+    struct worker {
+        int device = 0;
+        std::thread thread;
+        std::unique_ptr<Kernel> kernel;
+        std::function<void(Kernel&)> job;
+        bool has_job = false, stop = false, done = false;
+        std::exception_ptr error;
+    };
+    void signal_done(worker& w)
+    {
+        {
+            std::lock_guard<std::mutex> lk(d_mutex);
+            w.has_job = false;
+            w.done = true;
+        }
+        d_cv_done.notify_all();
+    }
+    void wait_all()
+    {
+        std::unique_lock<std::mutex> lk(d_mutex);
+        d_cv_done.wait(lk, [this]() {
+            for (const worker& w : d_workers)
+                if (!w.done) return false;
+            return true;
+        });
+        for (worker& w : d_workers)
+            if (w.error) {
+                std::exception_ptr e = w.error;
+                w.error = nullptr;
+                lk.unlock();
+                std::rethrow_exception(e);
+            }
+    }
+    std::vector<worker> d_workers;
+    std::mutex d_mutex;
+    std::condition_variable d_cv, d_cv_done;
 };
 
 } // namespace gfdm

@@ -278,6 +278,27 @@ int gfdm_receiver_cancel_sc_interference(gfdm_receiver* h, gfdm_complex* out, co
     return gfdm_receiver_cancel_sc_interference_batch(h, out, td, fd, 1, GFDM_MEM_HOST);
 }
 
+/* TEST-ONLY entry (not part of include/gfdm_b200.h): the reference's legacy 2-D interface run through its OWN
+ * vector<vector<>> methods (lib/receiver_kernel_cc.cc:130-163,194-209,227-272), results serialised [k][m]:
+ *   fd = filter_superposition(in); td = demodulate_subcarrier(fd); ic = remove_sc_interference(sc_symbols = td, fd).
+ * tests/test_bindings.py compares the product's 2-D adapters (include/gfdm_b200.hpp) with these. */
+extern "C" __attribute__((visibility("default"))) int gfdm_ref_receiver_legacy_2d(gfdm_receiver* h, gfdm_complex* fd_out,
+                                                                                  gfdm_complex* td_out, gfdm_complex* ic_out,
+                                                                                  const gfdm_complex* in)
+{
+    REF_TRY
+    const int K = h->k->subcarriers(), M = h->k->timeslots();
+    std::vector<std::vector<cf>> fd(K, std::vector<cf>(M)), td(K, std::vector<cf>(M));
+    h->k->filter_superposition(fd, C(in));
+    h->k->demodulate_subcarrier(td, fd);
+    h->k->serialize_output(C(fd_out), fd);
+    h->k->serialize_output(C(td_out), td);
+    std::vector<std::vector<cf>> sym = td;
+    h->k->remove_sc_interference(sym, fd);
+    h->k->serialize_output(C(ic_out), sym);
+    REF_CATCH
+}
+
 /* ---- advanced receiver -------------------------------------------------- */
 int gfdm_advanced_receiver_create(gfdm_advanced_receiver** out, int M, int K, int L,
                                   const gfdm_complex* taps, int n_taps, const int* smap, int n_map,
