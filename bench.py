@@ -11,7 +11,8 @@ Workloads (BASELINE.json `configs`, sizes of SURVEY.md section 8; one *step* = o
       on every frame, then receiver_kernel_cc::generic_work on every modulated frame; 4096 frames per GPU.
   c1  K=16 M=5 (the reference's qa shape), same chain.
   c2  K=64 M=9 A=52 cp=16 cs=8: transmitter_kernel::generic_work (mapper + modulator + preamble + CP + window, ONE
-      kernel) -> remove_prefix -> receiver_kernel_cc::generic_work_equalize (per-frame channel).
+      kernel) -> receiver_kernel_cc::generic_work_equalize (per-frame channel) reading the block out of every frame in
+      place (remove_prefix_cc fused into the receiver's loads).
   c4  K=256 M=15 A=208: preamble_channel_estimator_cc::estimate_frame on the received preamble of every frame, then
       advanced_receiver_kernel_cc::generic_work_equalize with that estimate, 4 SIC iterations, per-frame multipath + AWGN.
   c5  K=2048 M=15: modulate -> demodulate with the two-pass kernels; --sweep runs 2^10 .. 2^20 total frames.
@@ -40,7 +41,7 @@ WORKLOADS = {
     'c1': dict(kind='modem', K=16, M=5, L=2, frames=1 << 18, alpha=0.5, seed=1001,
                desc='K=16 M=5 L=2 modulate->demodulate (BASELINE configs[0])'),
     'c2': dict(kind='txrx', K=64, M=9, L=2, A=52, cp=16, cs=8, frames=1 << 16, alpha=0.2, seed=1002,
-               desc='K=64 M=9 L=2 A=52 cp=16 cs=8 transmitter_kernel chain -> remove_prefix -> equalising receiver '
+               desc='K=64 M=9 L=2 A=52 cp=16 cs=8 transmitter_kernel chain -> equalising receiver on the framed samples '
                     '(BASELINE configs[1])'),
     'c4': dict(kind='est_sic', K=256, M=15, L=2, A=208, frames=1 << 14, alpha=0.5, seed=1004, ic_iter=4, snr_db=20.0,
                desc='K=256 M=15 L=2 A=208 QPSK preamble_channel_estimator -> advanced receiver (4 SIC iterations), '
@@ -152,11 +153,10 @@ class TxRxChain(object):
         self.n_in = A * M
         self.tx = capi.Transmitter(M, K, A, cp, cs, ramp, cfg.subcarrier_map, True, L, tx, cfg.window_taps, cfg.cyclic_shifts,
                                    cfg.full_preambles, lib=lib)
-        self.rp = capi.Remove_prefix(self.os, self.N, self.P + cp, lib=lib)
         self.rx = capi.Demodulator(M, K, L, rx, lib=lib)
-        self.handles = [self.tx, self.rp, self.rx]
-        self.stages = [('transmitter', 8 * (self.n_in + self.os)), ('remove_prefix', 8 * (self.os + self.N)),
-                       ('receiver_equalize', 24 * self.N)]
+        self.off = self.P + cp                                           # first sample of the block inside a frame
+        self.handles = [self.tx, self.rx]
+        self.stages = [('transmitter', 8 * (self.n_in + self.os)), ('receiver_equalize', 24 * self.N)]
         self.baseline_bytes = 8 * (self.n_in + self.os) + 24 * self.N   # 9,760 + 13,824 at C2
 
     def host_inputs(self, n, rank):
@@ -164,39 +164,34 @@ class TxRxChain(object):
         return {'sym': qam16(rng, (n, self.n_in)), 'eq': np.ones((n, self.N), np.complex64)}
 
     def host_buffers(self, n):
-        return {'frame': (n, self.os), 'blk': (n, self.N), 'out': (n, self.N)}
+        return {'frame': (n, self.os), 'out': (n, self.N)}
 
     def host_pass(self, p, n):
         from gfdm_b200 import capi
         self.tx.work_ptr(p['frame'], p['sym'], self.n_in, n, mem=capi.MEM_HOST)
-        self.rp.work_ptr(p['blk'], p['frame'], n, mem=capi.MEM_HOST)
-        self.rx.demodulate_ptr(p['out'], p['blk'], p['eq'], n, mem=capi.MEM_HOST)
+        self.rx.demodulate_strided_ptr(p['out'], p['frame'], p['eq'], self.os, self.off, n, mem=capi.MEM_HOST)
 
     def host_bytes(self, n):
-        return 8 * n * (self.n_in + self.os + 2 * self.N), 8 * n * (self.os + 2 * self.N)
+        return 8 * n * (self.n_in + self.os + self.N), 8 * n * (self.os + self.N)
 
-    host_path = 'gfdm_transmitter_work_batch + gfdm_remove_prefix_work_batch + gfdm_receiver_work_batch(eq), GFDM_MEM_HOST'
+    host_path = 'gfdm_transmitter_work_batch + gfdm_receiver_work_strided_batch(eq), GFDM_MEM_HOST'
 
     def device_setup(self, torch, dev, inputs, n):
         self.d_sym = torch.from_numpy(inputs['sym']).to(dev)
         self.d_eq = torch.from_numpy(inputs['eq']).to(dev)
         self.d_frame = torch.empty((n, self.os), dtype=torch.complex64, device=dev)
-        self.d_blk = torch.empty((n, self.N), dtype=torch.complex64, device=dev)
-        self.d_out = torch.empty_like(self.d_blk)
+        self.d_out = torch.empty((n, self.N), dtype=torch.complex64, device=dev)
         self.n = n
 
     def device_stage(self, i, n=None):
         n = self.n if n is None else n
         if i == 0:
             self.tx.work_ptr(self.d_frame.data_ptr(), self.d_sym.data_ptr(), self.n_in, n)
-        elif i == 1:
-            self.rp.work_ptr(self.d_blk.data_ptr(), self.d_frame.data_ptr(), n)
         else:
-            self.rx.demodulate_ptr(self.d_out.data_ptr(), self.d_blk.data_ptr(), self.d_eq.data_ptr(), n)
+            self.rx.demodulate_strided_ptr(self.d_out.data_ptr(), self.d_frame.data_ptr(), self.d_eq.data_ptr(), self.os, self.off, n)
 
     def kernel_names(self):
-        return {'transmitter': self.tx.last_kernel(), 'remove_prefix': self.rp.last_kernel(),
-                'receiver_equalize': self.rx.last_kernel()}
+        return {'transmitter': self.tx.last_kernel(), 'receiver_equalize': self.rx.last_kernel()}
 
     def check(self):
         assert np.isfinite(self.d_out[:2].cpu().numpy()).all(), 'non-finite receiver output'

@@ -2025,6 +2025,39 @@ int gfdm_resource_mapper_demap_chunks_batch(gfdm_resource_mapper* h, unsigned ch
     API_CATCH
 }
 
+/* ---- receiver reading frames in place (remove_prefix_cc fused into its loads) ---- */
+int gfdm_receiver_work_strided_batch(gfdm_receiver* h, gfdm_complex* out, const gfdm_complex* in, const gfdm_complex* eq,
+                                     size_t in_stride, size_t in_offset, int n, int mem)
+{
+    API_TRY
+    h->use();
+    if (n < 0) throw std::invalid_argument("n_frames MUST NOT be negative");
+    const size_t N = h->N;
+    if (in_stride < in_offset + N) throw std::invalid_argument("in_stride MUST hold in_offset + block_size samples");
+    Staging st(h, mem, true);
+    auto run = [&](cpx* dout, const cpx* d0, const cpx* d1, size_t, size_t nf) {
+        if (!nf) return;
+        const cpx* first = d0 + in_offset;
+        // cp.async.bulk needs 16-byte aligned frame starts: an even stride behind an aligned first frame
+        if (h->fused.available() && h->fused.supports_stride() && (!d1 || h->fused.supports_eq()) && in_stride % 2 == 0 &&
+            aligned16(first) && aligned16(dout) && aligned16(d1)) {
+            h->launches += h->fused.demodulate(dout, nullptr, first, d1, nf, h->stream, in_stride == N ? 0 : in_stride);
+            h->last_kernel = h->fused.rx_name();
+            return;
+        }
+        h->work_fmt.ensure(nf * N * sizeof(cpx));
+        launch_remove_cp(h->work_fmt.as<cpx>(), d0, (int)N, (int)in_offset, (int)(in_stride - N - in_offset), nf, h->stream);
+        h->launches += 1;
+        receiver_run(h, dout, h->work_fmt.as<cpx>(), d1, nf);
+    };
+    if (mem == GFDM_MEM_DEVICE)
+        run(reinterpret_cast<cpx*>(out), reinterpret_cast<const cpx*>(in), reinterpret_cast<const cpx*>(eq), 0, (size_t)n);
+    else
+        host_pipeline(h, (size_t)n, pipe_chunk(sizeof(cpx) * (in_stride + (eq ? 2 : 1) * N), (size_t)n), in, in_stride, eq, N, out, N, false,
+                      st.async, run);
+    API_CATCH
+}
+
 /* ---- short_burst_shaper: lib/short_burst_shaper_impl.cc:57-84, 161-182 ------ */
 struct gfdm_burst_shaper : HandleBase {
     ShaperArgs a;

@@ -83,7 +83,9 @@ public:
     const char* txc_name() const;
     const char* rxd_name() const;
     // out_td (soft symbols) and/or out_fd (fft_filter_downsample result) may be null; eq may be null
-    int demodulate(cpx* out_td, cpx* out_fd, const cpx* in, const cpx* eq, size_t frames, cudaStream_t s);
+    // in_stride != 0: frame f is read from in + f*in_stride (single-pass shapes; even strides and 16-byte aligned starts)
+    bool supports_stride() const;
+    int demodulate(cpx* out_td, cpx* out_fd, const cpx* in, const cpx* eq, size_t frames, cudaStream_t s, size_t in_stride = 0);
     // advanced receiver: successive interference cancellation resident in the receiver kernel.
     // Call after init_rx; returns false when the shape / constellation has no fused path.
     bool init_sic(const std::vector<std::complex<float>>& ic_taps, const std::vector<std::complex<float>>& points,

@@ -172,6 +172,7 @@ class Library(object):
         'gfdm_transmitter_work_chunks_batch': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int]),
         'gfdm_receiver_work_decide_batch': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int]),
         'gfdm_resource_mapper_demap_chunks_batch': (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int]),
+        'gfdm_receiver_work_strided_batch': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, c_int, c_int]),
         'gfdm_burst_shaper_create': (c_int, [POINTER(c_void_p), c_int, c_int, c_float, c_float]),
         'gfdm_burst_shaper_destroy': (None, [c_void_p]),
         'gfdm_burst_shaper_pre_padding': (c_int, [c_void_p]),
@@ -511,6 +512,24 @@ class Demodulator(_Handle):
         self._ck(self._dll.gfdm_receiver_work_batch(self._h, c_void_p(out_ptr), c_void_p(in_ptr),
                                                     c_void_p(eq_ptr) if eq_ptr else None,
                                                     n_frames, mem))
+
+    def demodulate_strided_batch(self, frames, offset, eq_arr=None):
+        """frames[n, stride] still carrying prefix / suffix: demodulates frames[:, offset:offset + block_size] in place."""
+        a = _c64(frames)
+        if a.ndim != 2 or a.shape[1] < offset + self.block_size():
+            raise RuntimeError('frames MUST have shape [n_frames, >= offset + block_size]')
+        eq = None
+        if eq_arr is not None:
+            eq = _c64(eq_arr)
+            self._two_dim(eq, self.block_size())
+        out = np.empty((a.shape[0], self.block_size()), np.complex64)
+        self._ck(self._dll.gfdm_receiver_work_strided_batch(self._h, _ptr(out), _ptr(a), _ptr(eq) if eq is not None else None,
+                                                            a.shape[1], offset, a.shape[0], MEM_HOST))
+        return out
+
+    def demodulate_strided_ptr(self, out_ptr, in_ptr, eq_ptr, stride, offset, n_frames, mem=MEM_DEVICE):
+        self._ck(self._dll.gfdm_receiver_work_strided_batch(self._h, c_void_p(out_ptr), c_void_p(in_ptr),
+                                                            c_void_p(eq_ptr) if eq_ptr else None, stride, offset, n_frames, mem))
 
     @staticmethod
     def _iq(array, size):

@@ -402,6 +402,14 @@ GFDM_B200_API int gfdm_resource_mapper_demap_chunks_batch(gfdm_resource_mapper* 
                                                           const unsigned char* in, size_t size_per_frame,
                                                           int n_frames, int mem);
 
+/* remove_prefix_cc (lib/remove_prefix_cc_impl.cc:84-115) fused into the receiver's loads: frame f of the batch is the
+ * block_size samples at in + f*in_stride + in_offset (in_stride >= in_offset + block_size), i.e. the frames still carry
+ * preamble / cyclic prefix / suffix and are never copied to a packed array (single-pass shapes read them in place;
+ * elsewhere the gather kernel runs first).  f_eq_in (may be NULL) and out are packed [n_frames][block_size]. */
+GFDM_B200_API int gfdm_receiver_work_strided_batch(gfdm_receiver* h, gfdm_complex* out, const gfdm_complex* in,
+                                                   const gfdm_complex* f_eq_in, size_t in_stride, size_t in_offset,
+                                                   int n_frames, int mem);
+
 /* ---- short_burst_shaper: lib/short_burst_shaper_impl.cc:57-84 (ctor checks), :161-182 (work) ---------------------
  * The sample path of the block that follows the transmitter in the reference's flowgraphs: every burst becomes
  *   [pre_padding zeros | in * scale | post_padding zeros]      (volk_32fc_s32fc_multiply_32fc: plain complex product).

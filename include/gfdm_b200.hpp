@@ -175,6 +175,13 @@ public:
         detail::check(
             gfdm_receiver_work_batch(d_h.get(), detail::c(out), detail::c(in), detail::c(f_eq_in), n_frames, mem));
     }
+    // frames read in place: frame f = block_size() samples at in + f*in_stride + in_offset (remove_prefix_cc fused in)
+    void generic_work_strided_batch(gfdm_complex* out, const gfdm_complex* in, const gfdm_complex* f_eq_in, size_t in_stride,
+                                    size_t in_offset, int n_frames, int mem = GFDM_MEM_HOST)
+    {
+        detail::check(gfdm_receiver_work_strided_batch(d_h.get(), detail::c(out), detail::c(in), detail::c(f_eq_in), in_stride,
+                                                       in_offset, n_frames, mem));
+    }
     void fft_filter_downsample(gfdm_complex* p_out, const gfdm_complex* p_in)
     {
         detail::check(gfdm_receiver_fft_filter_downsample(d_h.get(), detail::c(p_out), detail::c(p_in)));
@@ -753,18 +760,17 @@ public:
                 w.kernel.reset(); // handles are destroyed on the thread that owns their device selection
             });
         }
-        wait_all(); // construction errors (no such device, invalid kernel parameters) surface here
-    }
-    ~multi_gpu()
-    {
-        {
-            std::lock_guard<std::mutex> lk(d_mutex);
-            for (worker& w : d_workers) w.stop = true;
+        // construction errors (no such device, invalid kernel parameters) surface here; the workers are stopped and joined
+        // first -- a constructor that throws does not run the destructor, and the condition variables must not be
+        // destroyed while a worker still waits on them
+        try {
+            wait_all();
+        } catch (...) {
+            shutdown();
+            throw;
         }
-        d_cv.notify_all();
-        for (worker& w : d_workers)
-            if (w.thread.joinable()) w.thread.join();
     }
+    ~multi_gpu() { shutdown(); }
     multi_gpu(const multi_gpu&) = delete;
     multi_gpu& operator=(const multi_gpu&) = delete;
     size_t n_devices() const { return d_workers.size(); }
@@ -800,6 +806,16 @@ private:
         bool has_job = false, stop = false, done = false;
         std::exception_ptr error;
     };
+    void shutdown()
+    {
+        {
+            std::lock_guard<std::mutex> lk(d_mutex);
+            for (worker& w : d_workers) w.stop = true;
+        }
+        d_cv.notify_all();
+        for (worker& w : d_workers)
+            if (w.thread.joinable()) w.thread.join();
+    }
     void signal_done(worker& w)
     {
         {
@@ -817,13 +833,15 @@ private:
                 if (!w.done) return false;
             return true;
         });
-        for (worker& w : d_workers)
-            if (w.error) {
-                std::exception_ptr e = w.error;
-                w.error = nullptr;
-                lk.unlock();
-                std::rethrow_exception(e);
-            }
+        std::exception_ptr first;
+        for (worker& w : d_workers) {
+            if (w.error && !first) first = w.error;
+            w.error = nullptr; // the first error is reported, none is left behind for a later call
+        }
+        if (first) {
+            lk.unlock();
+            std::rethrow_exception(first);
+        }
     }
     std::vector<worker> d_workers;
     std::mutex d_mutex;

@@ -92,3 +92,14 @@ def assert_complex_close(res, ref, rel=1e-5, mx=1e-4, what=''):
     """north_star tolerance: rel-L2 <= 1e-5 and max-abs <= 1e-4 of signal RMS."""
     r, m = rel_l2(res, ref), max_abs_over_rms(res, ref)
     assert r <= rel and m <= mx, '%s rel-l2 %.3e (<= %.1e), max-abs/rms %.3e (<= %.1e)' % (what, r, rel, m, mx)
+
+
+# (M, K) with a single-kernel (shared-memory resident) modulator / receiver: csrc/fused_shapes_*.cu, parameters chosen by
+# tools/shape_chooser.py -- every power-of-two K in 16..1024 for M in {3, 5, 7, 9, 15, 21} (M = 21 does not fit at K = 1024)
+# plus the reference's other test shapes; K = 2048 / M = 15 runs the two-pass kernels.
+FUSED_TABLE = set((M, K) for K in (16, 32, 64, 128, 256, 512, 1024) for M in (3, 5, 7, 9, 15, 21)) - {(21, 1024)} | \
+    {(8, 16), (16, 4), (7, 8), (19, 32), (16, 64)}
+
+
+def fused_expected(M, K):
+    return (M, K) in FUSED_TABLE or (M, K) == (15, 2048)

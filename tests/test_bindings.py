@@ -162,7 +162,7 @@ def cpp_probe(tmp_path_factory):
 
 def test_cpp_layer_compiles_with_reference_include_names(cpp_probe):
     exe, _ = cpp_probe
-    out = subprocess.run([exe], capture_output=True, text=True)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0 and 'OK exceptions' in out.stdout, out.stdout + out.stderr
 
 
@@ -175,7 +175,7 @@ def test_cpp_layer_round_trip(cpp_probe, port):
     sym = design.get_random_qpsk(M * K, rng=np.random.RandomState(5)).astype(np.complex64)
     taps.tofile(d / 'taps.bin')
     sym.tofile(d / 'sym.bin')
-    out = subprocess.run([exe, str(d / 'taps.bin'), str(d / 'sym.bin'), str(d / 'y.bin')], capture_output=True, text=True)
+    out = subprocess.run([exe, str(d / 'taps.bin'), str(d / 'sym.bin'), str(d / 'y.bin')], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and out.stdout.startswith('OK'), out.stdout + out.stderr
     y = np.fromfile(d / 'y.bin', np.complex64)
     ref = capi.Demodulator(M, K, L, np.conj(taps), lib=port).demodulate(capi.Modulator(M, K, L, taps, lib=port).modulate(sym))

@@ -36,13 +36,13 @@ def blocks_probe(tmp_path_factory):
 
 
 def test_block_shims_compile_and_validate_without_a_device(blocks_probe):
-    out = subprocess.run([blocks_probe, '--dry'], capture_output=True, text=True)
+    out = subprocess.run([blocks_probe, '--dry'], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0 and 'OK dry' in out.stdout, out.stdout + out.stderr
 
 
 @pytest.mark.gpu
 def test_block_shims_work_equals_per_frame_kernel_calls(blocks_probe):
-    out = subprocess.run([blocks_probe], capture_output=True, text=True)
+    out = subprocess.run([blocks_probe], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and 'OK blocks' in out.stdout, out.stdout + out.stderr
 
 
@@ -68,7 +68,7 @@ def _reference_2d(ref, M, K, L, taps, x):
 
 def _probe_2d(exe, tmp, M, K, L):
     out = subprocess.run([exe, str(M), str(K), str(L), str(tmp / 'taps.bin'), str(tmp / 'x.bin'), str(tmp / 'out.bin')],
-                         capture_output=True, text=True)
+                         capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and 'OK' in out.stdout, out.stdout + out.stderr
     return np.fromfile(str(tmp / 'out.bin'), np.complex64).reshape(3, M * K)
 
@@ -100,5 +100,44 @@ def test_single_process_multi_gpu_driver_is_bit_identical(tmp_path):
     streams and threads); `gpurun --gpus N` exercises N devices with the same binary."""
     exe = _compile(tmp_path, 'multi_gpu_probe.cc', 'multi_gpu')
     for workers, frames in ((2, 257), (3, 40), (8, 1000)):
-        out = subprocess.run([exe, str(workers), str(frames)], capture_output=True, text=True)
+        out = subprocess.run([exe, str(workers), str(frames)], capture_output=True, text=True, timeout=300)
         assert out.returncode == 0 and out.stdout.startswith('OK'), out.stdout + out.stderr
+
+
+def test_multi_gpu_driver_host_logic_without_a_device(tmp_path):
+    """The worker-pool logic of gr::gfdm::multi_gpu with a stand-in kernel type: a factory that throws fails the constructor
+    (workers joined, nothing left waiting -- a hang here cost a GPU session), job exceptions reach the caller once, shards
+    partition the batch."""
+    src = tmp_path / 'mg_logic.cc'
+    src.write_text(r'''
+#include <gfdm_b200.hpp>
+#include <atomic>
+#include <cstdio>
+using namespace gr::gfdm;
+struct fake { int id; };
+int main()
+{
+    bool threw = false;
+    try {
+        multi_gpu<fake> bad({ 0, 1 }, [&]() -> std::unique_ptr<fake> { throw std::runtime_error("no device"); });
+    } catch (const std::exception&) { threw = true; }
+    if (!threw) { printf("FAIL ctor\n"); return 1; }
+    for (size_t n : { (size_t)0, (size_t)1, (size_t)7, (size_t)4096 })
+        for (size_t w : { (size_t)1, (size_t)3, (size_t)8 }) {
+            size_t next = 0;
+            for (size_t r = 0; r < w; ++r) {
+                const auto b = multi_gpu<fake>::shard_bounds(n, w, r);
+                if (b.first != next || b.second < b.first) { printf("FAIL bounds\n"); return 1; }
+                next = b.second;
+            }
+            if (next != n) { printf("FAIL bounds cover\n"); return 1; }
+        }
+    printf("OK\n");
+    return 0;
+}
+''')
+    exe = tmp_path / 'mg_logic'
+    subprocess.run(['g++', '-std=c++17', '-I' + os.path.join(ROOT, 'include'), str(src), '-o', str(exe), '-L' + LIBDIR, '-lgfdm_b200',
+                    '-Wl,-rpath,' + LIBDIR, '-lpthread'], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0 and 'OK' in out.stdout, out.stdout + out.stderr

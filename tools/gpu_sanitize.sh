@@ -4,10 +4,12 @@ TAG=${1:-r02}
 OUT=gpurun_out
 mkdir -p $OUT
 for tool in memcheck racecheck synccheck; do
-  echo "== compute-sanitizer --tool $tool"
-  timeout 1200 compute-sanitizer --tool $tool --print-limit 20 --log-file $OUT/${TAG}_sanitizer_$tool.log \
-      python tools/sanitize_target.py > $OUT/${TAG}_sanitizer_${tool}_stdout.txt 2>&1
-  echo "rc=$?" >> $OUT/${TAG}_sanitizer_${tool}_stdout.txt
-  tail -5 $OUT/${TAG}_sanitizer_$tool.log
-  tail -3 $OUT/${TAG}_sanitizer_${tool}_stdout.txt
+  for k in 16 64 256 1024 2048 128; do
+    echo "== compute-sanitizer --tool $tool, K=$k"
+    timeout 300 compute-sanitizer --tool $tool --print-limit 10 --log-file $OUT/${TAG}_sanitizer_${tool}_k$k.log \
+        python tools/sanitize_target.py $k > $OUT/${TAG}_sanitizer_${tool}_k${k}_stdout.txt 2>&1
+    echo "rc=$?" >> $OUT/${TAG}_sanitizer_${tool}_k${k}_stdout.txt
+    tail -2 $OUT/${TAG}_sanitizer_${tool}_k$k.log
+    tail -2 $OUT/${TAG}_sanitizer_${tool}_k${k}_stdout.txt
+  done
 done

@@ -44,14 +44,14 @@ for M, K, frames in ((5, 16, 300), (9, 64, 70), (15, 256, 9), (15, 1024, 3), (15
         adv = capi.Advanced_receiver(M, K, L, np.conj(taps), smap, 2, (pts, rule), 1, lib=lib)
         adv.demodulate_batch(x, eq); seen.append(adv.last_kernel())
     cp, cs = K // 4, K // 8
-    cfg = design.get_gfdm_configuration(M, K, A, L, cp, cs, 'rrc', .5, cyclic_shifts=(0, 2))
-    tx = capi.Transmitter(M, K, A, cp, cs, cs, cfg.subcarrier_map, True, L, cfg.tx_filter_taps, cfg.window_taps, [0, 2],
-                          cfg.full_preambles, lib=lib)
+    window = design.get_raised_cosine_ramp(cs, design.get_window_len(cp, M, K, cs))
+    pre = [crand(2 * K + cp + cs) for _ in range(2)]
+    tx = capi.Transmitter(M, K, A, cp, cs, cs, smap, True, L, taps, window, [0, 2], pre, lib=lib)
     s = crand(frames, tx.input_vector_size())
     tx.work_all_batch(s); seen.append(tx.last_kernel())
     sh = capi.Burst_shaper(3, 5, 0.5 + 0.1j, lib=lib)
     tx.work_shaped_batch(sh, s); seen.append(tx.last_kernel() + '+shaper')
-    est = capi.Preamble_channel_estimator(M, K, A, True, 1, cfg.core_preamble, lib=lib)
+    est = capi.Preamble_channel_estimator(M, K, A, True, 1, crand(2 * K), lib=lib)
     est.estimate_frame_batch(crand(frames, 2 * K)); seen.append(est.last_kernel())
 print('kernels exercised:')
 for k in sorted(set(seen)):
