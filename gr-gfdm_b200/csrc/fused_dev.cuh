@@ -200,7 +200,10 @@ static __device__ unsigned long long g_stage_cycles[32];
 
 // ----------------------------------------------------------------------------------------
 // compile-time shape of one fused kernel
-template <int M_, int R1_, int R2_, int T_, int IPT_, int MINB_, bool TMEM_ = true>
+// TW_TMEM_ = false keeps the pass-1 row-FFT twiddles in shared memory even when the table lives in tensor memory, and
+// KEEP_COLS_ reserves that many extra tensor-memory columns per thread: the interference-cancelling receiver of the
+// shapes with two subcarriers per thread parks its kept frequency blocks there (fused_kernels.cuh).
+template <int M_, int R1_, int R2_, int T_, int IPT_, int MINB_, bool TMEM_ = true, bool TW_TMEM_ = true, int KEEP_COLS_ = 0>
 struct Shape {
     static constexpr int M = M_, R1 = R1_, R2 = R2_, T = T_, IPT = IPT_, MINB = MINB_;
     static constexpr int K = R1 * R2;
@@ -233,7 +236,7 @@ struct Shape {
     // (2M 32-bit columns each) and, for two-pass rows, its R1 pass-1 twiddles W_K^{n0*k1}, n0 = tid % R2.
     // Warp w owns lanes 32*(w%4).., the warps sharing a lane quarter take consecutive column blocks.
     static constexpr bool TBL_TMEM = !TBL_SMEM && TMEM_; // the two-pass kernels (fused_twopass.cu) opt out
-    static constexpr bool TW_TMEM = TBL_TMEM && TWO_PASS && T % R2 == 0;
+    static constexpr bool TW_TMEM = TBL_TMEM && TWO_PASS && T % R2 == 0 && TW_TMEM_;
     static constexpr int TW_ELEMS = (TWO_PASS && !TW_TMEM) ? K : 0;
     static constexpr int P_MAX = BUDGET_ELEMS - BUF_ELEMS - TW_ELEMS;
     static_assert(P_MAX >= 0, "frame group does not fit in shared memory");
@@ -246,7 +249,8 @@ struct Shape {
     static constexpr int P_ELEMS = PF > F * PR * K ? PF : F * PR * K;
     static constexpr int TMEM_TBL_COLS = IPT * 2 * M;             // per thread
     static constexpr int TMEM_TW_COLS = TW_TMEM ? 2 * R1 : 0;     // per thread
-    static constexpr int TMEM_PER_THREAD = TMEM_TBL_COLS + TMEM_TW_COLS;
+    static constexpr int TMEM_KEEP_COLS = KEEP_COLS_;             // per thread
+    static constexpr int TMEM_PER_THREAD = TMEM_TBL_COLS + TMEM_TW_COLS + TMEM_KEEP_COLS;
     static constexpr int TMEM_USED = ((T / 32 + 3) / 4) * TMEM_PER_THREAD;
     static constexpr int TMEM_COLS = TMEM_USED <= 32 ? 32 : TMEM_USED <= 64 ? 64 : TMEM_USED <= 128 ? 128 : TMEM_USED <= 256 ? 256 : 512;
     static_assert(!TBL_TMEM || (TMEM_USED <= 512 && TMEM_COLS * MINB <= 512), "constants do not fit in tensor memory");
@@ -312,7 +316,22 @@ __device__ __forceinline__ void row_fft(cpx* __restrict__ buf, const cpx* __rest
     } else {
         // pass 1: item (row, n0): radix-R1 over x[R2*n1 + n0], then W_K^{n0*k1}; in place
         constexpr int ITEMS1 = S::ROWS * R2;
-        for (int it = tid; it < ITEMS1; it += T) {
+        // Twiddles in tensor memory: tcgen05.ld is a warp-wide (.sync.aligned) instruction, so a warp whose last round is
+        // only partly populated (ITEMS1 not a multiple of 32) must still execute it with every lane -- the surplus lanes
+        // run the round on the last item's addresses for the loads and skip the stores.  Whole warps still drop out.
+        constexpr bool PARTIAL_WARP = S::TW_TMEM && ITEMS1 % 32 != 0;
+        constexpr int ROUNDS1 = (ITEMS1 + T - 1) / T;
+#pragma unroll 1
+        for (int rd = 0; rd < ROUNDS1; ++rd) {
+            int it = tid + rd * T;
+            bool live = true;
+            if constexpr (PARTIAL_WARP) {
+                if ((it & ~31) >= ITEMS1) break; // no lane of this warp has an item
+                live = it < ITEMS1;
+                it = live ? it : ITEMS1 - 1;
+            } else {
+                if (it >= ITEMS1) break;
+            }
             const int row = it / R2, n0 = it - row * R2;
             cpx* p = buf + row * RS + n0;
             cpx a[R1];
@@ -321,7 +340,7 @@ __device__ __forceinline__ void row_fft(cpx* __restrict__ buf, const cpx* __rest
             rf::FFTN<R1, DIR>::run(a);
             // twiddle + store in chunks of 8; the empty asm keeps the chunks in program order so that
             // at most 8 twiddles are live next to the 2*R1 data registers (no spills in this hot loop)
-            p[0] = a[0];
+            if (live) p[0] = a[0];
 #pragma unroll
             for (int c = 0; c < R1; c += 8) {
                 cpx w[8];
@@ -340,7 +359,7 @@ __device__ __forceinline__ void row_fft(cpx* __restrict__ buf, const cpx* __rest
                 for (int i = 0; i < 8; ++i)
                     if (c + i > 0 && c + i < R1) {
                         if (DIR > 0) w[i].y = -w[i].y;
-                        p[(R2 + 1) * (c + i)] = cmul(a[c + i], w[i]);
+                        if (live) p[(R2 + 1) * (c + i)] = cmul(a[c + i], w[i]);
                     }
                 asm volatile("" ::: "memory");
             }

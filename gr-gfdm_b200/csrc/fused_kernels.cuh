@@ -366,7 +366,8 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_rx_kernel(cpx* __restrict
     for (int i = tid; i < S::TBL_ELEMS; i += T) tbl_s[i] = table[i];
     for (int i = tid; i < L * M && i < S::IC_OFF; i += T) taps_s[i] = taps[i];
     if constexpr (SIC) {
-        static_assert(IPT == 1, "the cancellation loop keeps one subcarrier per thread in registers");
+        static_assert(IPT == 1 || (S::TBL_TMEM && S::TMEM_KEEP_COLS >= IPT * 2 * M),
+                      "the cancellation loop keeps one subcarrier per thread in registers, or the kept blocks in tensor memory");
         for (int i = tid; i < M && i < 32; i += T) taps_s[S::IC_OFF + i] = cscale(sic.ic_taps[i], inv_m); // 1/M of the IFFT folded in
     }
     // constellation: interference cancellation and the hard-decision output (mode 2)
@@ -499,8 +500,80 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_rx_kernel(cpx* __restrict
         }
         __syncthreads();
         STAGE_MARK(22) // stage C' reads
-        if (eq != nullptr) {
-            // Y[b*M+m] back to the linear [b][m] order, divide by the channel, combine the L parts
+        // Equalisation with overlap 2 (every reference configuration): the division and the tap combine stay in registers.
+        // The channel of the group is read coalesced (consecutive lanes on consecutive bins), inverted once and handed to
+        // the owning threads through shared memory; the only neighbour a subcarrier needs is k-1, i.e. the previous lane
+        // (a shuffle) -- lane 0 takes it from a small per-warp hand-over array in the unused tail of the row buffer.
+        // Shared-memory traffic: 2*IPT*M accesses per thread (+ broadcast tap reads) instead of 7*IPT*M.
+        constexpr bool EQ_FAST_OK = !S::TWO_PASS || S::BUF_ELEMS - F * N >= F * N / 32;
+        if (eq != nullptr && L == 2 && EQ_FAST_OK) {
+            const cpx* eqg = eq + (size_t)g * F * N;
+            {
+                // IPT*M bins per thread in chunks of CH: loads of a chunk in flight together, few live registers
+                constexpr int PER = IPT * M, CH = 5;
+#pragma unroll
+                for (int q0 = 0; q0 < PER; q0 += CH) {
+                    cpx hq[CH];
+#pragma unroll
+                    for (int c = 0; c < CH; ++c) {
+                        const int i = tid + (q0 + c) * T;
+                        hq[c] = (q0 + c < PER && i < fh * N) ? ldg_stream(eqg + i) : cmake(1.f, 0.f);
+                    }
+#pragma unroll
+                    for (int c = 0; c < CH; ++c) {
+                        if (q0 + c < PER) {
+                            const float rden = __fdividef(1.0f, hq[c].x * hq[c].x + hq[c].y * hq[c].y);
+                            // 1/h = conj(h) / |h|^2 (volk_32fc_x2_divide_32fc)
+                            buf[tid + (q0 + c) * T] = cmake(hq[c].x * rden, -hq[c].y * rden);
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            cpx* bnd = buf + F * N; // [item warp][M]: the equalised bins of every warp's last lane
+#pragma unroll
+            for (int j = 0; j < IPT; ++j) {
+                const int it = tid + j * T;
+                const cpx* rr = buf + (size_t)it * M;
+#pragma unroll
+                for (int m = 0; m < M; ++m) v[j][m] = cmul(v[j][m], rr[m]);
+                if constexpr (K >= 32) {
+                    if ((tid & 31) == 31) {
+                        cpx* b = bnd + (size_t)(it >> 5) * M;
+#pragma unroll
+                        for (int m = 0; m < M; ++m) b[m] = v[j][m];
+                    }
+                }
+            }
+            if constexpr (K >= 32) __syncthreads();
+#pragma unroll
+            for (int j = 0; j < IPT; ++j) {
+                const int it = tid + j * T;
+                const int f = it / K, k = it - f * K;
+                const int lane = tid & 31;
+                // R_k[m] = taps[M+m] * Yeq[(k-1) M + m] + taps[m] * Yeq[k M + m]   (receiver_kernel_cc.cc:165-192, L = 2)
+                if constexpr (K >= 32) {
+                    // subcarrier k-1 is the previous lane; for lane 0 the last lane of another warp (k = 0: K-1 of the same frame)
+                    const int src = k == 0 ? it + K - 1 : it - 1;
+                    const cpx* b = bnd + (size_t)(src >> 5) * M;
+#pragma unroll
+                    for (int m = 0; m < M; ++m) {
+                        cpx pv = cmake(__shfl_up_sync(0xffffffffu, v[j][m].x, 1), __shfl_up_sync(0xffffffffu, v[j][m].y, 1));
+                        if (lane == 0) pv = b[m];
+                        v[j][m] = cadd(cmul(taps_s[M + m], pv), cmul(taps_s[m], v[j][m]));
+                    }
+                } else { // whole frames inside a warp: k-1 (wrapping inside the frame) is another lane
+                    const int src = k == 0 ? lane + K - 1 : lane - 1;
+#pragma unroll
+                    for (int m = 0; m < M; ++m) {
+                        const cpx pv = cmake(__shfl_sync(0xffffffffu, v[j][m].x, src), __shfl_sync(0xffffffffu, v[j][m].y, src));
+                        v[j][m] = cadd(cmul(taps_s[M + m], pv), cmul(taps_s[m], v[j][m]));
+                    }
+                }
+            }
+            __syncthreads(); // the inverted channel and the hand-over array are dead: the row buffer may be reused
+        } else if (eq != nullptr) {
+            // any other overlap: Y[b*M+m] back to the linear [b][m] order, divide by the channel, combine the L parts
 #pragma unroll
             for (int j = 0; j < IPT; ++j) {
                 cpx* dst = buf + (size_t)(tid + j * T) * M;
@@ -547,7 +620,7 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_rx_kernel(cpx* __restrict
             }
             __syncthreads();
         }
-        if constexpr (SIC) {
+        if constexpr (SIC && IPT == 1) {
             // v[0] = R_k (kept frequency block of this thread's subcarrier); iterate decide -> re-modulate the
             // neighbours -> subtract -> back to time domain without leaving the SM
             const int f = tid / K, k = tid - f * K;
@@ -574,7 +647,9 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_rx_kernel(cpx* __restrict
                 } else {
 #pragma unroll
                     for (int m = 0; m < M; ++m)
-                        d[m] = cnt ? pts_s[decide_symbol_grid(y[m], pts_s, sic.n_points, sic.rule, sic.grid, lut_s)]
+                        d[m] = cnt ? pts_s[(sic.rule != 1 && sic.grid.n_re > 0)
+                                               ? decide_symbol_grid_fast(y[m], sic.grid, lut_s)
+                                               : decide_symbol_grid(y[m], pts_s, sic.n_points, sic.rule, sic.grid, lut_s)]
                                    : cmake(0.f, 0.f);
                 }
                 if (sic.phase_comp > 0 && it == 0) {
@@ -618,6 +693,129 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_rx_kernel(cpx* __restrict
             }
 #pragma unroll
             for (int m = 0; m < M; ++m) v[0][m] = y[m];
+        
+        }
+        if constexpr (SIC && IPT > 1) {
+            // Two (or more) subcarriers per thread: the kept frequency blocks R_k / M wait in tensor memory, the soft symbols
+            // never stay in registers across an iteration -- every new y is decided at once and only the DECISIONS (one byte
+            // per symbol: constellation index, 255 = inactive subcarrier) are exchanged through shared memory, double
+            // buffered in the tail of the row buffer.  lib/advanced_receiver_kernel_cc.cc:56-76, receiver_kernel_cc.cc:274-299.
+            constexpr int EXB = F * N;                                  // bytes of one decision buffer
+            constexpr int EX_OFF = S::BUF_ELEMS - (2 * EXB + 7) / 8;    // both buffers at the end of the row buffer
+            static_assert(EX_OFF >= T * M, "decision buffers must not overlap the output staging of item 0");
+            unsigned char* ex0 = reinterpret_cast<unsigned char*>(buf + EX_OFF);
+            const cpx* ic_s = taps_s + S::IC_OFF;
+            const cpx* pts_s = taps_s + S::PTS_OFF;
+            float* red_s = reinterpret_cast<float*>(taps_s + S::RED_OFF);
+            const uint32_t keep = tmem_mine + S::TMEM_TBL_COLS + S::TMEM_TW_COLS;
+            const float qa = sic.qpsk_a;
+            const int n_pts = sic.n_points;
+            auto point = [&](unsigned char b) -> cpx {
+                if (qa > 0.f) return b < 4 ? cmake((b & 1) ? qa : -qa, (b & 2) ? qa : -qa) : cmake(0.f, 0.f);
+                return (int)b < n_pts ? pts_s[b] : cmake(0.f, 0.f);
+            };
+            auto decide = [&](cpx y) -> unsigned char {
+                if (qa > 0.f) return (unsigned char)(2 * (y.y > 0.f) + (y.x > 0.f));
+                if (sic.rule != 1 && sic.grid.n_re > 0) return (unsigned char)decide_symbol_grid_fast(y, sic.grid, lut_s);
+                return (unsigned char)decide_symbol_grid(y, pts_s, n_pts, sic.rule, sic.grid, lut_s);
+            };
+            // prologue: park R_k / M, first soft symbols, first decisions (+ the phase estimate's partial sums)
+            float part = 0.f;
+#pragma unroll
+            for (int j = 0; j < IPT; ++j) {
+                const int it = tid + j * T, k = it % K;
+                const int cnt = sic.count[k];
+                float kf[2 * M];
+#pragma unroll
+                for (int m = 0; m < M; ++m) {
+                    v[j][m] = cscale(v[j][m], inv_m);
+                    kf[2 * m] = v[j][m].x;
+                    kf[2 * m + 1] = v[j][m].y;
+                }
+                tmem_st<2 * M>(keep + j * 2 * M, kf);
+                rf::FFTN<M, +1>::run(v[j]); // y = IFFT_M(R_k) / M
+                {   // (ic_iter >= 1: without iterations the host runs the plain receiver)
+                    unsigned char* mine = ex0 + (size_t)it * M;
+#pragma unroll
+                    for (int m = 0; m < M; ++m) {
+                        const unsigned char b = cnt ? decide(v[j][m]) : (unsigned char)255;
+                        mine[m] = b;
+                        if (sic.phase_comp > 0 && cnt) {
+                            const cpx dd = point(b);
+                            part += (float)cnt * (atan2f(dd.y, dd.x) - atan2f(v[j][m].y, v[j][m].x));
+                        }
+                    }
+                }
+            }
+            tmem_wait_st();
+            {
+                if (sic.phase_comp > 0) {
+                    // calculate_phase_offset (:78-91): mean over the map of arg(decided) - arg(soft); fixed-order tree.
+                    // One frame per CTA pass here (F == 1): warp partials, then one sum
+                    static_assert(F == 1, "phase compensation of the tensor-memory variant assumes one frame per CTA pass");
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+                    if ((tid & 31) == 0) red_s[tid >> 5] = part;
+                    __syncthreads();
+                    float phi = 0.f;
+                    for (int q = 0; q < T / 32; ++q) phi += red_s[q];
+                    phi *= sic.inv_map_total;
+                    float sn, cs;
+                    sincosf(phi, &sn, &cs);
+                    const cpx rot = cmake(cs, sn);
+#pragma unroll
+                    for (int j = 0; j < IPT; ++j) { // the kept blocks stay rotated (:61-71)
+                        float kf[2 * M];
+                        tmem_ld<2 * M>(kf, keep + j * 2 * M);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int m = 0; m < M; ++m) {
+                            const cpx r = cmul(cmake(kf[2 * m], kf[2 * m + 1]), rot);
+                            kf[2 * m] = r.x;
+                            kf[2 * m + 1] = r.y;
+                        }
+                        tmem_st<2 * M>(keep + j * 2 * M, kf);
+                    }
+                    tmem_wait_st();
+                }
+                __syncthreads();
+                for (int iter = 0; iter < sic.ic_iter; ++iter) {
+                    const bool last = iter == sic.ic_iter - 1;
+                    const unsigned char* cur = ex0 + (size_t)(iter & 1) * EXB;
+                    unsigned char* nxt = ex0 + (size_t)((iter + 1) & 1) * EXB;
+#pragma unroll
+                    for (int j = 0; j < IPT; ++j) {
+                        const int it = tid + j * T, f = it / K, k = it - f * K;
+                        const int kp = k == 0 ? K - 1 : k - 1, kn = k == K - 1 ? 0 : k + 1;
+                        const unsigned char* prev = cur + ((size_t)f * K + kp) * M;
+                        const unsigned char* next = cur + ((size_t)f * K + kn) * M;
+                        cpx d[M];
+#pragma unroll
+                        for (int m = 0; m < M; ++m) d[m] = cadd(point(prev[m]), point(next[m]));
+                        // the last iteration stages its results where the decision buffers live (item 0's slice lies in
+                        // front of them): before the first overlapping slice is written every thread has read
+                        if (last && j == 1) __syncthreads();
+                        rf::FFTN<M, -1>::run(d);
+                        float kf[2 * M];
+                        tmem_ld<2 * M>(kf, keep + j * 2 * M);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int m = 0; m < M; ++m) d[m] = csub(cmake(kf[2 * m], kf[2 * m + 1]), cmul(ic_s[m], d[m]));
+                        rf::FFTN<M, +1>::run(d);
+                        if (!last) {
+                            const int cnt = sic.count[k];
+                            unsigned char* mine = nxt + (size_t)it * M;
+#pragma unroll
+                            for (int m = 0; m < M; ++m) mine[m] = cnt ? decide(d[m]) : (unsigned char)255;
+                        } else {
+                            cpx* dst = buf + (size_t)it * M; // output staging, linear [k][m] (bulk-stored below)
+#pragma unroll
+                            for (int m = 0; m < M; ++m) dst[m] = d[m];
+                        }
+                    }
+                    if (!last) __syncthreads();
+                }
+            }
         }
         // output staging in the linear [k][m] order; item j covers the contiguous slice
         // [j*T*M, (j+1)*T*M), which is bulk-stored as soon as it is complete so that the first
@@ -635,7 +833,7 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_rx_kernel(cpx* __restrict
                 unsigned char* dst = reinterpret_cast<unsigned char*>(buf) + (size_t)(tid + j * T) * M;
                 const cpx* pts_s = taps_s + S::PTS_OFF;
                 decide_block<M>(v[j], dst, pts_s, sic.n_points, sic.rule, sic.grid, lut_s);
-            } else {
+            } else if constexpr (!(SIC && IPT > 1)) { // (that variant's cancellation loop has staged its results already)
                 cpx* dst = buf + (size_t)(tid + j * T) * M;
 #pragma unroll
                 for (int m = 0; m < M; ++m) dst[m] = v[j][m];
@@ -705,12 +903,31 @@ static void launch_rx(cpx* out, const cpx* in, const cpx* eq, const cpx* table, 
     a.in_stride = in_stride;
     fused_rx_kernel<S, false><<<grid, S::T, S::SMEM_BYTES, s>>>(out, in, eq, table, tw, taps, L, mode, n_frames, a);
 }
+// The cancellation loop runs on the shape itself when a thread owns one subcarrier, otherwise on a companion shape whose
+// tensor memory has room for the kept blocks (row-FFT twiddles back in shared memory): SicShape<S>.
+template <class S, bool ONE = S::IPT == 1>
+struct SicShape {
+    typedef S type;
+};
+template <class S>
+struct SicShape<S, false> {
+    typedef Shape<S::M, S::R1, S::R2, S::T, S::IPT, S::MINB, true, false, S::IPT * 2 * S::M> type;
+};
+template <class S>
+constexpr bool sic_shape_ok()
+{
+    typedef typename SicShape<S>::type X;
+    if (S::IPT == 1) return S::T / (S::K < 32 ? S::K : 32) <= 32; // partial sums of the phase estimate: 32-float scratch
+    return X::TBL_TMEM && X::F == 1 && X::TMEM_USED <= 512 && X::TMEM_COLS * X::MINB <= 512 && X::T / 32 <= 32 &&
+           X::BUF_ELEMS - (2 * X::F * X::N + 7) / 8 >= X::T * X::M;
+}
 template <class S>
 static void launch_sic(cpx* out, const cpx* in, const cpx* eq, const cpx* table, const cpx* tw, const cpx* taps, int L,
                        int n_frames, int grid, SicArgs sic, cudaStream_t s)
 {
-    if constexpr (S::IPT == 1)
-        fused_rx_kernel<S, true><<<grid, S::T, S::SMEM_BYTES, s>>>(out, in, eq, table, tw, taps, L, 0, n_frames, sic);
+    typedef typename SicShape<S>::type X;
+    if constexpr (sic_shape_ok<S>())
+        fused_rx_kernel<X, true><<<grid, X::T, X::SMEM_BYTES, s>>>(out, in, eq, table, tw, taps, L, 0, n_frames, sic);
 }
 
 
@@ -741,10 +958,10 @@ static ShapeEntry make_entry(const char* mn, const char* rn, const char* tn)
     e.modc_name = std::string(mn) + "+chunks";
     e.txc_name = std::string(tn) + "+chunks";
     e.rxd_name = std::string(rn) + "+decide";
-    // the phase-compensation reduction of the cancellation loop keeps T / min(K, 32) partial sums in a 32-float scratch
-    if constexpr (S::IPT == 1 && S::T / (S::K < 32 ? S::K : 32) <= 32) {
+    if constexpr (sic_shape_ok<S>()) {
         e.sic = &launch_sic<S>;
-        e.sic_fn = (const void*)&fused_rx_kernel<S, true>;
+        e.sic_fn = (const void*)&fused_rx_kernel<typename SicShape<S>::type, true>;
+        e.sic_smem = SicShape<S>::type::SMEM_BYTES;
     }
     return e;
 }

@@ -347,7 +347,7 @@ bool FusedModem::init_sic(const std::vector<std::complex<float>>& ic_taps,
         if (k < 0 || k >= e->K || count[k] == 255) return false;
         ++count[k];
     }
-    impl_->sic_grid_cap = fused_grid_cap(e->sic_fn, e->T, e->smem);
+    impl_->sic_grid_cap = fused_grid_cap(e->sic_fn, e->T, e->sic_smem ? e->sic_smem : e->smem);
     impl_->d_ic = upload(to_cpx(ic_taps));
     impl_->d_points = upload(to_cpx(points));
     impl_->d_count = upload(count);
@@ -375,6 +375,8 @@ int FusedModem::demodulate_sic(cpx* out, const cpx* in, const cpx* eq, size_t fr
                                cudaStream_t s)
 {
     const ShapeEntry* e = impl_->e;
+    // no iterations: advanced_receiver_kernel_cc::generic_work is the plain receiver (perform_ic_iterations does nothing)
+    if (ic_iter <= 0 && e->sic_smem) return demodulate(out, nullptr, in, eq, frames, s);
     int launches = 0;
     const size_t N = (size_t)e->M * e->K;
     const size_t max_chunk = (size_t)1 << 20;

@@ -45,6 +45,7 @@ struct ShapeEntry {
     const void* rx_fn;
     const void* sic_fn;
     const char* sic_name;
+    size_t sic_smem = 0; // shared memory of the cancellation variant (a companion shape when IPT > 1)
     // chunk entries: modulator / transmitter chain with byte input, receiver with hard-decision output
     tx_launch_t modc, txc;
     sic_launch_t rxd;
