@@ -375,8 +375,10 @@ __device__ __forceinline__ void row_fft(cpx* __restrict__ buf, const cpx* __rest
             if constexpr (ITEMS2 % 32 == 0) {
                 if (it >= ITEMS2) break; // whole warps drop out together
             } else {
-                // surplus lanes of the last warp redo the last item (same reads, same values written):
-                // no divergence around the warp barrier and b[] stays in registers
+                // whole warps without an item drop out; the surplus lanes of the one partly populated warp redo the
+                // last item (same reads, same values written, same warp as its owner): no divergence around the warp
+                // barrier and b[] stays in registers
+                if ((it & ~31) >= ITEMS2) break;
                 it = it < ITEMS2 ? it : ITEMS2 - 1;
             }
             const int row = it / R1, k1 = it - row * R1;

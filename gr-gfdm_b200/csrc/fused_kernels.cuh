@@ -355,6 +355,7 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_rx_kernel(cpx* __restrict
     cpx* pre = tbl_s + S::TBL_ELEMS;
     cpx* taps_s = pre + S::P_ELEMS;
     uint64_t* bar_p = reinterpret_cast<uint64_t*>(taps_s + S::TAPS_ELEMS);
+    uint64_t* bar_h = bar_p + 2; // channel of the current group (equalising variant); bar_p + 1 holds the tensor-memory slot
     const int tid = threadIdx.x;
     const int n_groups = (n_frames + F - 1) / F;
     const float inv_m = 1.0f / (float)M;
@@ -377,7 +378,10 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_rx_kernel(cpx* __restrict
     unsigned char* lut_s = reinterpret_cast<unsigned char*>(taps_s + S::RED_OFF + 16);
     if constexpr (SIC || DEC)
         if (tid < 64) lut_s[tid] = sic.grid.lut[tid];
-    if (tid == 0) mbar_init(bar_p, 1);
+    if (tid == 0) {
+        mbar_init(bar_p, 1);
+        mbar_init(bar_h, 1);
+    }
     // table columns of this thread -> tensor memory (once per CTA)
     uint32_t tmem_base = 0, tmem_mine = 0;
     if constexpr (S::TBL_TMEM) {
@@ -422,12 +426,14 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_rx_kernel(cpx* __restrict
         if (tid == 0) load_head(g);
         load_rest(g);
     }
-    uint32_t phase = 0;
+    uint32_t phase = 0, phase_h = 0;
     STAGE_INIT();
     for (; g < n_groups; g += gridDim.x) {
         const int fh = min(F, n_frames - g * F);
         const int gn = g + gridDim.x;
         cpx v[IPT][M];
+        // the channel of this group is needed ~10k cycles from now: into L2 with it
+        if (eq != nullptr && tid == 0) bulk_prefetch_l2(eq + (size_t)g * F * N, (uint32_t)fh * N * sizeof(cpx));
         STAGE_MARK(15) // loop top (bulk store issue)
         mbar_wait(bar_p, phase);
         phase ^= 1;
@@ -501,42 +507,34 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_rx_kernel(cpx* __restrict
         __syncthreads();
         STAGE_MARK(22) // stage C' reads
         // Equalisation with overlap 2 (every reference configuration): the division and the tap combine stay in registers.
-        // The channel of the group is read coalesced (consecutive lanes on consecutive bins), inverted once and handed to
-        // the owning threads through shared memory; the only neighbour a subcarrier needs is k-1, i.e. the previous lane
-        // (a shuffle) -- lane 0 takes it from a small per-warp hand-over array in the unused tail of the row buffer.
-        // Shared-memory traffic: 2*IPT*M accesses per thread (+ broadcast tap reads) instead of 7*IPT*M.
+        // The channel of the group arrives by ONE bulk copy (TMA) into the row buffer, which is free once the columns are in
+        // registers, in exactly the [k][m] order its owners read it in; it was pulled into L2 at the top of the iteration,
+        // so the copy is short.  The only neighbour a subcarrier needs is k-1, i.e. the previous lane (a shuffle) -- lane 0
+        // takes it from a small per-warp hand-over array in the unused tail of the row buffer.
         constexpr bool EQ_FAST_OK = !S::TWO_PASS || S::BUF_ELEMS - F * N >= F * N / 32;
         if (eq != nullptr && L == 2 && EQ_FAST_OK) {
             const cpx* eqg = eq + (size_t)g * F * N;
-            {
-                // IPT*M bins per thread in chunks of CH: loads of a chunk in flight together, few live registers
-                constexpr int PER = IPT * M, CH = 5;
-#pragma unroll
-                for (int q0 = 0; q0 < PER; q0 += CH) {
-                    cpx hq[CH];
-#pragma unroll
-                    for (int c = 0; c < CH; ++c) {
-                        const int i = tid + (q0 + c) * T;
-                        hq[c] = (q0 + c < PER && i < fh * N) ? ldg_stream(eqg + i) : cmake(1.f, 0.f);
-                    }
-#pragma unroll
-                    for (int c = 0; c < CH; ++c) {
-                        if (q0 + c < PER) {
-                            const float rden = __fdividef(1.0f, hq[c].x * hq[c].x + hq[c].y * hq[c].y);
-                            // 1/h = conj(h) / |h|^2 (volk_32fc_x2_divide_32fc)
-                            buf[tid + (q0 + c) * T] = cmake(hq[c].x * rden, -hq[c].y * rden);
-                        }
-                    }
-                }
+            if (tid == 0) {
+                fence_proxy_async();
+                mbar_expect_tx(bar_h, (uint32_t)fh * N * sizeof(cpx));
+                bulk_load(buf, eqg, (uint32_t)fh * N * sizeof(cpx), bar_h);
             }
-            __syncthreads();
+            mbar_wait(bar_h, phase_h);
+            phase_h ^= 1;
             cpx* bnd = buf + F * N; // [item warp][M]: the equalised bins of every warp's last lane
 #pragma unroll
             for (int j = 0; j < IPT; ++j) {
                 const int it = tid + j * T;
-                const cpx* rr = buf + (size_t)it * M;
+                if (it < fh * K) { // (frames behind the batch end have no channel)
+                    const cpx* hh = buf + (size_t)it * M;
 #pragma unroll
-                for (int m = 0; m < M; ++m) v[j][m] = cmul(v[j][m], rr[m]);
+                    for (int m = 0; m < M; ++m) {
+                        const cpx h1 = hh[m];
+                        const float rden = __fdividef(1.0f, h1.x * h1.x + h1.y * h1.y);
+                        const cpx num = cmulc(v[j][m], h1); // y * conj(h) / |h|^2, volk_32fc_x2_divide_32fc
+                        v[j][m] = cmake(num.x * rden, num.y * rden);
+                    }
+                }
                 if constexpr (K >= 32) {
                     if ((tid & 31) == 31) {
                         cpx* b = bnd + (size_t)(it >> 5) * M;
