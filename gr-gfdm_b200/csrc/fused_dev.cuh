@@ -318,7 +318,7 @@ __device__ __forceinline__ void row_fft(cpx* __restrict__ buf, const cpx* __rest
         constexpr int ITEMS1 = S::ROWS * R2;
         // Twiddles in tensor memory: tcgen05.ld is a warp-wide (.sync.aligned) instruction, so a warp whose last round is
         // only partly populated (ITEMS1 not a multiple of 32) must still execute it with every lane -- the surplus lanes
-        // run the round on the last item's addresses for the loads and skip the stores.  Whole warps still drop out.
+        // run the round without touching shared memory.  Whole warps still drop out.
         constexpr bool PARTIAL_WARP = S::TW_TMEM && ITEMS1 % 32 != 0;
         constexpr int ROUNDS1 = (ITEMS1 + T - 1) / T;
 #pragma unroll 1
@@ -336,7 +336,7 @@ __device__ __forceinline__ void row_fft(cpx* __restrict__ buf, const cpx* __rest
             cpx* p = buf + row * RS + n0;
             cpx a[R1];
 #pragma unroll
-            for (int i = 0; i < R1; ++i) a[i] = p[(R2 + 1) * i];
+            for (int i = 0; i < R1; ++i) a[i] = live ? p[(R2 + 1) * i] : cmake(0.f, 0.f); // (surplus lanes touch no data)
             rf::FFTN<R1, DIR>::run(a);
             // twiddle + store in chunks of 8; the empty asm keeps the chunks in program order so that
             // at most 8 twiddles are live next to the 2*R1 data registers (no spills in this hot loop)

@@ -642,12 +642,15 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_rx_kernel(cpx* __restrict
                     // gr::digital::constellation_qpsk: idx = 2*(im > 0) + (re > 0), point = (+-a, +-a): no table lookup
 #pragma unroll
                     for (int m = 0; m < M; ++m) d[m] = cmake(y[m].x > 0.f ? qa : -qa, y[m].y > 0.f ? qa : -qa);
+                } else if (sic.rule != 1 && sic.grid.n_re > 0) {
+                    // grid constellation (square / rectangular QAM): straight-line quantiser, no call in this loop
+#pragma unroll
+                    for (int m = 0; m < M; ++m)
+                        d[m] = cnt ? pts_s[decide_symbol_grid_fast(y[m], sic.grid, lut_s)] : cmake(0.f, 0.f);
                 } else {
 #pragma unroll
                     for (int m = 0; m < M; ++m)
-                        d[m] = cnt ? pts_s[(sic.rule != 1 && sic.grid.n_re > 0)
-                                               ? decide_symbol_grid_fast(y[m], sic.grid, lut_s)
-                                               : decide_symbol_grid(y[m], pts_s, sic.n_points, sic.rule, sic.grid, lut_s)]
+                        d[m] = cnt ? pts_s[decide_symbol_grid(y[m], pts_s, sic.n_points, sic.rule, sic.grid, lut_s)]
                                    : cmake(0.f, 0.f);
                 }
                 if (sic.phase_comp > 0 && it == 0) {
@@ -698,24 +701,53 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_rx_kernel(cpx* __restrict
             // never stay in registers across an iteration -- every new y is decided at once and only the DECISIONS (one byte
             // per symbol: constellation index, 255 = inactive subcarrier) are exchanged through shared memory, double
             // buffered in the tail of the row buffer.  lib/advanced_receiver_kernel_cc.cc:56-76, receiver_kernel_cc.cc:274-299.
-            constexpr int EXB = F * N;                                  // bytes of one decision buffer
+            // A record = the M decisions of one subcarrier packed into W4 16-byte words: one 128-bit store by its owner, one
+            // 128-bit load per neighbour (byte-wide accesses at a 15-byte stride would be 4-way bank conflicts each).
+            constexpr int W4 = (M + 15) / 16;
+            constexpr int EXB = F * K * W4 * 16;                        // bytes of one decision buffer
             constexpr int EX_OFF = S::BUF_ELEMS - (2 * EXB + 7) / 8;    // both buffers at the end of the row buffer
-            static_assert(EX_OFF >= T * M, "decision buffers must not overlap the output staging of item 0");
-            unsigned char* ex0 = reinterpret_cast<unsigned char*>(buf + EX_OFF);
+            static_assert(EX_OFF >= T * M && (EX_OFF % 2) == 0, "decision buffers must not overlap the output staging of item 0");
+            uint4* ex0 = reinterpret_cast<uint4*>(buf + EX_OFF);
             const cpx* ic_s = taps_s + S::IC_OFF;
             const cpx* pts_s = taps_s + S::PTS_OFF;
             float* red_s = reinterpret_cast<float*>(taps_s + S::RED_OFF);
             const uint32_t keep = tmem_mine + S::TMEM_TBL_COLS + S::TMEM_TW_COLS;
             const float qa = sic.qpsk_a;
             const int n_pts = sic.n_points;
-            auto point = [&](unsigned char b) -> cpx {
-                if (qa > 0.f) return b < 4 ? cmake((b & 1) ? qa : -qa, (b & 2) ? qa : -qa) : cmake(0.f, 0.f);
+            auto point = [&](unsigned b) -> cpx {
+                if (qa > 0.f) return b < 4u ? cmake((b & 1u) ? qa : -qa, (b & 2u) ? qa : -qa) : cmake(0.f, 0.f);
                 return (int)b < n_pts ? pts_s[b] : cmake(0.f, 0.f);
             };
-            auto decide = [&](cpx y) -> unsigned char {
-                if (qa > 0.f) return (unsigned char)(2 * (y.y > 0.f) + (y.x > 0.f));
-                if (sic.rule != 1 && sic.grid.n_re > 0) return (unsigned char)decide_symbol_grid_fast(y, sic.grid, lut_s);
-                return (unsigned char)decide_symbol_grid(y, pts_s, n_pts, sic.rule, sic.grid, lut_s);
+            auto decide = [&](cpx y) -> unsigned {
+                if (qa > 0.f) return (unsigned)(2 * (y.y > 0.f) + (y.x > 0.f));
+                if (sic.rule != 1 && sic.grid.n_re > 0) return (unsigned)decide_symbol_grid_fast(y, sic.grid, lut_s);
+                return (unsigned)decide_symbol_grid(y, pts_s, n_pts, sic.rule, sic.grid, lut_s);
+            };
+            auto byte_of = [](const uint4 (&r)[W4], int m) -> unsigned {
+                const uint4& q = r[m >> 4];
+                const unsigned w = ((m >> 2) & 3) == 0 ? q.x : ((m >> 2) & 3) == 1 ? q.y : ((m >> 2) & 3) == 2 ? q.z : q.w;
+                return (w >> (8 * (m & 3))) & 0xffu;
+            };
+            // decisions of one subcarrier -> its record in decision buffer `dstb`
+            auto publish = [&](uint4* dstb, int it, const cpx (&y)[M], int cnt) {
+                unsigned w[W4 * 4];
+#pragma unroll
+                for (int q = 0; q < W4 * 4; ++q) w[q] = 0xffffffffu; // 255 = no symbol (inactive subcarrier, padding)
+                auto put = [&](int m, unsigned b) { w[m >> 2] = (w[m >> 2] & ~(0xffu << (8 * (m & 3)))) | (b << (8 * (m & 3))); };
+                if (cnt) { // the decision rule is picked outside the unrolled loops: the common ones stay call-free
+                    if (qa > 0.f) {
+#pragma unroll
+                        for (int m = 0; m < M; ++m) put(m, (unsigned)(2 * (y[m].y > 0.f) + (y[m].x > 0.f)));
+                    } else if (sic.rule != 1 && sic.grid.n_re > 0) {
+#pragma unroll
+                        for (int m = 0; m < M; ++m) put(m, (unsigned)decide_symbol_grid_fast(y[m], sic.grid, lut_s));
+                    } else {
+#pragma unroll
+                        for (int m = 0; m < M; ++m) put(m, decide(y[m]));
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < W4; ++q) dstb[(size_t)it * W4 + q] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
             };
             // prologue: park R_k / M, first soft symbols, first decisions (+ the phase estimate's partial sums)
             float part = 0.f;
@@ -732,16 +764,13 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_rx_kernel(cpx* __restrict
                 }
                 tmem_st<2 * M>(keep + j * 2 * M, kf);
                 rf::FFTN<M, +1>::run(v[j]); // y = IFFT_M(R_k) / M
-                {   // (ic_iter >= 1: without iterations the host runs the plain receiver)
-                    unsigned char* mine = ex0 + (size_t)it * M;
+                // (ic_iter >= 1: without iterations the host runs the plain receiver)
+                publish(ex0, it, v[j], cnt);
+                if (sic.phase_comp > 0 && cnt) {
 #pragma unroll
                     for (int m = 0; m < M; ++m) {
-                        const unsigned char b = cnt ? decide(v[j][m]) : (unsigned char)255;
-                        mine[m] = b;
-                        if (sic.phase_comp > 0 && cnt) {
-                            const cpx dd = point(b);
-                            part += (float)cnt * (atan2f(dd.y, dd.x) - atan2f(v[j][m].y, v[j][m].x));
-                        }
+                        const cpx dd = point(decide(v[j][m]));
+                        part += (float)cnt * (atan2f(dd.y, dd.x) - atan2f(v[j][m].y, v[j][m].x));
                     }
                 }
             }
@@ -779,17 +808,21 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_rx_kernel(cpx* __restrict
                 __syncthreads();
                 for (int iter = 0; iter < sic.ic_iter; ++iter) {
                     const bool last = iter == sic.ic_iter - 1;
-                    const unsigned char* cur = ex0 + (size_t)(iter & 1) * EXB;
-                    unsigned char* nxt = ex0 + (size_t)((iter + 1) & 1) * EXB;
+                    const uint4* cur = ex0 + (size_t)(iter & 1) * (EXB / 16);
+                    uint4* nxt = ex0 + (size_t)((iter + 1) & 1) * (EXB / 16);
 #pragma unroll
                     for (int j = 0; j < IPT; ++j) {
                         const int it = tid + j * T, f = it / K, k = it - f * K;
                         const int kp = k == 0 ? K - 1 : k - 1, kn = k == K - 1 ? 0 : k + 1;
-                        const unsigned char* prev = cur + ((size_t)f * K + kp) * M;
-                        const unsigned char* next = cur + ((size_t)f * K + kn) * M;
+                        uint4 rp[W4], rn[W4];
+#pragma unroll
+                        for (int q = 0; q < W4; ++q) {
+                            rp[q] = cur[((size_t)f * K + kp) * W4 + q];
+                            rn[q] = cur[((size_t)f * K + kn) * W4 + q];
+                        }
                         cpx d[M];
 #pragma unroll
-                        for (int m = 0; m < M; ++m) d[m] = cadd(point(prev[m]), point(next[m]));
+                        for (int m = 0; m < M; ++m) d[m] = cadd(point(byte_of(rp, m)), point(byte_of(rn, m)));
                         // the last iteration stages its results where the decision buffers live (item 0's slice lies in
                         // front of them): before the first overlapping slice is written every thread has read
                         if (last && j == 1) __syncthreads();
@@ -801,10 +834,7 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_rx_kernel(cpx* __restrict
                         for (int m = 0; m < M; ++m) d[m] = csub(cmake(kf[2 * m], kf[2 * m + 1]), cmul(ic_s[m], d[m]));
                         rf::FFTN<M, +1>::run(d);
                         if (!last) {
-                            const int cnt = sic.count[k];
-                            unsigned char* mine = nxt + (size_t)it * M;
-#pragma unroll
-                            for (int m = 0; m < M; ++m) mine[m] = cnt ? decide(d[m]) : (unsigned char)255;
+                            publish(nxt, it, d, sic.count[k]);
                         } else {
                             cpx* dst = buf + (size_t)it * M; // output staging, linear [k][m] (bulk-stored below)
 #pragma unroll
@@ -917,7 +947,7 @@ constexpr bool sic_shape_ok()
     typedef typename SicShape<S>::type X;
     if (S::IPT == 1) return S::T / (S::K < 32 ? S::K : 32) <= 32; // partial sums of the phase estimate: 32-float scratch
     return X::TBL_TMEM && X::F == 1 && X::TMEM_USED <= 512 && X::TMEM_COLS * X::MINB <= 512 && X::T / 32 <= 32 &&
-           X::BUF_ELEMS - (2 * X::F * X::N + 7) / 8 >= X::T * X::M;
+           X::BUF_ELEMS - 4 * X::F * X::K * ((X::M + 15) / 16) >= X::T * X::M; // two packed decision buffers behind item 0's staging
 }
 template <class S>
 static void launch_sic(cpx* out, const cpx* in, const cpx* eq, const cpx* table, const cpx* tw, const cpx* taps, int L,
