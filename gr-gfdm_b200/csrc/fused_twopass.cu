@@ -21,8 +21,12 @@
 // Shared memory per CTA (same carve-up as fused_modem.cu): row buffer `buf` (M rows of K1, padded),
 // the row-FFT twiddles and the staging region P.  Input moves by cp.async.bulk (TMA 1D) and is prefetched
 // one pass ahead wherever a region is free; the pieces that cannot be resident early are fetched one
-// compute step ahead.  The equalising / interference-cancelling variants are not provided for this shape
-// (the filter needs both parities of Y); those entry points use the staged path of api.cu.
+// compute step ahead.  The equalising / interference-cancelling variants are not provided for this shape; those
+// entry points use the staged path of api.cu.  Why, and how it would be done: with Y/H between FFT and filter the taps
+// cannot be folded into the table, and R_k = G1[k-1] Y[k-1] + G0[k] Y[k] (G0 = T[m]/H, G1 = T[M+m]/H) mixes a bin of each
+// parity, i.e. of each pass.  Pass 0 would write P_k = G0 Y_k (even k) and Q_{k+1} = G1 Y_k to two per-CTA scratch arrays
+// that stay in L2 (as the modulator's even samples do), pass 1 would add its own terms, run every M-point IFFT and store
+// record pairs (2k'+1, 2k'+2) contiguously: 24 N bytes of HBM traffic plus 4 x N/2 complex of L2 traffic per frame.
 #include "fused.h"
 #include "fused_dev.cuh"
 
