@@ -630,8 +630,11 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_rx_kernel(cpx* __restrict
 #pragma unroll
             for (int m = 0; m < M; ++m) y[m] = v[0][m];
             rf::FFTN<M, +1>::run(y);
-            // the 1/M of transform_subcarriers_to_td is part of the folded table (the kept block is R_k / M already) and of
-            // the taps ic_s
+#pragma unroll
+            for (int m = 0; m < M; ++m) y[m] = cscale(y[m], inv_m);
+            // the 1/M of every later transform_subcarriers_to_td is folded into the kept block and the taps (ic_s), once
+#pragma unroll
+            for (int m = 0; m < M; ++m) v[0][m] = cscale(v[0][m], inv_m);
             const float qa = cnt ? sic.qpsk_a : 0.f;
             for (int it = 0; it < sic.ic_iter; ++it) {
                 cpx d[M];
@@ -754,7 +757,8 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_rx_kernel(cpx* __restrict
                 const int cnt = sic.count[k];
                 float kf[2 * M];
 #pragma unroll
-                for (int m = 0; m < M; ++m) { // (R_k / M already: the 1/M is part of the folded table)
+                for (int m = 0; m < M; ++m) {
+                    v[j][m] = cscale(v[j][m], inv_m);
                     kf[2 * m] = v[j][m].x;
                     kf[2 * m + 1] = v[j][m].y;
                 }
@@ -847,11 +851,9 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_rx_kernel(cpx* __restrict
 #pragma unroll
         for (int j = 0; j < IPT; ++j) {
             if (!SIC && mode != 1) {
-                rf::FFTN<M, +1>::run(v[j]); // y = IFFT_M(R_k) / M, the 1/M being part of the folded table
-            } else if (!SIC) {
-                // fft_[equalize_]filter_downsample returns R_k itself (the rare entry pays the multiply)
+                rf::FFTN<M, +1>::run(v[j]);
 #pragma unroll
-                for (int m = 0; m < M; ++m) v[j][m] = cscale(v[j][m], (float)M);
+                for (int m = 0; m < M; ++m) v[j][m] = cscale(v[j][m], inv_m);
             }
             if constexpr (DEC) {
                 // hard decisions (symbols2bits' argmin / the constellation's decision rule): the soft symbols never

@@ -95,9 +95,7 @@ std::vector<std::complex<double>> make_fold_table_d(int M, int K, int L, const s
             }
             const std::complex<double> w = std::polar(1.0, sign * 2.0 * M_PI * (double)((long)m * n1 % N) / (double)N);
             std::complex<double> c = G * w;
-            // modulator: the 1/N of the N-point IFFT; receiver: the 1/M of transform_subcarriers_to_td (:211-225) -- every
-            // stage between the table and the output is linear, so the scale costs nothing at run time
-            c /= sign > 0 ? (double)N : (double)M;
+            if (sign > 0) c /= (double)N;
             t[(size_t)m * K + n1] = c;
         }
     return t;

@@ -294,7 +294,7 @@ template <class S>
 __global__ void __launch_bounds__(S::T, 1) fused_rx2_kernel(cpx* __restrict__ out, const cpx* __restrict__ in,
                                                            const cpx* __restrict__ tables,
                                                            const cpx* __restrict__ tw, const cpx* __restrict__ w2,
-                                                           cpx* __restrict__ scratch, int mode, int n_frames)
+                                                           int mode, int n_frames)
 {
     constexpr int M = S::M, K1 = S::K, K = 2 * K1, N = M * K, T = S::T, RS = S::RS;
     static_assert(S::F == 1 && S::IPT == 2 && S::TWO_PASS, "two-pass kernels: one half-frame per CTA pass, two items per thread");
@@ -312,6 +312,7 @@ __global__ void __launch_bounds__(S::T, 1) fused_rx2_kernel(cpx* __restrict__ ou
     cpx* pre = tw_s + S::TW_ELEMS + S::TBL_ELEMS;
     uint64_t* bars = reinterpret_cast<uint64_t*>(pre + S::P_ELEMS + S::TAPS_ELEMS); // one per step
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const float inv_m = 1.0f / (float)M;
 
     for (int i = tid; i < S::TW_ELEMS; i += T) tw_s[i] = tw[i];
     if (tid == 0)
@@ -347,6 +348,8 @@ __global__ void __launch_bounds__(S::T, 1) fused_rx2_kernel(cpx* __restrict__ ou
                            first ? l2_policy_evict_last() : l2_policy_evict_first());
         }
     };
+    // copy-out index math: element i = tid + q*T of a staged item is element e of record r
+    const int r0 = tid / M, e0 = tid - r0 * M;
 
     int g = blockIdx.x;
     if (g < n_frames) {
@@ -420,10 +423,9 @@ __global__ void __launch_bounds__(S::T, 1) fused_rx2_kernel(cpx* __restrict__ ou
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 if (mode == 0) {
-                    rf::FFTN<M, +1>::run(v[j]); // the 1/M is part of the folded table
-                } else {
+                    rf::FFTN<M, +1>::run(v[j]);
 #pragma unroll
-                    for (int m = 0; m < M; ++m) v[j][m] = cscale(v[j][m], (float)M); // mode 1 returns R_k itself
+                    for (int m = 0; m < M; ++m) v[j][m] = cscale(v[j][m], inv_m);
                 }
                 cpx* st = buf + j * T * M;
 #pragma unroll
@@ -431,26 +433,16 @@ __global__ void __launch_bounds__(S::T, 1) fused_rx2_kernel(cpx* __restrict__ ou
                 __syncthreads();
                 // item 0's staging has been copied out: the upper halves of the rows that lie inside it are free
                 if (j == 1 && has_next) issue(gn, 1, 0, N1A, true, p == 1);
-                // Records of the two parities alternate in the output, so a pass on its own could only write 120-byte runs
-                // with 120-byte gaps (half-filled sectors, measured: 8.6k cycles per pass against 3.2k for the contiguous
-                // stores of the single-pass kernel).  Pass 0 therefore parks its records in this CTA's L2-resident scratch
-                // (contiguous), and pass 1 writes the item's 2T records -- its own out of the staging, the others out of
-                // the scratch -- with consecutive lanes on consecutive output elements.
-                cpx* sc = scratch + (size_t)blockIdx.x * (M * K1) + (size_t)j * T * M;
-                if (p == 0) {
-                    const uint64_t pol_keep = l2_policy_evict_last();
-#pragma unroll 5
-                    for (int q = 0; q < M; ++q) stg_hint(sc + tid + q * T, st[tid + q * T], pol_keep);
-                } else {
-                    const uint64_t pol_drop = l2_policy_evict_first();
-                    cpx* ob = of + (size_t)(2 * j * T) * M; // records 2*j*T .. 2*(j+1)*T - 1
-#pragma unroll 5
-                    for (int q = 0; q < 2 * M; ++q) {        // (5 loads in flight; v[1] is still live during item 0)
-                        const int i2 = tid + q * T;          // output element of this item's region
-                        const int rr = i2 / M, e = i2 - rr * M, kl = rr >> 1;
-                        const cpx val = (rr & 1) ? st[kl * M + e] : ldg_hint(sc + kl * M + e, pol_drop);
-                        stg_stream(ob + i2, val);
-                    }
+                cpx* ob = of + (2 * j * T + p) * M; // record 2*(j*T + r) + p starts at ob + 2*M*r
+#pragma unroll
+                for (int q = 0; q < M; ++q) {
+                    // i = tid + q*T = M*(r0 + (T/M)*q) + e0 + (T%M)*q
+                    constexpr int TQ = T / M, TR = T % M;
+                    int e = e0 + TR * q, r = r0 + TQ * q;
+#pragma unroll
+                    for (int c = 0; c < (M - 1 + TR * (M - 1)) / M; ++c)
+                        if (e >= M) { e -= M; ++r; }
+                    stg_stream(ob + 2 * M * r + e, st[tid + q * T]);
                 }
             }
             __syncthreads();
@@ -470,7 +462,7 @@ struct TwoPass {
     cpx* d_table = nullptr;
     cpx* d_tw = nullptr;
     cpx* d_w2 = nullptr;
-    cpx* d_scratch = nullptr; // grid_cap x M*K1: modulator -- even samples of pass 0, receiver -- parity-0 records (L2 resident)
+    cpx* d_scratch = nullptr; // modulator: grid_cap x M*K1 even samples of pass 0 (L2 resident)
     int grid_cap = 0;
     size_t smem = 0;
     std::string name;
@@ -551,7 +543,6 @@ TwoPass* twopass_create_rx(int M, int K, int L, const std::vector<std::complex<f
         t->d_w2 = upload(w);
         t->d_table = upload(P);
         t->d_tw = upload(make_row_twiddles(S::R1, S::R2));
-        GFDM_CUDA_CHECK(cudaMalloc(&t->d_scratch, sizeof(cpx) * (size_t)t->grid_cap * M * K1)); // parity-0 records of pass 0
     } catch (...) {
         twopass_free(t);
         throw;
@@ -582,7 +573,7 @@ int twopass_demodulate(TwoPass* t, cpx* out, const cpx* in, int mode, size_t fra
     for (size_t f0 = 0; f0 < frames; f0 += max_chunk) {
         const int nf = (int)std::min(max_chunk, frames - f0);
         const int grid = nf < t->grid_cap ? nf : t->grid_cap;
-        fused_rx2_kernel<S><<<grid, S::T, S::SMEM_BYTES, s>>>(out + f0 * N, in + f0 * N, t->d_table, t->d_tw, t->d_w2, t->d_scratch, mode, nf);
+        fused_rx2_kernel<S><<<grid, S::T, S::SMEM_BYTES, s>>>(out + f0 * N, in + f0 * N, t->d_table, t->d_tw, t->d_w2, mode, nf);
         ++launches;
     }
     GFDM_CUDA_CHECK(cudaGetLastError());
