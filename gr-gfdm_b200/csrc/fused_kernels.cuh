@@ -107,6 +107,11 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_mod_kernel(cpx* __restric
     }
     __syncthreads();
 
+    // The plain modulator never stages the tail of a group that does not fit region P: the threads whose records lie behind
+    // PF read them straight from global memory (pulled into L2 when the head is issued), ahead of their shared-memory
+    // reads.  A second bulk copy per group costs its issuing thread ~1400 cycles while the head copy is still in flight
+    // (stage profile r02h: "tail load issue" 1441 of 14.7k cycles per frame at C3), and every warp waits for that thread.
+    constexpr bool REG_TAIL = !TXF && !CHK && PF < F * N;
     // issue the bulk loads of group gg: head -> P, tail -> R
     auto load_head = [&](int gg) {
         const int el = min(F, n_frames - gg * F) * EL;
@@ -124,7 +129,7 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_mod_kernel(cpx* __restric
         if (el > PF) bulk_prefetch_l2(in + (size_t)gg * F * EL + PF, (uint32_t)(el - PF) * sizeof(cpx));
     };
     auto load_tail = [&](int gg) {
-        if constexpr (CHK) return;
+        if constexpr (CHK || REG_TAIL) return;
         const int el = min(F, n_frames - gg * F) * EL;
         const uint32_t bytes = (uint32_t)max(el - PF, 0) * sizeof(cpx);
         mbar_expect_tx(bar_r, bytes);
@@ -162,8 +167,8 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_mod_kernel(cpx* __restric
         // the tail of the staged group (region R) is only read by the items whose records lie behind PF: the plain
         // modulator waits for it right before the first of those (the transmitter's gather may touch it anywhere)
         constexpr int J_TAIL = PF / (T * M); // first item with a record at or behind PF
-        constexpr bool LATE_TAIL = !TXF && !CHK && PF < F * N && J_TAIL >= 1 && J_TAIL < IPT;
-        if (!CHK && !LATE_TAIL && PF < F * N) mbar_wait(bar_r, phase);
+        constexpr bool LATE_TAIL = !REG_TAIL && !TXF && !CHK && PF < F * N && J_TAIL >= 1 && J_TAIL < IPT;
+        if (!CHK && !REG_TAIL && !LATE_TAIL && PF < F * N) mbar_wait(bar_r, phase);
         STAGE_MARK(0) // wait for the bulk loads
 
         cpx v[IPT][M];
@@ -174,6 +179,25 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_mod_kernel(cpx* __restric
                 const unsigned char* src = pre_b + (tid + j * T) * M;
 #pragma unroll
                 for (int m = 0; m < M; ++m) v[j][m] = lookup(src[m]);
+            }
+        } else if constexpr (!TXF && REG_TAIL) {
+            // records behind PF first (global loads in flight while the others are read from shared memory)
+            const cpx* gin = in + (size_t)g * F * N;
+#pragma unroll
+            for (int j = IPT - 1; j >= 0; --j) {
+                const int e = (tid + j * T) * M; // (f*K + k)*M
+                if (e >= PF) {
+#pragma unroll
+                    for (int m = 0; m < M; ++m) v[j][m] = e < fh * N ? ldg_stream(gin + e + m) : cmake(0.f, 0.f);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < IPT; ++j) {
+                const int e = (tid + j * T) * M;
+                if (e < PF) {
+#pragma unroll
+                    for (int m = 0; m < M; ++m) v[j][m] = pre[e + m];
+                }
             }
         } else if constexpr (!TXF) {
 #pragma unroll
@@ -246,12 +270,16 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_mod_kernel(cpx* __restric
 #pragma unroll
             for (int m = 0; m < M; ++m) v[j][m] = src[m * RS];
         }
+        STAGE_MARK(7) // stage C reads (own loads issued)
         __syncthreads(); // R is dead: fetch the tail of the next group while stage C computes and stores
-        if (tid == 0 && gn < n_groups) {
-            fence_proxy_async();
-            load_tail(gn);
+        STAGE_MARK(8) // barrier behind the column reads
+        if constexpr (!REG_TAIL) {
+            if (tid == 0 && gn < n_groups) {
+                fence_proxy_async();
+                load_tail(gn);
+            }
         }
-        STAGE_MARK(5) // stage C reads
+        STAGE_MARK(5) // issue of the tail load (transmitter chain / shapes whose group fits region P: none)
 #pragma unroll
         for (int j = 0; j < IPT; ++j) {
             const int it = tid + j * T;
@@ -338,7 +366,10 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_mod_kernel(cpx* __restric
 // frame of the NEXT group (TMA prefetch); the remaining rows are prefetched into registers.
 
 // DEC = true: the output is the hard decision of every soft symbol, one byte per symbol (chunks) -- see the epilogue.
-template <class S, bool SIC, bool DEC = false>
+// EQ = true: the equalising variants (eq != nullptr).  A template parameter, not a run-time branch: the plain receiver is the
+// headline kernel and must not carry the equaliser's registers, barrier and branches (measured: 0.223 -> 0.237 ms at C3 with
+// the equaliser compiled into the same kernel).
+template <class S, bool SIC, bool DEC = false, bool EQ = false>
 __global__ void __launch_bounds__(S::T, S::MINB) fused_rx_kernel(cpx* __restrict__ out, const cpx* __restrict__ in,
                                                                  const cpx* __restrict__ eq,
                                                                  const cpx* __restrict__ table,
@@ -433,7 +464,8 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_rx_kernel(cpx* __restrict
         const int gn = g + gridDim.x;
         cpx v[IPT][M];
         // the channel of this group is needed ~10k cycles from now: into L2 with it
-        if (eq != nullptr && tid == 0) bulk_prefetch_l2(eq + (size_t)g * F * N, (uint32_t)fh * N * sizeof(cpx));
+        if constexpr (EQ)
+            if (tid == 0) bulk_prefetch_l2(eq + (size_t)g * F * N, (uint32_t)fh * N * sizeof(cpx));
         STAGE_MARK(15) // loop top (bulk store issue)
         mbar_wait(bar_p, phase);
         phase ^= 1;
@@ -512,7 +544,7 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_rx_kernel(cpx* __restrict
         // so the copy is short.  The only neighbour a subcarrier needs is k-1, i.e. the previous lane (a shuffle) -- lane 0
         // takes it from a small per-warp hand-over array in the unused tail of the row buffer.
         constexpr bool EQ_FAST_OK = !S::TWO_PASS || S::BUF_ELEMS - F * N >= F * N / 32;
-        if (eq != nullptr && L == 2 && EQ_FAST_OK) {
+        if (EQ && L == 2 && EQ_FAST_OK) {
             const cpx* eqg = eq + (size_t)g * F * N;
             if (tid == 0) {
                 fence_proxy_async();
@@ -570,7 +602,7 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_rx_kernel(cpx* __restrict
                 }
             }
             __syncthreads(); // the inverted channel and the hand-over array are dead: the row buffer may be reused
-        } else if (eq != nullptr) {
+        } else if (EQ) {
             // any other overlap: Y[b*M+m] back to the linear [b][m] order, divide by the channel, combine the L parts
 #pragma unroll
             for (int j = 0; j < IPT; ++j) {
@@ -921,7 +953,10 @@ template <class S>
 static void launch_rxd(cpx* out, const cpx* in, const cpx* eq, const cpx* table, const cpx* tw, const cpx* taps, int L,
                        int n_frames, int grid, SicArgs sic, cudaStream_t s)
 {
-    fused_rx_kernel<S, false, true><<<grid, S::T, S::SMEM_BYTES, s>>>(out, in, eq, table, tw, taps, L, 0, n_frames, sic);
+    if (eq)
+        fused_rx_kernel<S, false, true, true><<<grid, S::T, S::SMEM_BYTES, s>>>(out, in, eq, table, tw, taps, L, 0, n_frames, sic);
+    else
+        fused_rx_kernel<S, false, true, false><<<grid, S::T, S::SMEM_BYTES, s>>>(out, in, eq, table, tw, taps, L, 0, n_frames, sic);
 }
 template <class S>
 static void launch_rx(cpx* out, const cpx* in, const cpx* eq, const cpx* table, const cpx* tw, const cpx* taps, int L,
@@ -929,7 +964,10 @@ static void launch_rx(cpx* out, const cpx* in, const cpx* eq, const cpx* table, 
 {
     SicArgs a{};
     a.in_stride = in_stride;
-    fused_rx_kernel<S, false><<<grid, S::T, S::SMEM_BYTES, s>>>(out, in, eq, table, tw, taps, L, mode, n_frames, a);
+    if (eq)
+        fused_rx_kernel<S, false, false, true><<<grid, S::T, S::SMEM_BYTES, s>>>(out, in, eq, table, tw, taps, L, mode, n_frames, a);
+    else
+        fused_rx_kernel<S, false, false, false><<<grid, S::T, S::SMEM_BYTES, s>>>(out, in, eq, table, tw, taps, L, mode, n_frames, a);
 }
 // The cancellation loop runs on the shape itself when a thread owns one subcarrier, otherwise on a companion shape whose
 // tensor memory has room for the kept blocks (row-FFT twiddles back in shared memory): SicShape<S>.
@@ -954,8 +992,12 @@ static void launch_sic(cpx* out, const cpx* in, const cpx* eq, const cpx* table,
                        int n_frames, int grid, SicArgs sic, cudaStream_t s)
 {
     typedef typename SicShape<S>::type X;
-    if constexpr (sic_shape_ok<S>())
-        fused_rx_kernel<X, true><<<grid, X::T, X::SMEM_BYTES, s>>>(out, in, eq, table, tw, taps, L, 0, n_frames, sic);
+    if constexpr (sic_shape_ok<S>()) {
+        if (eq)
+            fused_rx_kernel<X, true, false, true><<<grid, X::T, X::SMEM_BYTES, s>>>(out, in, eq, table, tw, taps, L, 0, n_frames, sic);
+        else
+            fused_rx_kernel<X, true, false, false><<<grid, X::T, X::SMEM_BYTES, s>>>(out, in, eq, table, tw, taps, L, 0, n_frames, sic);
+    }
 }
 
 
@@ -973,7 +1015,8 @@ static ShapeEntry make_entry(const char* mn, const char* rn, const char* tn)
     e.mod = &launch_mod<S>;
     e.rx = &launch_rx<S>;
     e.mod_fn = (const void*)&fused_mod_kernel<S, false>;
-    e.rx_fn = (const void*)&fused_rx_kernel<S, false>;
+    e.rx_fn = (const void*)&fused_rx_kernel<S, false, false, false>;
+    e.rx_eq_fn = (const void*)&fused_rx_kernel<S, false, false, true>;
     e.sic = nullptr;
     e.sic_fn = nullptr;
     e.sic_name = "none";
@@ -982,13 +1025,15 @@ static ShapeEntry make_entry(const char* mn, const char* rn, const char* tn)
     e.rxd = &launch_rxd<S>;
     e.modc_fn = (const void*)&fused_mod_kernel<S, false, true>;
     e.txc_fn = (const void*)&fused_mod_kernel<S, true, true>;
-    e.rxd_fn = (const void*)&fused_rx_kernel<S, false, true>;
+    e.rxd_fn = (const void*)&fused_rx_kernel<S, false, true, false>;
+    e.rxd_eq_fn = (const void*)&fused_rx_kernel<S, false, true, true>;
     e.modc_name = std::string(mn) + "+chunks";
     e.txc_name = std::string(tn) + "+chunks";
     e.rxd_name = std::string(rn) + "+decide";
     if constexpr (sic_shape_ok<S>()) {
         e.sic = &launch_sic<S>;
-        e.sic_fn = (const void*)&fused_rx_kernel<typename SicShape<S>::type, true>;
+        e.sic_fn = (const void*)&fused_rx_kernel<typename SicShape<S>::type, true, false, false>;
+        e.sic_eq_fn = (const void*)&fused_rx_kernel<typename SicShape<S>::type, true, false, true>;
         e.sic_smem = SicShape<S>::type::SMEM_BYTES;
     }
     return e;

@@ -163,6 +163,7 @@ void FusedModem::init_rx(int M, int K, int L, const std::vector<std::complex<flo
     p->eq_ok = L * M <= 64;
     try {
         p->rx_grid_cap = fused_grid_cap(e->rx_fn, e->T, e->smem);
+        fused_grid_cap(e->rx_eq_fn, e->T, e->smem); // opts the equalising kernel into its shared-memory size as well
         p->d_table = upload(make_fold_table(M, K, L, taps, -1, true));
         p->d_table_eq = upload(make_fold_table(M, K, L, taps, -1, false));
         p->d_tw = upload(make_row_twiddles(e->R1, e->R2));
@@ -282,7 +283,10 @@ int FusedModem::demodulate_decide(unsigned char* chunks_out, const cpx* in, cons
                                   int rule, const DecideGrid& dgrid, size_t frames, cudaStream_t s)
 {
     const ShapeEntry* e = impl_->e;
-    if (!impl_->rxd_grid_cap) impl_->rxd_grid_cap = fused_grid_cap(e->rxd_fn, e->T, e->smem);
+    if (!impl_->rxd_grid_cap) {
+        impl_->rxd_grid_cap = fused_grid_cap(e->rxd_fn, e->T, e->smem);
+        fused_grid_cap(e->rxd_eq_fn, e->T, e->smem);
+    }
     int launches = 0;
     const size_t N = (size_t)e->M * e->K, max_chunk = (size_t)1 << 20;
     SicArgs a{};
@@ -348,6 +352,7 @@ bool FusedModem::init_sic(const std::vector<std::complex<float>>& ic_taps,
         ++count[k];
     }
     impl_->sic_grid_cap = fused_grid_cap(e->sic_fn, e->T, e->sic_smem ? e->sic_smem : e->smem);
+    fused_grid_cap(e->sic_eq_fn, e->T, e->sic_smem ? e->sic_smem : e->smem);
     impl_->d_ic = upload(to_cpx(ic_taps));
     impl_->d_points = upload(to_cpx(points));
     impl_->d_count = upload(count);

@@ -44,6 +44,10 @@ struct ShapeEntry {
     const void* mod_fn;
     const void* rx_fn;
     const void* sic_fn;
+    // the equalising variants are kernels of their own (same launch geometry and shared memory)
+    const void* rx_eq_fn = nullptr;
+    const void* rxd_eq_fn = nullptr;
+    const void* sic_eq_fn = nullptr;
     const char* sic_name;
     size_t sic_smem = 0; // shared memory of the cancellation variant (a companion shape when IPT > 1)
     // chunk entries: modulator / transmitter chain with byte input, receiver with hard-decision output

@@ -16,7 +16,7 @@ import bench  # noqa: E402
 
 w = dict(bench.WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else 'c3'])
 frames = int(sys.argv[2]) if len(sys.argv) > 2 else w['frames']
-lib = capi.load(os.path.join(ROOT, 'gr-gfdm_b200', 'lib', 'libgfdm_b200_prof.so'))
+lib = capi.load(os.environ.get('GFDM_PROF_LIB') or os.path.join(ROOT, 'gr-gfdm_b200', 'lib', 'libgfdm_b200_prof.so'))
 twopass = w['K'] == 2048
 dbg = lib.dll.gfdm_debug_stage_cycles2 if twopass else lib.dll.gfdm_debug_stage_cycles
 dbg.argtypes = [ctypes.c_void_p, ctypes.c_int]
@@ -28,7 +28,8 @@ d_tx = torch.empty_like(d_in)
 d_out = torch.empty_like(d_in)
 eq = torch.ones_like(d_in)
 names = {0: 'mod: wait bulk load', 1: 'mod: A read staging', 2: 'mod: A fft+row write', 3: 'mod: row fft (warp0)',
-         4: 'mod: barrier after rows', 5: 'mod: C read columns', 6: 'mod: C table+ifft+store',
+         4: 'mod: barrier after rows', 7: 'mod: C read columns', 8: 'mod: barrier behind the reads', 5: 'mod: tail load issue',
+         6: 'mod: C table+ifft+store',
          15: 'rx: loop top/store issue', 16: 'rx: wait bulk load', 17: "rx: A' read staging", 18: "rx: A' fft+table+wait store", 19: 'rx: row write',
          20: 'rx: row fft (warp0)', 21: 'rx: barrier after rows', 22: "rx: C' read columns", 23: "rx: C' ifft+staging"}
 
