@@ -107,11 +107,6 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_mod_kernel(cpx* __restric
     }
     __syncthreads();
 
-    // The plain modulator never stages the tail of a group that does not fit region P: the threads whose records lie behind
-    // PF read them straight from global memory (pulled into L2 when the head is issued), ahead of their shared-memory
-    // reads.  A second bulk copy per group costs its issuing thread ~1400 cycles while the head copy is still in flight
-    // (stage profile r02h: "tail load issue" 1441 of 14.7k cycles per frame at C3), and every warp waits for that thread.
-    constexpr bool REG_TAIL = !TXF && !CHK && PF < F * N;
     // issue the bulk loads of group gg: head -> P, tail -> R
     auto load_head = [&](int gg) {
         const int el = min(F, n_frames - gg * F) * EL;
@@ -129,7 +124,7 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_mod_kernel(cpx* __restric
         if (el > PF) bulk_prefetch_l2(in + (size_t)gg * F * EL + PF, (uint32_t)(el - PF) * sizeof(cpx));
     };
     auto load_tail = [&](int gg) {
-        if constexpr (CHK || REG_TAIL) return;
+        if constexpr (CHK) return;
         const int el = min(F, n_frames - gg * F) * EL;
         const uint32_t bytes = (uint32_t)max(el - PF, 0) * sizeof(cpx);
         mbar_expect_tx(bar_r, bytes);
@@ -167,8 +162,8 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_mod_kernel(cpx* __restric
         // the tail of the staged group (region R) is only read by the items whose records lie behind PF: the plain
         // modulator waits for it right before the first of those (the transmitter's gather may touch it anywhere)
         constexpr int J_TAIL = PF / (T * M); // first item with a record at or behind PF
-        constexpr bool LATE_TAIL = !REG_TAIL && !TXF && !CHK && PF < F * N && J_TAIL >= 1 && J_TAIL < IPT;
-        if (!CHK && !REG_TAIL && !LATE_TAIL && PF < F * N) mbar_wait(bar_r, phase);
+        constexpr bool LATE_TAIL = !TXF && !CHK && PF < F * N && J_TAIL >= 1 && J_TAIL < IPT;
+        if (!CHK && !LATE_TAIL && PF < F * N) mbar_wait(bar_r, phase);
         STAGE_MARK(0) // wait for the bulk loads
 
         cpx v[IPT][M];
@@ -179,25 +174,6 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_mod_kernel(cpx* __restric
                 const unsigned char* src = pre_b + (tid + j * T) * M;
 #pragma unroll
                 for (int m = 0; m < M; ++m) v[j][m] = lookup(src[m]);
-            }
-        } else if constexpr (!TXF && REG_TAIL) {
-            // records behind PF first (global loads in flight while the others are read from shared memory)
-            const cpx* gin = in + (size_t)g * F * N;
-#pragma unroll
-            for (int j = IPT - 1; j >= 0; --j) {
-                const int e = (tid + j * T) * M; // (f*K + k)*M
-                if (e >= PF) {
-#pragma unroll
-                    for (int m = 0; m < M; ++m) v[j][m] = e < fh * N ? ldg_stream(gin + e + m) : cmake(0.f, 0.f);
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < IPT; ++j) {
-                const int e = (tid + j * T) * M;
-                if (e < PF) {
-#pragma unroll
-                    for (int m = 0; m < M; ++m) v[j][m] = pre[e + m];
-                }
             }
         } else if constexpr (!TXF) {
 #pragma unroll
@@ -273,13 +249,14 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_mod_kernel(cpx* __restric
         STAGE_MARK(7) // stage C reads (own loads issued)
         __syncthreads(); // R is dead: fetch the tail of the next group while stage C computes and stores
         STAGE_MARK(8) // barrier behind the column reads
-        if constexpr (!REG_TAIL) {
-            if (tid == 0 && gn < n_groups) {
-                fence_proxy_async();
-                load_tail(gn);
-            }
+        // (this second bulk copy of the group costs thread 0 ~1400 cycles while the head copy is still in flight -- stage
+        // profile r02h -- and every warp waits for it at the next barrier; reading the tail records straight from global
+        // memory instead was measured slower, experiments/README.md)
+        if (tid == 0 && gn < n_groups) {
+            fence_proxy_async();
+            load_tail(gn);
         }
-        STAGE_MARK(5) // issue of the tail load (transmitter chain / shapes whose group fits region P: none)
+        STAGE_MARK(5) // issue of the tail load
 #pragma unroll
         for (int j = 0; j < IPT; ++j) {
             const int it = tid + j * T;
