@@ -42,16 +42,6 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint
                  "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
-// Ampere-style asynchronous 16-byte copies (LSU path, no TMA descriptor queue) whose completion is reported to an mbarrier:
-// every thread issues its copies and then arrives; the arrival fires when that thread's copies have landed.
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc)
-{
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_mbar_arrive(uint64_t* bar) // counts as one of the barrier's expected arrivals
-{
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 // L2 eviction policies (createpolicy): evict_last keeps data that is read again soon (second pass of the
 // two-pass kernels, their per-CTA scratch), evict_first marks data that is dead after this access
 __device__ __forceinline__ uint64_t l2_policy_evict_last()

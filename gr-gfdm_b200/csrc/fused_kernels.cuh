@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_mod_kernel(cpx* __restric
     for (int i = tid; i < S::TBL_ELEMS; i += T) tbl_s[i] = table[i];
     if (tid == 0) {
         mbar_init(bar_p, 1);
-        mbar_init(bar_r, T); // every thread arrives once per group (load_tail)
+        mbar_init(bar_r, 1);
     }
     // table columns of this thread -> tensor memory (once per CTA)
     uint32_t tmem_base = 0, tmem_mine = 0;
@@ -123,16 +123,12 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_mod_kernel(cpx* __restric
         // now so that the later bulk load is an L2 hit
         if (el > PF) bulk_prefetch_l2(in + (size_t)gg * F * EL + PF, (uint32_t)(el - PF) * sizeof(cpx));
     };
-    // The tail does not travel by a second bulk copy: issuing one while the head copy is still in flight costs its thread
-    // ~1400 cycles (stage profile r02h, "tail load issue") and every warp waits for that thread at the next barrier.  ALL
-    // threads copy it instead, 16 bytes at a time through the LSU (cp.async), and report to the same mbarrier (T arrivals).
     auto load_tail = [&](int gg) {
         if constexpr (CHK) return;
         const int el = min(F, n_frames - gg * F) * EL;
-        const int units = max(el - PF, 0) / 2; // 16-byte units (PF and el are even)
-        const cpx* src = in + (size_t)gg * F * EL + PF;
-        for (int u = tid; u < units; u += T) cp_async16(buf + 2 * u, src + 2 * u);
-        cp_async_mbar_arrive(bar_r);
+        const uint32_t bytes = (uint32_t)max(el - PF, 0) * sizeof(cpx);
+        mbar_expect_tx(bar_r, bytes);
+        if (bytes) bulk_load(buf, in + (size_t)gg * F * EL + PF, bytes, bar_r);
     };
     // transmitter: position of this thread's subcarrier(s) in the sorted subcarrier map (-1: unused)
     // The gather of stage A is loop invariant: staged index of timeslot 0, stride over timeslots, and how many
@@ -153,8 +149,8 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_mod_kernel(cpx* __restric
     }
 
     int g = blockIdx.x;
-    if (g < n_groups) {
-        if (tid == 0) load_head(g);
+    if (tid == 0 && g < n_groups) {
+        load_head(g);
         load_tail(g);
     }
     uint32_t phase = 0;
@@ -253,7 +249,13 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_mod_kernel(cpx* __restric
         STAGE_MARK(7) // stage C reads (own loads issued)
         __syncthreads(); // R is dead: fetch the tail of the next group while stage C computes and stores
         STAGE_MARK(8) // barrier behind the column reads
-        if (gn < n_groups) load_tail(gn);
+        // (this second bulk copy of the group costs thread 0 ~1400 cycles while the head copy is still in flight -- stage
+        // profile r02h -- and every warp waits for it at the next barrier; reading the tail records straight from global
+        // memory instead was measured slower, experiments/README.md)
+        if (tid == 0 && gn < n_groups) {
+            fence_proxy_async();
+            load_tail(gn);
+        }
         STAGE_MARK(5) // issue of the tail load
 #pragma unroll
         for (int j = 0; j < IPT; ++j) {
