@@ -432,6 +432,11 @@ static void modulator_run(gfdm_modulator* h, cpx* out, const cpx* in, size_t fra
     }
     if (h->fft_m.n == 0) h->fft_m.init(h->M);
     if (h->fft_n.n == 0) h->fft_n.init(h->N);
+    if (generic_smem_supported(h->M, h->K, h->fft_m, h->fft_n)) { // frame resident in shared memory: one kernel, 16 N bytes
+        h->launches += launch_generic_smem_mod(out, in, h->M, h->K, h->L, h->fft_m, h->fft_n, h->d_taps, frames, h->stream);
+        h->last_kernel = "generic_smem_mod_kernel";
+        return;
+    }
     const size_t el = frames * (size_t)h->N;
     h->work_a.ensure(el * sizeof(cpx));
     h->work_b.ensure(el * sizeof(cpx));
@@ -543,6 +548,11 @@ static void receiver_fd(gfdm_receiver* h, cpx* R, const cpx* in, const cpx* eq, 
         return;
     }
     if (h->fft_n.n == 0) h->fft_n.init(h->N);
+    if (generic_smem_supported(h->M, h->K, h->fft_m, h->fft_n)) {
+        h->launches += launch_generic_smem_rx(R, in, eq, 1, h->M, h->K, h->L, h->fft_m, h->fft_n, h->d_taps, frames, h->stream);
+        h->last_kernel = "generic_smem_rx_kernel";
+        return;
+    }
     const size_t el = frames * (size_t)h->N;
     h->work_a.ensure(el * sizeof(cpx));
     h->work_b.ensure(el * sizeof(cpx));
@@ -585,6 +595,12 @@ static void receiver_run(gfdm_receiver* h, cpx* out, const cpx* in, const cpx* e
     if (h->fused.available() && (!eq || h->fused.supports_eq()) && aligned16(out) && aligned16(in) && aligned16(eq)) {
         h->launches += h->fused.demodulate(out, nullptr, in, eq, frames, h->stream);
         h->last_kernel = h->fused.rx_name();
+        return;
+    }
+    if (h->fft_n.n == 0) h->fft_n.init(h->N);
+    if (generic_smem_supported(h->M, h->K, h->fft_m, h->fft_n)) {
+        h->launches += launch_generic_smem_rx(out, in, eq, 0, h->M, h->K, h->L, h->fft_m, h->fft_n, h->d_taps, frames, h->stream);
+        h->last_kernel = "generic_smem_rx_kernel";
         return;
     }
     const size_t el = frames * (size_t)h->N;
@@ -1378,6 +1394,10 @@ static void tx_modulate(gfdm_transmitter* h, cpx* blk, const cpx* in, size_t nin
     }
     if (h->fft_m.n == 0) h->fft_m.init(h->M);
     if (h->fft_n.n == 0) h->fft_n.init(h->N);
+    if (generic_smem_supported(h->M, h->K, h->fft_m, h->fft_n)) {
+        h->launches += launch_generic_smem_mod(blk, mp, h->M, h->K, h->L, h->fft_m, h->fft_n, h->d_taps, frames, h->stream);
+        return;
+    }
     h->work_a.ensure(el * sizeof(cpx));
     h->work_b.ensure(el * sizeof(cpx));
     cpx* A = h->work_a.as<cpx>();

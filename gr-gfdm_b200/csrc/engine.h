@@ -20,6 +20,16 @@ struct FftPlan {
 int fft_exec(const FftPlan& p, cpx* out, const cpx* in, cpx* scratch, size_t batch, bool inverse,
              float scale, cudaStream_t s);
 
+// ---------------------------------------------------------------- generic_smem.cu
+// Any-shape modulator / receiver with the frame resident in shared memory (N <= 12288): one kernel per batch, 16 N bytes
+// of HBM traffic per frame (24 N with a per-frame channel).  For the shapes that have no fused kernel.
+bool generic_smem_supported(int M, int K, const FftPlan& fft_m, const FftPlan& fft_n);
+int launch_generic_smem_mod(cpx* out, const cpx* in, int M, int K, int L, const FftPlan& fft_m, const FftPlan& fft_n,
+                            const cpx* d_taps, size_t frames, cudaStream_t s);
+// mode 0: soft symbols (generic_work[_equalize]), mode 1: R (fft_[equalize_]filter_downsample); eq may be null
+int launch_generic_smem_rx(cpx* out, const cpx* in, const cpx* eq, int mode, int M, int K, int L, const FftPlan& fft_m,
+                           const FftPlan& fft_n, const cpx* d_taps, size_t frames, cudaStream_t s);
+
 // ---------------------------------------------------------------- stage_kernels.cu
 // modulator: X[b*M+m] = sum_i T[((i+h)%L)*M+m] * D[((b-i+h) mod K)*M+m], m < part_len
 void launch_mod_filter(cpx* X, const cpx* D, const cpx* taps, int M, int K, int L, size_t frames, cudaStream_t s);

@@ -197,8 +197,33 @@ def next_rows(M, K, frames):
                16 * burst, eb.last_kernel())
 
 
+def shape_rows():
+    """modulate -> demodulate on shapes beyond the BASELINE ones: entries of the open fused-shape table (the reference's own
+    test shapes M=21/K=128, M=9/K=32, ...) and shapes outside it, which run the frame-resident generic kernels."""
+    rng = np.random.default_rng(19)
+    for M, K, L in ((21, 128, 2), (9, 32, 2), (15, 128, 2), (9, 512, 2), (15, 512, 2), (5, 1024, 2), (21, 512, 2), (7, 256, 2),
+                    (25, 96, 2), (127, 16, 4), (15, 96, 2)):
+        N = M * K
+        frames = max(256, (1 << 26) // N)       # ~0.5 GB per buffer: larger than L2
+        taps = design.get_frequency_domain_filter('rrc', 0.5, M, K, L)
+        mod = capi.Modulator(M, K, L, taps, lib=lib)
+        rx = capi.Demodulator(M, K, L, np.conj(taps), lib=lib)
+        mod.set_stream(stream.cuda_stream)
+        rx.set_stream(stream.cuda_stream)
+        d_s = torch.from_numpy(crand(rng, frames, N)).cuda()
+        d_x = torch.empty_like(d_s)
+        d_y = torch.empty_like(d_s)
+        ms = timed(lambda: mod.modulate_ptr(d_x.data_ptr(), d_s.data_ptr(), frames))
+        report('modulator_kernel_cc::generic_work', 'K=%d M=%d L=%d' % (K, M, L), frames, ms, 16 * N, mod.last_kernel())
+        ms = timed(lambda: rx.demodulate_ptr(d_y.data_ptr(), d_x.data_ptr(), 0, frames))
+        report('receiver_kernel_cc::generic_work', 'K=%d M=%d L=%d' % (K, M, L), frames, ms, 16 * N, rx.last_kernel())
+        del d_s, d_x, d_y
+
+
 if __name__ == '__main__':
     what = sys.argv[1:] or ['tx']
+    if 'shapes' in what:
+        shape_rows()
     if 'tx' in what:
         tx_chain(9, 64, 52, 16, 8, 1 << 16)            # BASELINE configs[1]
         tx_chain(15, 1024, 832, 64, 32, 4096)           # headline shape with CP
