@@ -25,20 +25,29 @@ struct GenArgs {
     const cpx* taps; // L*M, normalised
 };
 
-// one Stockham pass of radix p over `batch` contiguous transforms of length n (fft_engine.cu: stockham_pass)
-template <bool INV>
+// floor(a / d) for 0 <= a < 2^20, 1 <= d < 2^20 without an integer division (~25 instructions): (a + 0.5) / d is never
+// closer than 0.5 / d >= 4.7e-7 (relative: >= 2^-20 / quotient ... far above fp32 rounding of one multiply) to an integer
+__device__ __forceinline__ int fdiv(int a, float inv_d) { return __float2int_rd(((float)a + 0.5f) * inv_d); }
+
+// one Stockham pass of radix p over `batch` contiguous transforms of length n (fft_engine.cu: stockham_pass); P > 0: the
+// radix as a compile-time constant (unrolled multiply-add chain), P = 0: any radix
+template <bool INV, int P>
 __device__ __forceinline__ void smem_pass(cpx* __restrict__ out, const cpx* __restrict__ in, const cpx* __restrict__ tw, int n,
-                                          int p, int Ns, int total, int tid)
+                                          int p_rt, int Ns, int total, int tid)
 {
+    const int p = P > 0 ? P : p_rt;
     const int span = Ns * p, stride = n / p, step = n / span;
+    const float inv_n = 1.0f / (float)n, inv_span = 1.0f / (float)span, inv_ns = 1.0f / (float)Ns;
+    const bool one = total == n;
     for (int gid = tid; gid < total; gid += GT) {
-        const int b = gid / n, o = gid - b * n;
-        const int q = o / span, rem = o - q * span;
-        const int t = rem / Ns, k = rem - t * Ns;
+        const int b = one ? 0 : fdiv(gid, inv_n), o = gid - b * n;
+        const int q = fdiv(o, inv_span), rem = o - q * span;
+        const int t = Ns == 1 ? rem : fdiv(rem, inv_ns), k = rem - t * Ns;
         const int e = (k + t * Ns) * step; // < n
         const cpx* x = in + b * n + q * Ns + k;
         cpx acc = x[0];
         int idx = 0;
+#pragma unroll
         for (int r = 1; r < p; ++r) {
             idx += e;
             if (idx >= n) idx -= n;
@@ -49,13 +58,24 @@ __device__ __forceinline__ void smem_pass(cpx* __restrict__ out, const cpx* __re
         out[gid] = acc;
     }
 }
+template <bool INV>
+__device__ __forceinline__ void smem_pass_any(cpx* out, const cpx* in, const cpx* tw, int n, int p, int Ns, int total, int tid)
+{
+    switch (p) {
+    case 2: smem_pass<INV, 2>(out, in, tw, n, p, Ns, total, tid); break;
+    case 3: smem_pass<INV, 3>(out, in, tw, n, p, Ns, total, tid); break;
+    case 4: smem_pass<INV, 4>(out, in, tw, n, p, Ns, total, tid); break;
+    case 5: smem_pass<INV, 5>(out, in, tw, n, p, Ns, total, tid); break;
+    default: smem_pass<INV, 0>(out, in, tw, n, p, Ns, total, tid); break;
+    }
+}
 // whole transform between the two buffers; returns the buffer that holds the result
 template <bool INV>
 __device__ __forceinline__ cpx* smem_fft(cpx* src, cpx* dst, const cpx* tw, int n, const int* rad, int n_rad, int batch, int tid)
 {
     int Ns = 1;
     for (int i = 0; i < n_rad; ++i) {
-        smem_pass<INV>(dst, src, tw, n, rad[i], Ns, batch * n, tid);
+        smem_pass_any<INV>(dst, src, tw, n, rad[i], Ns, batch * n, tid);
         __syncthreads();
         Ns *= rad[i];
         cpx* t = src;
@@ -80,15 +100,20 @@ __global__ void __launch_bounds__(GT) generic_smem_mod_kernel(cpx* __restrict__ 
         __syncthreads();
         cpx* D = smem_fft<false>(A, B, a.tw_m, M, a.rad_m, a.n_rad_m, K, tid); // D_k = FFT_M(d_k), [k][m]
         cpx* X = D == A ? B : A;
+        const float inv_mf = 1.0f / (float)M;
         for (int r = tid; r < N; r += GT) {
-            const int b = r / M, m = r - b * M;
+            const int b = fdiv(r, inv_mf), m = r - b * M;
             cpx acc = cmake(0.f, 0.f);
             if (m < part_len) {
                 // the same accumulation order as the reference's k-loop produces for this bin (:113-135)
+                int k = b + h, tp = (L - 1 + h) % L; // i = L-1 first: k = (b - i + h) mod K, tap block (i + h) mod L
+                k -= L - 1;
+                k %= K;
+                if (k < 0) k += K;
                 for (int i = L - 1; i >= 0; --i) {
-                    int k = (b - i + h) % K;
-                    if (k < 0) k += K;
-                    acc = cadd(acc, cmul(D[k * M + m], __ldg(reinterpret_cast<const float2*>(a.taps) + ((i + h) % L) * M + m)));
+                    acc = cadd(acc, cmul(D[k * M + m], __ldg(reinterpret_cast<const float2*>(a.taps) + tp * M + m)));
+                    k = k + 1 == K ? 0 : k + 1;
+                    tp = tp == 0 ? L - 1 : tp - 1;
                 }
             }
             X[r] = acc;
@@ -122,12 +147,15 @@ __global__ void __launch_bounds__(GT) generic_smem_rx_kernel(cpx* __restrict__ o
             __syncthreads();
         }
         cpx* R = Y == A ? B : A;
+        const float inv_mf = 1.0f / (float)M;
         for (int r = tid; r < N; r += GT) { // filter_subcarriers_and_downsample_fd (:165-192)
-            const int k = r / M, m = r - k * M;
+            const int k = fdiv(r, inv_mf), m = r - k * M;
             cpx acc = cmake(0.f, 0.f);
+            int kk = (k + K - h % K) % K, tp = h % L; // i = 0: subcarrier (k - h) mod K, tap block h mod L
             for (int i = 0; i < L; ++i) {
-                const int src = ((k + i + K - h) % K) * M;
-                acc = cadd(acc, cmul(__ldg(reinterpret_cast<const float2*>(a.taps) + ((i + h) % L) * M + m), Y[src + m]));
+                acc = cadd(acc, cmul(__ldg(reinterpret_cast<const float2*>(a.taps) + tp * M + m), Y[kk * M + m]));
+                kk = kk + 1 == K ? 0 : kk + 1;
+                tp = tp + 1 == L ? 0 : tp + 1;
             }
             R[r] = acc;
         }
