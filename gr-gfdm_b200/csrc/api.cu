@@ -432,7 +432,7 @@ static void modulator_run(gfdm_modulator* h, cpx* out, const cpx* in, size_t fra
     }
     if (h->fft_m.n == 0) h->fft_m.init(h->M);
     if (h->fft_n.n == 0) h->fft_n.init(h->N);
-    if (generic_smem_supported(h->M, h->K, h->fft_m, h->fft_n)) { // frame resident in shared memory: one kernel, 16 N bytes
+    if (generic_smem_supported(h->M, h->K, h->L, h->fft_m, h->fft_n)) { // frame resident in shared memory: one kernel, 16 N bytes
         h->launches += launch_generic_smem_mod(out, in, h->M, h->K, h->L, h->fft_m, h->fft_n, h->d_taps, frames, h->stream);
         h->last_kernel = "generic_smem_mod_kernel";
         return;
@@ -548,7 +548,7 @@ static void receiver_fd(gfdm_receiver* h, cpx* R, const cpx* in, const cpx* eq, 
         return;
     }
     if (h->fft_n.n == 0) h->fft_n.init(h->N);
-    if (generic_smem_supported(h->M, h->K, h->fft_m, h->fft_n)) {
+    if (generic_smem_supported(h->M, h->K, h->L, h->fft_m, h->fft_n)) {
         h->launches += launch_generic_smem_rx(R, in, eq, 1, h->M, h->K, h->L, h->fft_m, h->fft_n, h->d_taps, frames, h->stream);
         h->last_kernel = "generic_smem_rx_kernel";
         return;
@@ -598,7 +598,7 @@ static void receiver_run(gfdm_receiver* h, cpx* out, const cpx* in, const cpx* e
         return;
     }
     if (h->fft_n.n == 0) h->fft_n.init(h->N);
-    if (generic_smem_supported(h->M, h->K, h->fft_m, h->fft_n)) {
+    if (generic_smem_supported(h->M, h->K, h->L, h->fft_m, h->fft_n)) {
         h->launches += launch_generic_smem_rx(out, in, eq, 0, h->M, h->K, h->L, h->fft_m, h->fft_n, h->d_taps, frames, h->stream);
         h->last_kernel = "generic_smem_rx_kernel";
         return;
@@ -1394,7 +1394,7 @@ static void tx_modulate(gfdm_transmitter* h, cpx* blk, const cpx* in, size_t nin
     }
     if (h->fft_m.n == 0) h->fft_m.init(h->M);
     if (h->fft_n.n == 0) h->fft_n.init(h->N);
-    if (generic_smem_supported(h->M, h->K, h->fft_m, h->fft_n)) {
+    if (generic_smem_supported(h->M, h->K, h->L, h->fft_m, h->fft_n)) {
         h->launches += launch_generic_smem_mod(blk, mp, h->M, h->K, h->L, h->fft_m, h->fft_n, h->d_taps, frames, h->stream);
         return;
     }

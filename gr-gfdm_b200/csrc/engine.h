@@ -23,7 +23,7 @@ int fft_exec(const FftPlan& p, cpx* out, const cpx* in, cpx* scratch, size_t bat
 // ---------------------------------------------------------------- generic_smem.cu
 // Any-shape modulator / receiver with the frame resident in shared memory (N <= 12288): one kernel per batch, 16 N bytes
 // of HBM traffic per frame (24 N with a per-frame channel).  For the shapes that have no fused kernel.
-bool generic_smem_supported(int M, int K, const FftPlan& fft_m, const FftPlan& fft_n);
+bool generic_smem_supported(int M, int K, int L, const FftPlan& fft_m, const FftPlan& fft_n);
 int launch_generic_smem_mod(cpx* out, const cpx* in, int M, int K, int L, const FftPlan& fft_m, const FftPlan& fft_n,
                             const cpx* d_taps, size_t frames, cudaStream_t s);
 // mode 0: soft symbols (generic_work[_equalize]), mode 1: R (fft_[equalize_]filter_downsample); eq may be null

@@ -32,6 +32,7 @@
 #include <cmath>
 #include <cstring>
 #include <string>
+#include <type_traits>
 
 namespace gfdm {
 
@@ -286,17 +287,23 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_mod_kernel(cpx* __restric
                 const int lo = max(tx.ramp, dup), hi = max(lo, min(N, W - tx.ramp));
                 const bool shaped = tx.shaped != 0;
                 const cpx scale = cmake(tx.sc_re, tx.sc_im);
-                for (int a = 0; a < tx.n_ant; ++a) {
-                    cpx* o = out + (size_t)a * tx.ant_stride + ((size_t)g * F + f) * os + tx.pre_pad + tx.P;
-                    int i = (n1 + tx.cp + tx.shift[a]) % N;
+                // two copies of the store loop: the burst shaper's scaling must not cost the plain chain a select per store
+                auto store_all = [&](auto SH) {
+                    constexpr bool sh = decltype(SH)::value;
+                    for (int a = 0; a < tx.n_ant; ++a) {
+                        cpx* o = out + (size_t)a * tx.ant_stride + ((size_t)g * F + f) * os + tx.pre_pad + tx.P;
+                        int i = (n1 + tx.cp + tx.shift[a]) % N;
 #pragma unroll
-                    for (int n2 = 0; n2 < M; ++n2) {
-                        if ((unsigned)(i - lo) < (unsigned)(hi - lo)) stg_stream(o + i, shaped ? cmul_rn(v[j][n2], scale) : v[j][n2]);
-                        else tx_store_edge(o, i, v[j][n2], N, W, tx.ramp, tx.front, tx.back, shaped, scale);
-                        i += K;
-                        i = (int)min((unsigned)i, (unsigned)(i - N)); // wrap at N without a branch (i < 2N)
+                        for (int n2 = 0; n2 < M; ++n2) {
+                            if ((unsigned)(i - lo) < (unsigned)(hi - lo)) stg_stream(o + i, sh ? cmul_rn(v[j][n2], scale) : v[j][n2]);
+                            else tx_store_edge(o, i, v[j][n2], N, W, tx.ramp, tx.front, tx.back, sh, scale);
+                            i += K;
+                            i = (int)min((unsigned)i, (unsigned)(i - N)); // wrap at N without a branch (i < 2N)
+                        }
                     }
-                }
+                };
+                if (shaped) store_all(std::true_type{});
+                else store_all(std::false_type{});
             }
         }
         if constexpr (TXF) {

@@ -202,7 +202,7 @@ def shape_rows():
     test shapes M=21/K=128, M=9/K=32, ...) and shapes outside it, which run the frame-resident generic kernels."""
     rng = np.random.default_rng(19)
     for M, K, L in ((21, 128, 2), (9, 32, 2), (15, 128, 2), (9, 512, 2), (15, 512, 2), (5, 1024, 2), (21, 512, 2), (7, 256, 2),
-                    (25, 96, 2), (127, 16, 4), (15, 96, 2)):
+                    (25, 96, 2), (127, 16, 4), (15, 96, 2), (16, 96, 2), (11, 416, 2), (13, 840, 2)):
         N = M * K
         frames = max(256, (1 << 26) // N)       # ~0.5 GB per buffer: larger than L2
         taps = design.get_frequency_domain_filter('rrc', 0.5, M, K, L)
