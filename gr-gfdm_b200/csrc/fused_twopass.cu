@@ -31,6 +31,7 @@
 #include "fused_dev.cuh"
 
 #include <cmath>
+#include <cstdlib>
 #include <string>
 
 namespace gfdm {
@@ -279,6 +280,252 @@ __global__ void __launch_bounds__(S::T, 1) fused_mod2_kernel(cpx* __restrict__ o
 }
 
 // ----------------------------------------------------------------------------------------
+// Tensor memory as a per-thread PARKING area (the two-pass modulator below): 4 sets of 2M columns per thread, nothing
+// stored at allocation.  Same addressing as Tmem4.
+template <class S>
+struct TmemPark {
+    static constexpr int SET = 2 * S::M;
+    static constexpr int PER_THREAD = 4 * SET;
+    static constexpr int COLS = 512;
+    static_assert(((S::T / 32 + 3) / 4) * PER_THREAD <= COLS, "parked sets do not fit in tensor memory");
+    static __device__ __forceinline__ void alloc(uint32_t* slot, int tid, uint32_t& base, uint32_t& mine)
+    {
+        if (tid < 32) tmem_alloc(slot, COLS);
+        tmem_fence_before_sync();
+        __syncthreads();
+        tmem_fence_after_sync();
+        base = *slot;
+        mine = base + ((uint32_t)(((tid >> 5) & 3) * 32) << 16) + (uint32_t)(tid >> 7) * PER_THREAD;
+    }
+    static __device__ __forceinline__ void st(uint32_t mine, int set, const cpx (&v)[S::M])
+    {
+        float tf[SET];
+#pragma unroll
+        for (int m = 0; m < S::M; ++m) {
+            tf[2 * m] = v[m].x;
+            tf[2 * m + 1] = v[m].y;
+        }
+        tmem_st<SET>(mine + set * SET, tf);
+        tmem_wait_st();
+    }
+    static __device__ __forceinline__ void ld(cpx (&v)[S::M], uint32_t mine, int set)
+    {
+        float tf[SET];
+        tmem_ld<SET>(tf, mine + set * SET);
+        tmem_wait_ld();
+#pragma unroll
+        for (int m = 0; m < S::M; ++m) v[m] = cmake(tf[2 * m], tf[2 * m + 1]);
+    }
+    static __device__ __forceinline__ void release(uint32_t base, int tid)
+    {
+        tmem_fence_before_sync();
+        __syncthreads();
+        if (tid < 32) tmem_dealloc(base, COLS);
+    }
+};
+
+// ----------------------------------------------------------------------------------------
+// modulator, second version: the frame is read ONCE and nothing goes through an L2 scratch.  Everything a thread has to
+// carry from pass 0 to pass 1 is its own: the M-point transforms of the odd-parity inputs E^1_b' of its two subcarrier
+// pairs (stage A computes both parities from one read of the symbols) and the even samples of its two output columns
+// (pass 1 writes 16-byte sample pairs).  Both wait in tensor memory (4 x 2M = 120 of the 128 columns a thread can have
+// at T = 512), so pass 1 has no loads, no M-point input transforms and no L2 round trip; the table columns, which used to
+// occupy the tensor memory, are read from L2 (coalesced, issued before the column reads that hide their latency).
+// Staging as in fused_mod2_kernel, but each region is filled once per frame: P (LO0 + head of HI1, then the late part
+// of HI1) is free again after stage A and takes the NEXT frame at once; buf (LO1|HI0) is refilled when pass 1 has read
+// its columns.
+template <class S>
+__global__ void __launch_bounds__(S::T, 1) fused_mod2p_kernel(cpx* __restrict__ out, const cpx* __restrict__ in,
+                                                             const cpx* __restrict__ tableP, const cpx* __restrict__ tw,
+                                                             const cpx* __restrict__ w2, int n_frames)
+{
+    constexpr int M = S::M, K1 = S::K, K = 2 * K1, N = M * K, T = S::T, RS = S::RS;
+    static_assert(S::F == 1 && S::IPT == 2 && S::TWO_PASS, "two-pass kernels: one half-frame per CTA pass, two items per thread");
+    constexpr int PIECE = T * M;
+    constexpr int HA = ((S::P_ELEMS - PIECE) / (2 * M)) * (2 * M);
+    constexpr int HB = PIECE - HA;
+    static_assert(HA > 0 && HB > 0 && HB <= PIECE && 2 * PIECE <= S::BUF_ELEMS, "staging does not fit");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    cpx* buf = reinterpret_cast<cpx*>(smem_raw);
+    cpx* tw_s = buf + S::BUF_ELEMS;
+    cpx* pre = tw_s + S::TW_ELEMS + S::TBL_ELEMS;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(pre + S::P_ELEMS + S::TAPS_ELEMS);
+    uint64_t* bar_p = bars;     // LO0 + head of HI1 (region P)
+    uint64_t* bar_r = bars + 1; // LO1 | HI0 (region buf)
+    uint64_t* bar_l = bars + 2; // late part of HI1
+    const int tid = threadIdx.x;
+
+    for (int i = tid; i < S::TW_ELEMS; i += T) tw_s[i] = tw[i];
+    if (tid == 0) {
+        mbar_init(bar_p, 1);
+        mbar_init(bar_r, 1);
+        mbar_init(bar_l, 1);
+    }
+    const cpx wj0 = w2[tid], wj1 = w2[tid + T];
+    uint32_t tmem_base = 0, tmem_mine = 0;
+    TmemPark<S>::alloc(reinterpret_cast<uint32_t*>(bars + 3), tid, tmem_base, tmem_mine);
+    __syncthreads();
+
+    auto load_p = [&](int g) {
+        const cpx* f = in + (size_t)g * N;
+        const uint64_t pol = l2_policy_evict_first();
+        mbar_expect_tx(bar_p, (uint32_t)(PIECE + HA) * sizeof(cpx));
+        bulk_load_hint(pre, f, PIECE * sizeof(cpx), bar_p, pol);
+        bulk_load_hint(pre + PIECE, f + 3 * PIECE, HA * sizeof(cpx), bar_p, pol);
+        bulk_prefetch_l2(f + 3 * PIECE + HA, HB * sizeof(cpx)); // the late piece and LO1|HI0 are fetched later: pull them
+        bulk_prefetch_l2(f + PIECE, 2 * PIECE * sizeof(cpx));   // into L2 now
+    };
+    auto load_r = [&](int g) {
+        mbar_expect_tx(bar_r, (uint32_t)(2 * PIECE) * sizeof(cpx));
+        bulk_load_hint(buf, in + (size_t)g * N + PIECE, 2 * PIECE * sizeof(cpx), bar_r, l2_policy_evict_first());
+    };
+    auto load_l = [&](int g) {
+        mbar_expect_tx(bar_l, (uint32_t)HB * sizeof(cpx));
+        bulk_load_hint(pre, in + (size_t)g * N + 3 * PIECE + HA, HB * sizeof(cpx), bar_l, l2_policy_evict_first());
+    };
+
+    int g = blockIdx.x;
+    if (tid == 0 && g < n_frames) {
+        load_p(g);
+        load_r(g);
+    }
+    uint32_t phase = 0;
+    STAGE_INIT();
+    for (; g < n_frames; g += gridDim.x) {
+        const int gn = g + gridDim.x;
+        const bool has_next = gn < n_frames;
+        mbar_wait(bar_p, phase);
+        mbar_wait(bar_r, phase);
+        STAGE_MARK(0) // wait for the bulk loads
+        {
+            cpx v[M], u[M];
+            // ---- step 0: b' = tid, lo record in P (LO0), hi record in buf (HI0); both parities of the radix-2 butterfly
+            {
+                const cpx* lo = pre + tid * M;
+                const cpx* hi = buf + PIECE + tid * M;
+#pragma unroll
+                for (int m = 0; m < M; ++m) {
+                    const cpx a = lo[m], b = hi[m];
+                    v[m] = cadd(a, b);
+                    u[m] = cmul(csub(a, b), wj0);
+                }
+            }
+            __syncthreads(); // LO0 consumed: its place takes the late part of HI1
+            if (tid == 0) {
+                fence_proxy_async();
+                load_l(g);
+            }
+            rf::FFTN<M, -1>::run(u);
+            TmemPark<S>::st(tmem_mine, 0, u); // E^1 of item 0 waits for pass 1
+            rf::FFTN<M, -1>::run(v);
+            TmemPark<S>::st(tmem_mine, 2, v); // E^0 of item 0 waits for the row buffer (still staging) in an output slot
+            STAGE_MARK(1) // step 0
+            mbar_wait(bar_l, phase);
+            // ---- step 1: b' = T + tid, lo record in buf (LO1), hi record in P (head after LO0, late part at 0)
+            {
+                const cpx* lo = buf + tid * M;
+                const int e = tid * M;
+                const cpx* hi = e < HA ? pre + PIECE + e : pre + (e - HA);
+#pragma unroll
+                for (int m = 0; m < M; ++m) {
+                    const cpx a = lo[m], b = hi[m];
+                    v[m] = cadd(a, b);
+                    u[m] = cmul(csub(a, b), wj1);
+                }
+            }
+            __syncthreads(); // staging fully consumed: P takes the next frame, buf takes the rows
+            if (tid == 0 && has_next) {
+                fence_proxy_async();
+                load_p(gn);
+            }
+            rf::FFTN<M, -1>::run(u);
+            TmemPark<S>::st(tmem_mine, 1, u);
+            rf::FFTN<M, -1>::run(v);
+            {
+                cpx* dst = buf + S::swz(tid + T);
+#pragma unroll
+                for (int m = 0; m < M; ++m) dst[m * RS] = v[m];
+            }
+            TmemPark<S>::ld(u, tmem_mine, 2);
+            {
+                cpx* dst = buf + S::swz(tid);
+#pragma unroll
+                for (int m = 0; m < M; ++m) dst[m * RS] = u[m];
+            }
+        }
+        __syncthreads();
+        STAGE_MARK(2) // step 1 + row writes
+#pragma unroll 1
+        for (int p = 0; p < 2; ++p) {
+            if (p == 1) {
+                // the odd-parity rows come out of tensor memory
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    cpx u[M];
+                    TmemPark<S>::ld(u, tmem_mine, j);
+                    cpx* dst = buf + S::swz(tid + j * T);
+#pragma unroll
+                    for (int m = 0; m < M; ++m) dst[m * RS] = u[m];
+                }
+                __syncthreads();
+                STAGE_MARK(6) // pass 1: rows out of tensor memory
+            }
+            // ---- stage B: K1-point inverse FFT of every row
+            row_fft<S, +1>(buf, tw_s, tid);
+            STAGE_MARK(3) // row FFT
+            __syncthreads();
+            STAGE_MARK(7) // barrier after the row FFT
+            // ---- stage C: table column of item 0 (L2; in flight during the column reads), column n' of all rows
+            cpx tc[M], c0[M], c1[M];
+            const cpx* tp = tableP + (size_t)p * M * K1 + tid;
+#pragma unroll
+            for (int m = 0; m < M; ++m) tc[m] = ldg_nc(tp + (size_t)m * K1);
+            {
+                const cpx* src = buf + tid;
+#pragma unroll
+                for (int m = 0; m < M; ++m) c0[m] = src[m * RS];
+#pragma unroll
+                for (int m = 0; m < M; ++m) c1[m] = src[T + m * RS];
+            }
+            STAGE_MARK(8) // table loads issued, column reads
+            __syncthreads(); // rows are dead
+            if (p == 1 && tid == 0 && has_next) {
+                fence_proxy_async();
+                load_r(gn); // buf takes LO1|HI0 of the next frame
+            }
+            STAGE_MARK(4) // stage C reads
+#pragma unroll
+            for (int m = 0; m < M; ++m) c0[m] = cmul(c0[m], tc[m]);
+#pragma unroll
+            for (int m = 0; m < M; ++m) tc[m] = ldg_nc(tp + T + (size_t)m * K1);
+            rf::FFTN<M, +1>::run(c0);
+            if (p == 0) {
+                TmemPark<S>::st(tmem_mine, 2, c0); // even samples wait for their odd neighbours
+#pragma unroll
+                for (int m = 0; m < M; ++m) c1[m] = cmul(c1[m], tc[m]);
+                rf::FFTN<M, +1>::run(c1);
+                TmemPark<S>::st(tmem_mine, 3, c1);
+            } else {
+                cpx ev[M];
+                TmemPark<S>::ld(ev, tmem_mine, 2);
+                cpx* dst = out + (size_t)g * N + 2 * tid;
+#pragma unroll
+                for (int n2 = 0; n2 < M; ++n2) stg_stream4(dst + (size_t)n2 * K, ev[n2], c0[n2]);
+#pragma unroll
+                for (int m = 0; m < M; ++m) c1[m] = cmul(c1[m], tc[m]);
+                rf::FFTN<M, +1>::run(c1);
+                TmemPark<S>::ld(ev, tmem_mine, 3);
+#pragma unroll
+                for (int n2 = 0; n2 < M; ++n2) stg_stream4(dst + 2 * T + (size_t)n2 * K, ev[n2], c1[n2]);
+            }
+            if (p == 0) { STAGE_MARK(5) } else { STAGE_MARK(9) } // stage C compute; parking (pass 0) / stores (pass 1)
+        }
+        phase ^= 1;
+    }
+    TmemPark<S>::release(tmem_base, tid);
+}
+
+// ----------------------------------------------------------------------------------------
 // receiver.  in: [n_frames][N] time samples; out: [n_frames][N]; mode 0: soft symbols, mode 1: R.
 // tables: [2 (half)][M][K1] = C_rx[m][n' + half*K1]; w2: W^{n'}.  A pass has four steps (item j, half h): the thread's
 // sample column n1 = tid + j*T + h*K1, i.e. M quarter rows of T samples, each moved by one bulk copy.
@@ -459,6 +706,7 @@ __global__ void __launch_bounds__(S::T, 1) fused_rx2_kernel(cpx* __restrict__ ou
 struct TwoPass {
     int M = 0, K = 0, L = 0;
     bool tx = false;
+    bool parked = true; // modulator: second parity and even samples parked in tensor memory (GFDM_MOD2_SCRATCH=1: first version)
     cpx* d_table = nullptr;
     cpx* d_tw = nullptr;
     cpx* d_w2 = nullptr;
@@ -493,7 +741,11 @@ TwoPass* twopass_create_tx(int M, int K, int L, const std::vector<std::complex<f
     t->smem = S::SMEM_BYTES;
     t->name = "fused_mod2_kernel<M=15,K=2x32x32,T=512>";
     try {
+        t->parked = std::getenv("GFDM_MOD2_SCRATCH") == nullptr;
         t->grid_cap = fused_grid_cap((const void*)&fused_mod2_kernel<S>, S::T, S::SMEM_BYTES);
+        const int cap_p = fused_grid_cap((const void*)&fused_mod2p_kernel<S>, S::T, S::SMEM_BYTES);
+        if (t->parked) t->grid_cap = cap_p;
+        if (t->parked) t->name = "fused_mod2p_kernel<M=15,K=2x32x32,T=512>";
         const std::vector<cpx> C = make_fold_table(M, K, L, taps, +1, true); // [m][n1]
         std::vector<cpx> P((size_t)2 * M * K1);
         for (int p = 0; p < 2; ++p)
@@ -558,7 +810,10 @@ int twopass_modulate(TwoPass* t, cpx* out, const cpx* in, size_t frames, cudaStr
     for (size_t f0 = 0; f0 < frames; f0 += max_chunk) {
         const int nf = (int)std::min(max_chunk, frames - f0);
         const int grid = nf < t->grid_cap ? nf : t->grid_cap;
-        fused_mod2_kernel<S><<<grid, S::T, S::SMEM_BYTES, s>>>(out + f0 * N, in + f0 * N, t->d_table, t->d_tw, t->d_w2, t->d_scratch, nf);
+        if (t->parked)
+            fused_mod2p_kernel<S><<<grid, S::T, S::SMEM_BYTES, s>>>(out + f0 * N, in + f0 * N, t->d_table, t->d_tw, t->d_w2, nf);
+        else
+            fused_mod2_kernel<S><<<grid, S::T, S::SMEM_BYTES, s>>>(out + f0 * N, in + f0 * N, t->d_table, t->d_tw, t->d_w2, t->d_scratch, nf);
         ++launches;
     }
     GFDM_CUDA_CHECK(cudaGetLastError());

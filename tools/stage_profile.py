@@ -36,7 +36,8 @@ names = {0: 'mod: wait bulk load', 1: 'mod: A read staging', 2: 'mod: A fft+row 
 
 if twopass:
     names = {0: 'mod2: wait bulk loads', 1: 'mod2: step 0 (read, fft)', 2: 'mod2: step 1 + row writes', 3: 'mod2: row fft (warp0)',
-             4: 'mod2: barrier + C read columns', 5: 'mod2: C table+ifft+store',
+             4: 'mod2: barrier + C read columns', 5: 'mod2: C table+ifft+store', 6: 'mod2p: pass 1 rows out of tensor memory', 7: 'mod2p: barrier after the row FFT', 8: 'mod2p: table loads + column reads',
+             9: 'mod2p: C pass 1 (ifft, unpark, stores)',
              16: "rx2: A' four steps + row writes", 17: 'rx2: row fft (warp0)', 18: "rx2: barrier + C' reads",
              19: "rx2: C' ifft+staging+stores", 20: 'rx2: step 0', 21: 'rx2: step 1', 22: 'rx2: step 2', 23: 'rx2: step 3'}
 
