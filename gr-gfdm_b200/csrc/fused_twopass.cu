@@ -702,11 +702,200 @@ __global__ void __launch_bounds__(S::T, 1) fused_rx2_kernel(cpx* __restrict__ ou
 }
 
 // ----------------------------------------------------------------------------------------
+// receiver, second version: the samples are read ONCE.  Pass 0 forms both parities of the radix-2 step from one set of
+// M-point transforms and table products (B^0 = a + b into the row buffer, B^1 = (a - b) W^{n'} parked in tensor memory),
+// so pass 1 has no loads, no transforms and no table products; the even-subcarrier records of pass 0 wait in tensor
+// memory as well, and pass 1 writes each thread's record PAIR (2k', 2k'+1: 2M contiguous elements) through a staging
+// area with ONE bulk store per item -- whole lines instead of M-element runs with M-element gaps.  The table columns come
+// from L2 (issued at the top of each step, in flight while the samples are read and transformed).
+// Homes and issue points of the quarter rows as in fused_rx2_kernel, with "next pass" = pass 0 of the next frame; the
+// quarter rows of step 1 (upper halves of the row buffer) follow the last bulk store of the frame.
+template <class S>
+__global__ void __launch_bounds__(S::T, 1) fused_rx2p_kernel(cpx* __restrict__ out, const cpx* __restrict__ in,
+                                                            const cpx* __restrict__ tables, const cpx* __restrict__ tw,
+                                                            const cpx* __restrict__ w2, int mode, int n_frames)
+{
+    constexpr int M = S::M, K1 = S::K, K = 2 * K1, N = M * K, T = S::T, RS = S::RS;
+    static_assert(S::F == 1 && S::IPT == 2 && S::TWO_PASS, "two-pass kernels: one half-frame per CTA pass, two items per thread");
+    constexpr int UP = RS / 2;
+    constexpr int NE = (S::P_ELEMS - M * T) / T;
+    static_assert(S::swz(T - 1) < UP && UP + T <= RS, "row halves");
+    static_assert(NE >= 1 && NE < M && M <= T / 32 && M * T * 2 <= S::BUF_ELEMS, "staging does not fit");
+    static_assert((M - NE - 1) * RS + UP + T <= S::BUF_ELEMS, "row halves");
+    constexpr uint32_t QBYTES = T * sizeof(cpx);
+    constexpr uint32_t STEP_BYTES = M * QBYTES;
+    constexpr int ITEM = 2 * T * M; // elements of one item's record pairs: a contiguous piece of the output frame
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    cpx* buf = reinterpret_cast<cpx*>(smem_raw);
+    cpx* tw_s = buf + S::BUF_ELEMS;
+    cpx* pre = tw_s + S::TW_ELEMS + S::TBL_ELEMS;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(pre + S::P_ELEMS + S::TAPS_ELEMS); // one per step
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const float inv_m = 1.0f / (float)M;
+
+    for (int i = tid; i < S::TW_ELEMS; i += T) tw_s[i] = tw[i];
+    if (tid == 0)
+        for (int s = 0; s < 4; ++s) mbar_init(bars + s, 1);
+    uint32_t tmem_base = 0, tmem_mine = 0;
+    TmemPark<S>::alloc(reinterpret_cast<uint32_t*>(bars + 4), tid, tmem_base, tmem_mine);
+    const cpx wj[2] = { w2[tid], w2[tid + T] };
+    __syncthreads();
+
+    auto qsrc = [&](int gg, int s, int n2) {
+        return in + (size_t)gg * N + (size_t)n2 * K + (s & 1) * K1 + (s >> 1) * T;
+    };
+    auto home = [&](int s, int n2) -> cpx* {
+        switch (s) {
+        case 0: return pre + n2 * T;
+        case 1: return buf + n2 * RS + UP;
+        case 2: return n2 < NE ? pre + (M + n2) * T : pre + (n2 - NE) * T;
+        default: return n2 < NE ? pre + (M - NE + n2) * T : buf + (n2 - NE) * RS + UP;
+        }
+    };
+    auto issue = [&](int gg, int s, int n_lo, int n_hi, bool arm) {
+        if (arm && tid == 0) mbar_expect_tx(bars + s, STEP_BYTES);
+        if (lane == 0 && warp >= n_lo && warp < n_hi) {
+            fence_proxy_async();
+            bulk_load_hint(home(s, warp), qsrc(gg, s, warp), QBYTES, bars + s, l2_policy_evict_first());
+        }
+    };
+
+    int g = blockIdx.x;
+    if (g < n_frames) {
+        issue(g, 0, 0, M, true);
+        issue(g, 1, 0, M, true);
+        issue(g, 2, 0, NE, true);
+    }
+    uint32_t phase = 0;
+    STAGE_INIT();
+    for (; g < n_frames; g += gridDim.x) {
+        const int gn = g + gridDim.x;
+        const bool has_next = gn < n_frames;
+        {
+            cpx v[M];
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                const int j = s >> 1, h = s & 1;
+                cpx tc[M], x[M];
+                const cpx* tp = tables + (size_t)h * M * K1 + tid + j * T;
+#pragma unroll
+                for (int m = 0; m < M; ++m) tc[m] = ldg_nc(tp + (size_t)m * K1);
+                mbar_wait(bars + s, phase);
+#pragma unroll
+                for (int n2 = 0; n2 < M; ++n2) x[n2] = home(s, n2)[tid];
+                __syncthreads(); // step s consumed
+                if (s == 0) {
+                    issue(g, 2, NE, M, false);
+                    issue(g, 3, 0, NE, true);
+                } else if (s == 1) {
+                    issue(g, 3, NE, M, false);
+                } else if (s == 2) {
+                    if (has_next) issue(gn, 2, 0, NE, true);
+                } else {
+                    if (has_next) issue(gn, 0, 0, M, true);
+                }
+                rf::FFTN<M, -1>::run(x);
+                if (h == 0) {
+#pragma unroll
+                    for (int m = 0; m < M; ++m) v[m] = cmul(x[m], tc[m]);
+                } else {
+#pragma unroll
+                    for (int m = 0; m < M; ++m) {
+                        const cpx b = cmul(x[m], tc[m]);
+                        x[m] = cmul(csub(v[m], b), wj[j]); // B^1: waits for pass 1
+                        v[m] = cadd(v[m], b);              // B^0: this pass
+                    }
+                    TmemPark<S>::st(tmem_mine, j, x);
+                    cpx* dst = buf + S::swz(tid + j * T);
+#pragma unroll
+                    for (int m = 0; m < M; ++m) dst[m * RS] = v[m];
+                }
+                STAGE_MARK(20 + s) // step s
+            }
+        }
+        __syncthreads();
+        STAGE_MARK(16) // barrier after the row writes
+        cpx* of = out + (size_t)g * N;
+#pragma unroll 1
+        for (int p = 0; p < 2; ++p) {
+            if (p == 1) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    cpx u[M];
+                    TmemPark<S>::ld(u, tmem_mine, j);
+                    cpx* dst = buf + S::swz(tid + j * T);
+#pragma unroll
+                    for (int m = 0; m < M; ++m) dst[m * RS] = u[m];
+                }
+                __syncthreads();
+                STAGE_MARK(24) // pass 1: rows out of tensor memory
+            }
+            // ---- stage B: K1-point forward FFT of every row
+            row_fft<S, -1>(buf, tw_s, tid);
+            STAGE_MARK(17) // row FFT
+            __syncthreads();
+            // ---- stage C': column k' of all rows = the M bins of subcarrier 2k'+p
+            cpx c[2][M];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const cpx* src = buf + tid + j * T;
+#pragma unroll
+                for (int m = 0; m < M; ++m) c[j][m] = src[m * RS];
+            }
+            __syncthreads(); // rows are dead
+            STAGE_MARK(18) // stage C' reads
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                if (mode == 0) {
+                    rf::FFTN<M, +1>::run(c[j]);
+#pragma unroll
+                    for (int m = 0; m < M; ++m) c[j][m] = cscale(c[j][m], inv_m);
+                }
+                if (p == 0) {
+                    TmemPark<S>::st(tmem_mine, 2 + j, c[j]); // record 2k' waits for record 2k'+1
+                } else {
+                    cpx ev[M];
+                    TmemPark<S>::ld(ev, tmem_mine, 2 + j);
+                    if (j == 1) { // item 0's store must have read the staging area
+                        if (tid == 0) bulk_wait_read();
+                        __syncthreads();
+                    }
+                    // records 2k' and 2k'+1 of k' = tid + j*T: 2M contiguous elements = M 16-byte stores (lane stride
+                    // 2M elements = 240 B at M = 15: conflict-free per quarter warp)
+                    float4* st = reinterpret_cast<float4*>(buf + (size_t)tid * 2 * M);
+#pragma unroll
+                    for (int q = 0; q < M; ++q) {
+                        const cpx e0 = 2 * q < M ? ev[2 * q] : c[j][2 * q - M];
+                        const cpx e1 = 2 * q + 1 < M ? ev[2 * q + 1] : c[j][2 * q + 1 - M];
+                        st[q] = make_float4(e0.x, e0.y, e1.x, e1.y);
+                    }
+                    fence_proxy_async();
+                    __syncthreads();
+                    if (tid == 0) bulk_store(of + (size_t)j * ITEM, buf, (uint32_t)ITEM * sizeof(cpx));
+                }
+            }
+            if (p == 0) { STAGE_MARK(19) } else { STAGE_MARK(25) } // M-IFFT + parking (pass 0) / staging + bulk stores (pass 1)
+        }
+        // the staging area is being read by the last store: the quarter rows of the next frame's step 1 (upper halves of
+        // the rows) follow it
+        if (has_next) {
+            if (tid == 0) bulk_wait_read();
+            __syncthreads();
+            issue(gn, 1, 0, M, true);
+        }
+        STAGE_MARK(26) // wait for the last store, issue step 1 of the next frame
+        phase ^= 1;
+    }
+    if (tid == 0) bulk_wait_all();
+    TmemPark<S>::release(tmem_base, tid);
+}
+
+// ----------------------------------------------------------------------------------------
 // host side
 struct TwoPass {
     int M = 0, K = 0, L = 0;
     bool tx = false;
-    bool parked = true; // modulator: second parity and even samples parked in tensor memory (GFDM_MOD2_SCRATCH=1: first version)
+    bool parked = true; // second parity + first-pass results parked in tensor memory (GFDM_MOD2_SCRATCH / GFDM_RX2_REREAD: first versions)
     cpx* d_table = nullptr;
     cpx* d_tw = nullptr;
     cpx* d_w2 = nullptr;
@@ -777,7 +966,11 @@ TwoPass* twopass_create_rx(int M, int K, int L, const std::vector<std::complex<f
     t->smem = S::SMEM_BYTES;
     t->name = "fused_rx2_kernel<M=15,K=2x32x32,T=512>";
     try {
+        t->parked = std::getenv("GFDM_RX2_REREAD") == nullptr; // (set: the first version, which reads the frame in both passes)
         t->grid_cap = fused_grid_cap((const void*)&fused_rx2_kernel<S>, S::T, S::SMEM_BYTES);
+        const int cap_p = fused_grid_cap((const void*)&fused_rx2p_kernel<S>, S::T, S::SMEM_BYTES);
+        if (t->parked) t->grid_cap = cap_p;
+        if (t->parked) t->name = "fused_rx2p_kernel<M=15,K=2x32x32,T=512>";
         // C_rx[m][n'] and C_rx[m][n'+K1] as [h][m][n']; the pass-1 twiddle W^{n'} = e^{-j2pi n'/K} is applied in the kernel
         const std::vector<std::complex<double>> C = make_fold_table_d(M, K, L, taps, -1, true);
         std::vector<cpx> P((size_t)2 * M * K1);
@@ -828,7 +1021,10 @@ int twopass_demodulate(TwoPass* t, cpx* out, const cpx* in, int mode, size_t fra
     for (size_t f0 = 0; f0 < frames; f0 += max_chunk) {
         const int nf = (int)std::min(max_chunk, frames - f0);
         const int grid = nf < t->grid_cap ? nf : t->grid_cap;
-        fused_rx2_kernel<S><<<grid, S::T, S::SMEM_BYTES, s>>>(out + f0 * N, in + f0 * N, t->d_table, t->d_tw, t->d_w2, mode, nf);
+        if (t->parked)
+            fused_rx2p_kernel<S><<<grid, S::T, S::SMEM_BYTES, s>>>(out + f0 * N, in + f0 * N, t->d_table, t->d_tw, t->d_w2, mode, nf);
+        else
+            fused_rx2_kernel<S><<<grid, S::T, S::SMEM_BYTES, s>>>(out + f0 * N, in + f0 * N, t->d_table, t->d_tw, t->d_w2, mode, nf);
         ++launches;
     }
     GFDM_CUDA_CHECK(cudaGetLastError());

@@ -39,7 +39,9 @@ if twopass:
              4: 'mod2: barrier + C read columns', 5: 'mod2: C table+ifft+store', 6: 'mod2p: pass 1 rows out of tensor memory', 7: 'mod2p: barrier after the row FFT', 8: 'mod2p: table loads + column reads',
              9: 'mod2p: C pass 1 (ifft, unpark, stores)',
              16: "rx2: A' four steps + row writes", 17: 'rx2: row fft (warp0)', 18: "rx2: barrier + C' reads",
-             19: "rx2: C' ifft+staging+stores", 20: 'rx2: step 0', 21: 'rx2: step 1', 22: 'rx2: step 2', 23: 'rx2: step 3'}
+             19: "rx2: C' ifft+staging+stores (parked: pass 0 ifft+park)", 20: 'rx2: step 0', 21: 'rx2: step 1', 22: 'rx2: step 2', 23: 'rx2: step 3',
+             24: 'rx2p: pass 1 rows out of tensor memory', 25: "rx2p: C' pass 1 (ifft, unpark, staging, bulk stores)",
+             26: 'rx2p: wait for the last store, issue step 1 of the next frame'}
 
 
 def run(label, fn, reps=5):
