@@ -4,9 +4,16 @@
 // One CTA still owns a whole frame, but visits it in two passes.  The K-point transform over the
 // subcarrier index is split by decimation in frequency (tools/fused_math_check.py, "two-pass"):
 // pass p in {0,1} computes the K1-point transform whose results are the outputs of parity p, so a pass
-// needs a K1-row buffer only (the C3 kernel's shared-memory budget), reads the frame once (pass 0 from
-// HBM, pass 1 from L2 -- 36 MB of live frames for 148 CTAs against 126 MB of L2) and writes half of
-// the output.  HBM traffic stays at the algorithmic 16*N bytes per frame.
+// needs a K1-row buffer only (the C3 kernel's shared-memory budget).  HBM traffic stays at the algorithmic
+// 16*N bytes per frame.  Two generations of kernels live here:
+//   * fused_mod2p_kernel / fused_rx2p_kernel (shipped): the frame is read ONCE; what pass 1 needs (the M-point results of
+//     the second parity) and what pass 0 produced for a location pass 1 completes (even samples / even records) is
+//     thread-private and waits in TENSOR MEMORY (4 x 2M columns per thread), so pass 1 has no loads, no transforms of
+//     the inputs and writes whole 16-byte pairs / one contiguous bulk store per item; the table columns, which used to fill
+//     the tensor memory, are read from L2 one step ahead of their use.
+//   * fused_mod2_kernel / fused_rx2_kernel (round 1; GFDM_MOD2_SCRATCH=1 / GFDM_RX2_REREAD=1 select them for A/B runs):
+//     both passes read the frame (pass 1 from L2) and re-derive the M-point transforms, the modulator's even samples
+//     wait in an L2-resident scratch, the receiver writes M-element runs with M-element gaps.
 //
 //   modulator (lib/modulator_kernel_cc.cc:98-141), W = e^{+j2pi/K}
 //     E^p_b'        = (d_b' + (-1)^p d_{b'+K1}) W^{p b'}              radix-2 butterfly on the raw symbols
@@ -351,8 +358,9 @@ __global__ void __launch_bounds__(S::T, 1) fused_mod2p_kernel(cpx* __restrict__ 
     cpx* pre = tw_s + S::TW_ELEMS + S::TBL_ELEMS;
     uint64_t* bars = reinterpret_cast<uint64_t*>(pre + S::P_ELEMS + S::TAPS_ELEMS);
     uint64_t* bar_p = bars;     // LO0 + head of HI1 (region P)
-    uint64_t* bar_r = bars + 1; // LO1 | HI0 (region buf)
+    uint64_t* bar_r = bars + 1; // HI0 (upper half of the staging in buf): step 0
     uint64_t* bar_l = bars + 2; // late part of HI1
+    uint64_t* bar_q = bars + 3; // LO1 (lower half of the staging in buf): step 1
     const int tid = threadIdx.x;
 
     for (int i = tid; i < S::TW_ELEMS; i += T) tw_s[i] = tw[i];
@@ -360,10 +368,11 @@ __global__ void __launch_bounds__(S::T, 1) fused_mod2p_kernel(cpx* __restrict__ 
         mbar_init(bar_p, 1);
         mbar_init(bar_r, 1);
         mbar_init(bar_l, 1);
+        mbar_init(bar_q, 1);
     }
     const cpx wj0 = w2[tid], wj1 = w2[tid + T];
     uint32_t tmem_base = 0, tmem_mine = 0;
-    TmemPark<S>::alloc(reinterpret_cast<uint32_t*>(bars + 3), tid, tmem_base, tmem_mine);
+    TmemPark<S>::alloc(reinterpret_cast<uint32_t*>(bars + 4), tid, tmem_base, tmem_mine);
     __syncthreads();
 
     auto load_p = [&](int g) {
@@ -376,8 +385,11 @@ __global__ void __launch_bounds__(S::T, 1) fused_mod2p_kernel(cpx* __restrict__ 
         bulk_prefetch_l2(f + PIECE, 2 * PIECE * sizeof(cpx));   // into L2 now
     };
     auto load_r = [&](int g) {
-        mbar_expect_tx(bar_r, (uint32_t)(2 * PIECE) * sizeof(cpx));
-        bulk_load_hint(buf, in + (size_t)g * N + PIECE, 2 * PIECE * sizeof(cpx), bar_r, l2_policy_evict_first());
+        // two copies: step 0 needs HI0 only, LO1 may land while it runs
+        mbar_expect_tx(bar_r, (uint32_t)PIECE * sizeof(cpx));
+        bulk_load_hint(buf + PIECE, in + (size_t)g * N + 2 * PIECE, PIECE * sizeof(cpx), bar_r, l2_policy_evict_first());
+        mbar_expect_tx(bar_q, (uint32_t)PIECE * sizeof(cpx));
+        bulk_load_hint(buf, in + (size_t)g * N + PIECE, PIECE * sizeof(cpx), bar_q, l2_policy_evict_first());
     };
     auto load_l = [&](int g) {
         mbar_expect_tx(bar_l, (uint32_t)HB * sizeof(cpx));
@@ -421,6 +433,7 @@ __global__ void __launch_bounds__(S::T, 1) fused_mod2p_kernel(cpx* __restrict__ 
             TmemPark<S>::st(tmem_mine, 2, v); // E^0 of item 0 waits for the row buffer (still staging) in an output slot
             STAGE_MARK(1) // step 0
             mbar_wait(bar_l, phase);
+            mbar_wait(bar_q, phase);
             // ---- step 1: b' = T + tid, lo record in buf (LO1), hi record in P (head after LO0, late part at 0)
             {
                 const cpx* lo = buf + tid * M;
@@ -767,15 +780,18 @@ __global__ void __launch_bounds__(S::T, 1) fused_rx2p_kernel(cpx* __restrict__ o
         issue(g, 2, 0, NE, true);
     }
     uint32_t phase = 0;
+    bool first = true; // first frame of this CTA: step 1 was issued up front, no store is in flight
     STAGE_INIT();
     for (; g < n_frames; g += gridDim.x) {
         const int gn = g + gridDim.x;
         const bool has_next = gn < n_frames;
         {
-            cpx v[M];
+            // Both h = 0 steps first: they read the prefetch region P only, so they run while the previous frame's last
+            // bulk store still drains the staging area; a_j (table x transform) waits in the record slots of tensor memory.
+            constexpr int ORDER[4] = { 0, 2, 1, 3 };
 #pragma unroll
-            for (int s = 0; s < 4; ++s) {
-                const int j = s >> 1, h = s & 1;
+            for (int i = 0; i < 4; ++i) {
+                const int s = ORDER[i], j = s >> 1, h = s & 1;
                 cpx tc[M], x[M];
                 const cpx* tp = tables + (size_t)h * M * K1 + tid + j * T;
 #pragma unroll
@@ -787,28 +803,40 @@ __global__ void __launch_bounds__(S::T, 1) fused_rx2p_kernel(cpx* __restrict__ o
                 if (s == 0) {
                     issue(g, 2, NE, M, false);
                     issue(g, 3, 0, NE, true);
-                } else if (s == 1) {
-                    issue(g, 3, NE, M, false);
                 } else if (s == 2) {
                     if (has_next) issue(gn, 2, 0, NE, true);
+                    if (!first) {
+                        // the quarter rows of step 1 live in the row buffer, which the previous frame's last store reads
+                        if (tid == 0) bulk_wait_read();
+                        __syncthreads();
+                        issue(g, 1, 0, M, true);
+                    }
+                } else if (s == 1) {
+                    issue(g, 3, NE, M, false);
                 } else {
-                    if (has_next) issue(gn, 0, 0, M, true);
+                    if (has_next) {
+                        issue(gn, 0, 0, M, true);
+                        if (lane == 0 && warp < M) bulk_prefetch_l2(qsrc(gn, 1, warp), QBYTES); // fetched after the stores
+                    }
                 }
                 rf::FFTN<M, -1>::run(x);
                 if (h == 0) {
 #pragma unroll
-                    for (int m = 0; m < M; ++m) v[m] = cmul(x[m], tc[m]);
+                    for (int m = 0; m < M; ++m) x[m] = cmul(x[m], tc[m]);
+                    TmemPark<S>::st(tmem_mine, 2 + j, x);
                 } else {
+                    cpx a[M];
+                    TmemPark<S>::ld(a, tmem_mine, 2 + j);
 #pragma unroll
                     for (int m = 0; m < M; ++m) {
                         const cpx b = cmul(x[m], tc[m]);
-                        x[m] = cmul(csub(v[m], b), wj[j]); // B^1: waits for pass 1
-                        v[m] = cadd(v[m], b);              // B^0: this pass
+                        x[m] = cmul(csub(a[m], b), wj[j]); // B^1: waits for pass 1
+                        a[m] = cadd(a[m], b);              // B^0: this pass
                     }
                     TmemPark<S>::st(tmem_mine, j, x);
                     cpx* dst = buf + S::swz(tid + j * T);
 #pragma unroll
-                    for (int m = 0; m < M; ++m) dst[m * RS] = v[m];
+                    for (int m = 0; m < M; ++m) dst[m * RS] = a[m];
                 }
                 STAGE_MARK(20 + s) // step s
             }
@@ -876,14 +904,9 @@ __global__ void __launch_bounds__(S::T, 1) fused_rx2p_kernel(cpx* __restrict__ o
             }
             if (p == 0) { STAGE_MARK(19) } else { STAGE_MARK(25) } // M-IFFT + parking (pass 0) / staging + bulk stores (pass 1)
         }
-        // the staging area is being read by the last store: the quarter rows of the next frame's step 1 (upper halves of
-        // the rows) follow it
-        if (has_next) {
-            if (tid == 0) bulk_wait_read();
-            __syncthreads();
-            issue(gn, 1, 0, M, true);
-        }
-        STAGE_MARK(26) // wait for the last store, issue step 1 of the next frame
+        // (the staging area is still being read by the last store: the next frame issues the quarter rows of its step 1,
+        // whose homes are the upper halves of the rows, after its two P-only steps)
+        first = false;
         phase ^= 1;
     }
     if (tid == 0) bulk_wait_all();

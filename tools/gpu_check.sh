@@ -12,6 +12,7 @@ echo "== bench reference" ; timeout 600 python bench.py --impl reference --steps
 for wl in c1 c2 c4 c5; do
   echo "== bench $wl" ; timeout 400 python bench.py --workload $wl --steps 10 --warmup 3 --cpu-seconds 6 2>&1 | tail -n 1 | tee $OUT/${TAG}_bench_$wl.json | cut -c1-200
 done
+echo "== bench c5 sweep" ; timeout 600 python bench.py --workload c5 --sweep --steps 5 --no-cpu 2>&1 | tail -n 1 | tee $OUT/${TAG}_bench_c5_sweep_n1.json | cut -c1-200
 echo "== per-row chain bench"
 timeout 600 python tools/chain_bench.py tx rx copy next shapes > $OUT/${TAG}_chain_bench.jsonl 2> $OUT/${TAG}_chain_bench.err; tail -n 2 $OUT/${TAG}_chain_bench.err
 echo "== ncu launch list"
@@ -22,4 +23,5 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:fuse
     python bench.py --steps 1 --warmup 3 --no-cpu --no-e2e --no-latency > $OUT/${TAG}_full_bench.log 2>&1
 rm -f $OUT/${TAG}_fused.ncu-rep.tmp
 ncu -i $OUT/${TAG}_fused.ncu-rep --page raw --csv > $OUT/${TAG}_fused_raw.csv 2>/dev/null && python tools/ncu_summary.py $OUT/${TAG}_fused_raw.csv > $OUT/${TAG}_c3_fused_ncu_full.txt
+timeout 200 python tools/stage_profile.py c5 2048 > $OUT/${TAG}_stage_cycles_c5.txt 2>&1
 ls -la $OUT | tail -n 20
