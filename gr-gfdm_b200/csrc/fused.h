@@ -49,7 +49,8 @@ bool twopass_supported(int M, int K);
 TwoPass* twopass_create_tx(int M, int K, int L, const std::vector<std::complex<float>>& taps);
 TwoPass* twopass_create_rx(int M, int K, int L, const std::vector<std::complex<float>>& taps);
 int twopass_modulate(TwoPass* t, cpx* out, const cpx* in, size_t frames, cudaStream_t s);
-int twopass_demodulate(TwoPass* t, cpx* out, const cpx* in, int mode, size_t frames, cudaStream_t s); // mode 0: y, 1: R
+int twopass_demodulate(TwoPass* t, cpx* out, const cpx* in, const cpx* eq, int mode, size_t frames, cudaStream_t s); // mode 0: y, 1: R
+bool twopass_supports_eq(const TwoPass* t);
 const char* twopass_name(const TwoPass* t);
 void twopass_destroy(TwoPass* t);
 

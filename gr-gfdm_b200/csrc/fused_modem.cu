@@ -176,7 +176,10 @@ void FusedModem::init_rx(int M, int K, int L, const std::vector<std::complex<flo
     impl_ = p;
 }
 
-bool FusedModem::supports_eq() const { return impl_ && impl_->e != nullptr && impl_->eq_ok; }
+bool FusedModem::supports_eq() const
+{
+    return impl_ && ((impl_->e != nullptr && impl_->eq_ok) || (impl_->tp != nullptr && twopass_supports_eq(impl_->tp)));
+}
 bool FusedModem::supports_stride() const { return impl_ && impl_->e != nullptr; }
 
 int FusedModem::modulate(cpx* out, const cpx* in, size_t frames, cudaStream_t s)
@@ -314,10 +317,9 @@ int FusedModem::demodulate(cpx* out_td, cpx* out_fd, const cpx* in, const cpx* e
 {
     if (impl_->tp) {
         if (in_stride) throw std::invalid_argument("the two-pass receiver kernel takes packed frames only");
-        if (eq) throw std::invalid_argument("the two-pass receiver kernel has no equalising variant");
         int n = 0;
-        if (out_td) n += twopass_demodulate(impl_->tp, out_td, in, 0, frames, s);
-        if (out_fd) n += twopass_demodulate(impl_->tp, out_fd, in, 1, frames, s);
+        if (out_td) n += twopass_demodulate(impl_->tp, out_td, in, eq, 0, frames, s);
+        if (out_fd) n += twopass_demodulate(impl_->tp, out_fd, in, eq, 1, frames, s);
         return n;
     }
     const ShapeEntry* e = impl_->e;

@@ -28,17 +28,18 @@
 // Shared memory per CTA (same carve-up as fused_modem.cu): row buffer `buf` (M rows of K1, padded),
 // the row-FFT twiddles and the staging region P.  Input moves by cp.async.bulk (TMA 1D) and is prefetched
 // one pass ahead wherever a region is free; the pieces that cannot be resident early are fetched one
-// compute step ahead.  The equalising / interference-cancelling variants are not provided for this shape; those
-// entry points use the staged path of api.cu.  Why, and how it would be done: with Y/H between FFT and filter the taps
-// cannot be folded into the table, and R_k = G1[k-1] Y[k-1] + G0[k] Y[k] (G0 = T[m]/H, G1 = T[M+m]/H) mixes a bin of each
-// parity, i.e. of each pass.  Pass 0 would write P_k = G0 Y_k (even k) and Q_{k+1} = G1 Y_k to two per-CTA scratch arrays
-// that stay in L2 (as the modulator's even samples do), pass 1 would add its own terms, run every M-point IFFT and store
-// record pairs (2k'+1, 2k'+2) contiguously: 24 N bytes of HBM traffic plus 4 x N/2 complex of L2 traffic per frame.
+// compute step ahead.
+// Equalisation (receiver_kernel_cc.cc:309-320) at this shape, overlap 2: fused_rx2p_kernel<S, true>.  With Y/H between FFT and
+// filter the taps cannot be folded into the table, and R_k = G1 Yeq[k-1] + G0 Yeq[k] mixes a block of each parity, i.e. of
+// each pass: pass 0 divides its (even) blocks by the channel and parks them in tensor memory, pass 1 divides the odd ones,
+// gets block 2k'-1 from the previous lane and combines both parities in registers -- 24 N bytes of HBM traffic per frame.
+// The interference-cancelling entry points still use the staged path of api.cu at this shape.
 #include "fused.h"
 #include "fused_dev.cuh"
 
 #include <cmath>
 #include <cstdlib>
+#include <stdexcept>
 #include <string>
 
 namespace gfdm {
@@ -723,10 +724,11 @@ __global__ void __launch_bounds__(S::T, 1) fused_rx2_kernel(cpx* __restrict__ ou
 // from L2 (issued at the top of each step, in flight while the samples are read and transformed).
 // Homes and issue points of the quarter rows as in fused_rx2_kernel, with "next pass" = pass 0 of the next frame; the
 // quarter rows of step 1 (upper halves of the row buffer) follow the last bulk store of the frame.
-template <class S>
+template <class S, bool EQ>
 __global__ void __launch_bounds__(S::T, 1) fused_rx2p_kernel(cpx* __restrict__ out, const cpx* __restrict__ in,
                                                             const cpx* __restrict__ tables, const cpx* __restrict__ tw,
-                                                            const cpx* __restrict__ w2, int mode, int n_frames)
+                                                            const cpx* __restrict__ w2, const cpx* __restrict__ eq,
+                                                            const cpx* __restrict__ taps, int mode, int n_frames)
 {
     constexpr int M = S::M, K1 = S::K, K = 2 * K1, N = M * K, T = S::T, RS = S::RS;
     static_assert(S::F == 1 && S::IPT == 2 && S::TWO_PASS, "two-pass kernels: one half-frame per CTA pass, two items per thread");
@@ -738,6 +740,7 @@ __global__ void __launch_bounds__(S::T, 1) fused_rx2p_kernel(cpx* __restrict__ o
     constexpr uint32_t QBYTES = T * sizeof(cpx);
     constexpr uint32_t STEP_BYTES = M * QBYTES;
     constexpr int ITEM = 2 * T * M; // elements of one item's record pairs: a contiguous piece of the output frame
+    static_assert(!EQ || S::BUF_ELEMS - ITEM >= 2 * (T / 32) * M, "no room for the hand-over array behind the staging area");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     cpx* buf = reinterpret_cast<cpx*>(smem_raw);
     cpx* tw_s = buf + S::BUF_ELEMS;
@@ -752,6 +755,14 @@ __global__ void __launch_bounds__(S::T, 1) fused_rx2p_kernel(cpx* __restrict__ o
     uint32_t tmem_base = 0, tmem_mine = 0;
     TmemPark<S>::alloc(reinterpret_cast<uint32_t*>(bars + 4), tid, tmem_base, tmem_mine);
     const cpx wj[2] = { w2[tid], w2[tid + T] };
+    // equalising variant (overlap 2): receive taps in shared memory, one more barrier for the channel copies
+    cpx* taps_s = pre + S::P_ELEMS;
+    uint64_t* bar_h = bars + 5;
+    uint32_t phase_h = 0;
+    if constexpr (EQ) {
+        if (tid < 2 * M) taps_s[tid] = taps[tid];
+        if (tid == 0) mbar_init(bar_h, 1);
+    }
     __syncthreads();
 
     auto qsrc = [&](int gg, int s, int n2) {
@@ -785,6 +796,9 @@ __global__ void __launch_bounds__(S::T, 1) fused_rx2p_kernel(cpx* __restrict__ o
     for (; g < n_frames; g += gridDim.x) {
         const int gn = g + gridDim.x;
         const bool has_next = gn < n_frames;
+        if constexpr (EQ) { // the frame's channel is read twice (one parity per pass): pull it into L2 now
+            if (tid < 2) bulk_prefetch_l2(eq + (size_t)g * N + (size_t)tid * ITEM, ITEM * sizeof(cpx));
+        }
         {
             // Both h = 0 steps first: they read the prefetch region P only, so they run while the previous frame's last
             // bulk store still drains the staging area; a_j (table x transform) waits in the record slots of tensor memory.
@@ -872,6 +886,84 @@ __global__ void __launch_bounds__(S::T, 1) fused_rx2p_kernel(cpx* __restrict__ o
             }
             __syncthreads(); // rows are dead
             STAGE_MARK(18) // stage C' reads
+            if constexpr (EQ) {
+                // Equalisation with overlap 2 (receiver_kernel_cc.cc:165-192,309-320): the rows now hold the true bins
+                // Y[(2k'+p) M + m].  The channel records of an item's subcarrier pairs arrive by one bulk copy into the (free)
+                // row buffer, in the order their owners read them; division in registers.
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    if (tid == 0) {
+                        fence_proxy_async();
+                        mbar_expect_tx(bar_h, (uint32_t)ITEM * sizeof(cpx));
+                        bulk_load(buf, eq + (size_t)g * N + (size_t)j * ITEM, (uint32_t)ITEM * sizeof(cpx), bar_h);
+                    }
+                    mbar_wait(bar_h, phase_h);
+                    phase_h ^= 1;
+                    const cpx* hh = buf + (size_t)tid * 2 * M + p * M;
+#pragma unroll
+                    for (int m = 0; m < M; ++m) {
+                        const cpx h1 = hh[m];
+                        const float rden = __fdividef(1.0f, h1.x * h1.x + h1.y * h1.y);
+                        const cpx num = cmulc(c[j][m], h1); // y * conj(h) / |h|^2, volk_32fc_x2_divide_32fc
+                        c[j][m] = cmake(num.x * rden, num.y * rden);
+                    }
+                    __syncthreads(); // channel consumed
+                    if (p == 0) TmemPark<S>::st(tmem_mine, 2 + j, c[j]); // equalised even block waits for its odd neighbours
+                }
+                if (p == 1) {
+                    // R_k[m] = taps[M+m] Yeq_{k-1}[m] + taps[m] Yeq_k[m].  Block 2k'+1 needs 2k' (parked, own), block 2k' needs
+                    // 2k'-1 = the odd block of the previous thread: a shuffle; lane 0 takes it from the hand-over array
+                    // behind the staging area (k' = 0 wraps to the last odd block of the frame).
+                    cpx* bnd = buf + ITEM; // [item][warp][M]
+                    if (lane == 31) {
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            cpx* b = bnd + (size_t)(j * (T / 32) + warp) * M;
+#pragma unroll
+                            for (int m = 0; m < M; ++m) b[m] = c[j][m];
+                        }
+                    }
+                    __syncthreads();
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        cpx ev[M];
+                        TmemPark<S>::ld(ev, tmem_mine, 2 + j);
+                        const int wprev = (j * (T / 32) + warp + 2 * (T / 32) - 1) % (2 * (T / 32)); // warp 0 of item 0: last of item 1
+                        const cpx* b = bnd + (size_t)wprev * M;
+#pragma unroll
+                        for (int m = 0; m < M; ++m) {
+                            cpx pv = cmake(__shfl_up_sync(0xffffffffu, c[j][m].x, 1), __shfl_up_sync(0xffffffffu, c[j][m].y, 1));
+                            if (lane == 0) pv = b[m];
+                            const cpx re = cadd(cmul(taps_s[M + m], pv), cmul(taps_s[m], ev[m]));
+                            c[j][m] = cadd(cmul(taps_s[M + m], ev[m]), cmul(taps_s[m], c[j][m]));
+                            ev[m] = re;
+                        }
+                        if (mode == 0) {
+                            rf::FFTN<M, +1>::run(ev);
+                            rf::FFTN<M, +1>::run(c[j]);
+#pragma unroll
+                            for (int m = 0; m < M; ++m) {
+                                ev[m] = cscale(ev[m], inv_m);
+                                c[j][m] = cscale(c[j][m], inv_m);
+                            }
+                        }
+                        if (j == 1) { // item 0's store must have read the staging area
+                            if (tid == 0) bulk_wait_read();
+                            __syncthreads();
+                        }
+                        float4* st = reinterpret_cast<float4*>(buf + (size_t)tid * 2 * M);
+#pragma unroll
+                        for (int q = 0; q < M; ++q) {
+                            const cpx e0 = 2 * q < M ? ev[2 * q] : c[j][2 * q - M];
+                            const cpx e1 = 2 * q + 1 < M ? ev[2 * q + 1] : c[j][2 * q + 1 - M];
+                            st[q] = make_float4(e0.x, e0.y, e1.x, e1.y);
+                        }
+                        fence_proxy_async();
+                        __syncthreads();
+                        if (tid == 0) bulk_store(of + (size_t)j * ITEM, buf, (uint32_t)ITEM * sizeof(cpx));
+                    }
+                }
+            } else {
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 if (mode == 0) {
@@ -902,6 +994,7 @@ __global__ void __launch_bounds__(S::T, 1) fused_rx2p_kernel(cpx* __restrict__ o
                     if (tid == 0) bulk_store(of + (size_t)j * ITEM, buf, (uint32_t)ITEM * sizeof(cpx));
                 }
             }
+            }
             if (p == 0) { STAGE_MARK(19) } else { STAGE_MARK(25) } // M-IFFT + parking (pass 0) / staging + bulk stores (pass 1)
         }
         // (the staging area is still being read by the last store: the next frame issues the quarter rows of its step 1,
@@ -923,6 +1016,8 @@ struct TwoPass {
     cpx* d_tw = nullptr;
     cpx* d_w2 = nullptr;
     cpx* d_scratch = nullptr; // modulator: grid_cap x M*K1 even samples of pass 0 (L2 resident)
+    cpx* d_table_eq = nullptr; // receiver, overlap 2: plain N-point twiddle in the same [h][M][K1] layout (equalising variant)
+    cpx* d_taps = nullptr;     // receiver, overlap 2: the L*M receive taps
     int grid_cap = 0;
     size_t smem = 0;
     std::string name;
@@ -939,6 +1034,8 @@ static void twopass_free(TwoPass* t)
     if (t->d_tw) cudaFree(t->d_tw);
     if (t->d_w2) cudaFree(t->d_w2);
     if (t->d_scratch) cudaFree(t->d_scratch);
+    if (t->d_table_eq) cudaFree(t->d_table_eq);
+    if (t->d_taps) cudaFree(t->d_taps);
     delete t;
 }
 void twopass_destroy(TwoPass* t) { twopass_free(t); }
@@ -991,9 +1088,23 @@ TwoPass* twopass_create_rx(int M, int K, int L, const std::vector<std::complex<f
     try {
         t->parked = std::getenv("GFDM_RX2_REREAD") == nullptr; // (set: the first version, which reads the frame in both passes)
         t->grid_cap = fused_grid_cap((const void*)&fused_rx2_kernel<S>, S::T, S::SMEM_BYTES);
-        const int cap_p = fused_grid_cap((const void*)&fused_rx2p_kernel<S>, S::T, S::SMEM_BYTES);
+        const int cap_p = fused_grid_cap((const void*)&fused_rx2p_kernel<S, false>, S::T, S::SMEM_BYTES);
+        fused_grid_cap((const void*)&fused_rx2p_kernel<S, true>, S::T, S::SMEM_BYTES); // opts the equalising variant into its shared memory
         if (t->parked) t->grid_cap = cap_p;
         if (t->parked) t->name = "fused_rx2p_kernel<M=15,K=2x32x32,T=512>";
+        if (t->parked && L == 2) { // the equalising variant combines exactly two blocks in registers
+            const std::vector<std::complex<double>> E = make_fold_table_d(M, K, L, taps, -1, false);
+            std::vector<cpx> Pe((size_t)2 * M * K1), tp((size_t)L * M);
+            for (int h = 0; h < 2; ++h)
+                for (int m = 0; m < M; ++m)
+                    for (int n = 0; n < K1; ++n) {
+                        const std::complex<double> c = E[(size_t)m * K + n + h * K1];
+                        Pe[((size_t)h * M + m) * K1 + n] = make_float2((float)c.real(), (float)c.imag());
+                    }
+            for (int i = 0; i < L * M; ++i) tp[i] = make_float2(taps[i].real(), taps[i].imag());
+            t->d_table_eq = upload(Pe);
+            t->d_taps = upload(tp);
+        }
         // C_rx[m][n'] and C_rx[m][n'+K1] as [h][m][n']; the pass-1 twiddle W^{n'} = e^{-j2pi n'/K} is applied in the kernel
         const std::vector<std::complex<double>> C = make_fold_table_d(M, K, L, taps, -1, true);
         std::vector<cpx> P((size_t)2 * M * K1);
@@ -1036,16 +1147,23 @@ int twopass_modulate(TwoPass* t, cpx* out, const cpx* in, size_t frames, cudaStr
     return launches;
 }
 
-int twopass_demodulate(TwoPass* t, cpx* out, const cpx* in, int mode, size_t frames, cudaStream_t s)
+bool twopass_supports_eq(const TwoPass* t) { return t && !t->tx && t->d_table_eq != nullptr; }
+
+int twopass_demodulate(TwoPass* t, cpx* out, const cpx* in, const cpx* eq, int mode, size_t frames, cudaStream_t s)
 {
     typedef S15x1024 S;
+    if (eq && !twopass_supports_eq(t)) throw std::invalid_argument("the two-pass receiver kernel equalises with overlap 2 only");
     int launches = 0;
     const size_t N = (size_t)t->M * t->K, max_chunk = (size_t)1 << 20;
     for (size_t f0 = 0; f0 < frames; f0 += max_chunk) {
         const int nf = (int)std::min(max_chunk, frames - f0);
         const int grid = nf < t->grid_cap ? nf : t->grid_cap;
-        if (t->parked)
-            fused_rx2p_kernel<S><<<grid, S::T, S::SMEM_BYTES, s>>>(out + f0 * N, in + f0 * N, t->d_table, t->d_tw, t->d_w2, mode, nf);
+        if (eq)
+            fused_rx2p_kernel<S, true><<<grid, S::T, S::SMEM_BYTES, s>>>(out + f0 * N, in + f0 * N, t->d_table_eq, t->d_tw, t->d_w2,
+                                                                        eq + f0 * N, t->d_taps, mode, nf);
+        else if (t->parked)
+            fused_rx2p_kernel<S, false><<<grid, S::T, S::SMEM_BYTES, s>>>(out + f0 * N, in + f0 * N, t->d_table, t->d_tw, t->d_w2, nullptr,
+                                                                         nullptr, mode, nf);
         else
             fused_rx2_kernel<S><<<grid, S::T, S::SMEM_BYTES, s>>>(out + f0 * N, in + f0 * N, t->d_table, t->d_tw, t->d_w2, mode, nf);
         ++launches;

@@ -80,6 +80,20 @@ def tx_chain(M, K, A, cp, cs, frames, shifts=(0,)):
     tx.set_chain_fusion(True)
 
 
+def rx_eq_row(M, K, frames):
+    """Equalising receiver alone (24N bytes/frame) -- the K = 2048 shape, whose frame is larger than shared memory."""
+    rng = np.random.default_rng(12)
+    N = M * K
+    taps = design.get_frequency_domain_filter('rrc', 0.5, M, K, 2)
+    d_x = torch.from_numpy(crand(rng, frames, N)).cuda()
+    d_h = torch.from_numpy((1 + 0.3 * crand(rng, frames, N)).astype(np.complex64)).cuda()
+    d_y = torch.empty_like(d_x)
+    rx = capi.Demodulator(M, K, 2, np.conj(taps), lib=lib)
+    rx.set_stream(stream.cuda_stream)
+    ms = timed(lambda: rx.demodulate_ptr(d_y.data_ptr(), d_x.data_ptr(), d_h.data_ptr(), frames))
+    report('receiver_kernel_cc::generic_work_equalize', 'K=%d M=%d' % (K, M), frames, ms, 24 * N, rx.last_kernel())
+
+
 def rx_rows(M, K, A, frames, ic_iter=4):
     """Receiver-side rows at one shape: equalising receiver (24N bytes/frame), preamble channel estimator
     (8*(2K+N)), advanced receiver with `ic_iter` SIC iterations resident on the SM (24N regardless of ic_iter)."""
@@ -231,6 +245,9 @@ if __name__ == '__main__':
     if 'rx' in what:
         rx_rows(15, 256, 208, 1 << 14)                  # BASELINE configs[3]: estimator + advanced receiver, 4 SIC iterations
         rx_rows(15, 1024, 832, 4096)
+        rx_eq_row(15, 2048, 2048)
+    if 'rx2048' in what:
+        rx_eq_row(15, 2048, 2048)
     if 'copy' in what:
         copy_rows(9, 64, 52, 16, 8, 1 << 16)
         copy_rows(15, 1024, 832, 64, 32, 4096)
