@@ -492,8 +492,6 @@ __global__ void __launch_bounds__(S::T, 1) fused_mod2p_kernel(cpx* __restrict__ 
             // ---- stage C: table column of item 0 (L2; in flight during the column reads), column n' of all rows
             cpx tc[M], c0[M], c1[M];
             const cpx* tp = tableP + (size_t)p * M * K1 + tid;
-#pragma unroll
-            for (int m = 0; m < M; ++m) tc[m] = ldg_nc(tp + (size_t)m * K1);
             {
                 const cpx* src = buf + tid;
 #pragma unroll
@@ -501,6 +499,8 @@ __global__ void __launch_bounds__(S::T, 1) fused_mod2p_kernel(cpx* __restrict__ 
 #pragma unroll
                 for (int m = 0; m < M; ++m) c1[m] = src[T + m * RS];
             }
+#pragma unroll
+            for (int m = 0; m < M; ++m) tc[m] = ldg_nc(tp + (size_t)m * K1); // in flight across the barrier
             STAGE_MARK(8) // table loads issued, column reads
             __syncthreads(); // rows are dead
             if (p == 1 && tid == 0 && has_next) {
