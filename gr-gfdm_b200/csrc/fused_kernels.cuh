@@ -488,7 +488,7 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_rx_kernel(cpx* __restrict
             }
         }
         // the previous group's bulk store must have finished reading R
-        if (tid == 0) bulk_wait_read();
+        if ((tid & 31) == 0) bulk_wait_read(); // (each warp's lane 0 issued that warp's stores)
         __syncthreads();
         STAGE_MARK(18) // M-FFT + table, wait for the previous store
 #pragma unroll
@@ -862,8 +862,8 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_rx_kernel(cpx* __restrict
             }
         }
         // output staging in the linear [k][m] order; item j covers the contiguous slice
-        // [j*T*M, (j+1)*T*M), which is bulk-stored as soon as it is complete so that the first
-        // slice drains to HBM while the next item's M-point IFFT runs
+        // [j*T*M, (j+1)*T*M), which leaves by bulk stores as soon as it is staged so that it
+        // drains to HBM while the next item's M-point IFFT runs
 #pragma unroll
         for (int j = 0; j < IPT; ++j) {
             if (!SIC && mode != 1) {
@@ -882,6 +882,25 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_rx_kernel(cpx* __restrict
 #pragma unroll
                 for (int m = 0; m < M; ++m) dst[m] = v[j][m];
             }
+            if constexpr (!(SIC && IPT > 1)) {
+                // every warp stores its own 32 records (a contiguous slice of the output) as soon as they are staged: no CTA
+                // barrier in the output stage, and the first bytes leave a warp-skew earlier (measured against one store per
+                // item, per group, and a deferred last store: experiments/README.md)
+                fence_proxy_async();
+                __syncwarp();
+                if ((tid & 31) == 0) {
+                    const int e0 = (j * T + (tid & ~31)) * M, e1 = min(e0 + 32 * M, fh * N);
+                    if (e1 > e0) {
+                        if constexpr (DEC)
+                            bulk_store(reinterpret_cast<unsigned char*>(out) + (size_t)g * F * N + e0,
+                                       reinterpret_cast<unsigned char*>(buf) + e0, (uint32_t)(e1 - e0));
+                        else
+                            bulk_store(out + (size_t)g * F * N + e0, buf + e0, (uint32_t)(e1 - e0) * sizeof(cpx));
+                    }
+                }
+                continue;
+            }
+            // (the cancellation loop of the two-subcarrier shapes stages CTA-wide: one store per item)
             fence_proxy_async();
             __syncthreads();
             if (tid == 0) {
@@ -897,7 +916,7 @@ __global__ void __launch_bounds__(S::T, S::MINB) fused_rx_kernel(cpx* __restrict
         }
         STAGE_MARK(23) // M-IFFT + output staging + store issue
     }
-    if (tid == 0) bulk_wait_all();
+    if ((tid & 31) == 0) bulk_wait_all(); // every issuing lane waits for its own stores
     if constexpr (S::TBL_TMEM) {
         tmem_fence_before_sync();
         __syncthreads();
