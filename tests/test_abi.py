@@ -86,3 +86,28 @@ def test_product_never_references_the_oracle():
             if f.endswith(('.py', '.cu', '.cuh', '.h', '.cc', '.cpp')):
                 txt = open(os.path.join(dirpath, f), errors='replace').read()
                 assert 'libgfdm_port' not in txt and 'libgfdm_ref' not in txt and 'gfdm_oracle' not in txt, f
+
+
+def test_fused_shape_table_matches_the_sources():
+    """The set of single-kernel shapes the GPU tests expect (conftest.FUSED_TABLE) is exactly what the translation units
+    csrc/fused_shapes_*.cu instantiate (GFDM_SHAPE(M, R1, R2, ...): K = R1 * R2), and what tools/shape_chooser.py accepts."""
+    import glob
+    import importlib.util
+    from conftest import FUSED_TABLE
+    found = set()
+    for path in glob.glob(os.path.join(ROOT, 'gr-gfdm_b200', 'csrc', 'fused_shapes_*.cu')):
+        for m in re.finditer(r'^\s*GFDM_SHAPE\((\d+),\s*(\d+),\s*(\d+),\s*(\d+),\s*(\d+),\s*(\d+)', open(path).read(), re.M):
+            M, R1, R2, T, IPT, MINB = (int(x) for x in m.groups())
+            assert (M, R1 * R2) not in found, 'shape instantiated twice: M=%d K=%d' % (M, R1 * R2)
+            found.add((M, R1 * R2))
+    assert found == set(FUSED_TABLE), (sorted(found - set(FUSED_TABLE)), sorted(set(FUSED_TABLE) - found))
+    spec = importlib.util.spec_from_file_location('shape_chooser', os.path.join(ROOT, 'tools', 'shape_chooser.py'))
+    chooser = importlib.util.module_from_spec(spec)
+    src = open(os.path.join(ROOT, 'tools', 'shape_chooser.py')).read()
+    assert 'def shape(' in src
+    # the chooser's budget arithmetic accepts every instantiated parameter set (it mirrors Shape's static_asserts)
+    exec(compile(src.split("if __name__")[0], 'shape_chooser', 'exec'), chooser.__dict__)
+    for path in glob.glob(os.path.join(ROOT, 'gr-gfdm_b200', 'csrc', 'fused_shapes_k*.cu')):   # (the baseline unit is hand-tuned)
+        for m in re.finditer(r'^\s*GFDM_SHAPE\((\d+),\s*(\d+),\s*(\d+),\s*(\d+),\s*(\d+),\s*(\d+)', open(path).read(), re.M):
+            M, R1, R2, T, IPT, MINB = (int(x) for x in m.groups())
+            assert chooser.shape(M, R1, R2, T, IPT, MINB) is not None, (M, R1, R2, T, IPT, MINB)
